@@ -1,0 +1,147 @@
+/* ocb.h -- C ABI of the B200-native matching + RANSAC-scoring path (libocb.so).
+ *
+ * The reference (jkflying/opencalibration) has no FFI for this path: it is two static C++ libraries,
+ * oc_match (src/match/CMakeLists.txt:1-6) and oc_model_inliers (src/model_inliers/CMakeLists.txt:1-8),
+ * called from src/pipeline/link_stage.cpp:75-112. The C++ adapters in opencalibration_b200/host/ keep those
+ * C++ signatures (include/opencalibration/match/match_features.hpp:10-16,
+ * include/opencalibration/model_inliers/ransac.hpp:15-20) and reach the GPU only through the entry points
+ * below. Each entry point names the reference code it replaces. Paths are relative to the reference root.
+ *
+ * Conventions
+ *   - plain pointers and sizes; the caller owns every buffer; nothing is retained after a call returns
+ *     (except descriptor sets registered with ocb_register_descriptors, which are copied to the device);
+ *   - every function returning int returns 0 on success or a negative code (-(cudaError_t) for CUDA
+ *     failures, OCB_E_* below otherwise); ocb_last_error() gives the message for the calling thread;
+ *   - there is no CPU fallback: without a usable CUDA device every compute entry point fails;
+ *   - host-buffer entry points are thread-safe and blocking (the reference calls this path concurrently
+ *     from OpenMP workers, src/pipeline/pipeline.cpp:42-49); each calling thread gets its own stream and
+ *     staging buffers on the device selected by ocb_set_device (default: device 0);
+ *   - *_device entry points take device pointers (16-byte aligned) and a cudaStream_t passed as void*,
+ *     enqueue asynchronously and do not synchronise.
+ *
+ * Descriptor rows: one row = the 64-byte memory image of std::bitset<486>
+ * (include/opencalibration/types/feature_2d.hpp:11,15): 8 little-endian uint64 words, bits 486..511 zero.
+ */
+#ifndef OCB_H
+#define OCB_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C"
+{
+#endif
+
+#define OCB_DESCRIPTOR_BITS 486
+#define OCB_ROW_BYTES 64
+#define OCB_ROW_WORDS 8
+#define OCB_DIST_INF 0xFFFFu /* "+infinity": no (second) candidate seen */
+#define OCB_NO_INDEX 0xFFFFFFFFu
+
+#define OCB_E_INVALID (-10001)   /* bad argument (null pointer, misaligned device pointer, size overflow) */
+#define OCB_E_NOT_FOUND (-10002) /* unknown descriptor-set id */
+#define OCB_E_NO_DEVICE (-10003) /* no CUDA device / driver */
+
+    /* Result of the top-2 search for one query row. Replaces the per-query state of the inner loop at
+     * src/match/match_features.cpp:74-93: best_k is the POSITION (in the candidate array as passed) of the
+     * first minimum, best_d / second_d are integer Hamming distances in [0,486]; second_d counts
+     * multiplicity (a later candidate at the same distance as the best becomes the second best, :88-91).
+     * n2 == 0 gives {0, OCB_DIST_INF, OCB_DIST_INF}; n2 == 1 gives second_d == OCB_DIST_INF. */
+    typedef struct ocb_top2
+    {
+        uint32_t best_k;
+        uint16_t best_d;
+        uint16_t second_d;
+    } ocb_top2;
+
+    /* One directed image pair of a batched submission (unit of data parallelism of
+     * src/pipeline/link_stage.cpp:75-112): query set -> candidate set, both registered beforehand. */
+    typedef struct ocb_pair
+    {
+        uint64_t query_set;
+        uint64_t candidate_set;
+    } ocb_pair;
+
+    enum ocb_model_kind
+    {
+        OCB_MODEL_HOMOGRAPHY = 0, /* include/opencalibration/model_inliers/homography_model.hpp:14-34 */
+        OCB_MODEL_ESSENTIAL = 1,  /* .../essential_matrix_model.hpp:15-33 */
+        OCB_MODEL_FUNDAMENTAL = 2 /* .../fundamental_matrix_model.hpp:15-31 */
+    };
+
+    /* ---- lifecycle ------------------------------------------------------------------------------ */
+    int ocb_device_count(void);
+    int ocb_init(int device);       /* idempotent; also selects `device` for the calling thread */
+    int ocb_set_device(int device); /* device used by the calling thread's host-buffer calls */
+    void ocb_shutdown(void);        /* frees cached staging buffers and registered descriptor sets */
+    const char *ocb_last_error(void);
+    const char *ocb_version(void);
+    /* Number of kernels this library has launched since load (all threads). */
+    uint64_t ocb_kernel_launches(void);
+    /* Tuning knobs for experiments ("k1_variant", "k1_items_per_sm", ...). Unknown key: OCB_E_INVALID. */
+    int ocb_set_option(const char *key, int64_t value);
+    int64_t ocb_get_option(const char *key);
+
+    /* ---- K1: Hamming top-2 --------------------------------------------------------------------------
+     * Replaces the loop nest of match_features_subset, src/match/match_features.cpp:71-93, on packed rows
+     * (the reference packs set_2 the same way, :62-66). q: [n1][8] uint64 query rows, c: [n2][8] candidate
+     * rows, out: [n1]. col_best_q (nullable, [n2]): cross-check extension that the reference does not have --
+     * for every candidate the position of the first query at minimum distance (OCB_NO_INDEX if n1 == 0),
+     * computed by a second pass with the roles swapped. The double-precision ratio test (:94) and the
+     * std::sort (:100-101) stay in the C++ adapter so their results are the reference's bit for bit. */
+    int ocb_match_top2(const uint64_t *q, size_t n1, const uint64_t *c, size_t n2, ocb_top2 *out,
+                       uint32_t *col_best_q);
+
+    /* Device-resident variant. d_q, d_c, d_out, d_col_best_q, d_workspace are device pointers;
+     * workspace_bytes >= ocb_match_top2_workspace_bytes(n1, n2, d_col_best_q != NULL). */
+    size_t ocb_match_top2_workspace_bytes(size_t n1, size_t n2, int with_col_best);
+    int ocb_match_top2_device(const void *d_q, size_t n1, const void *d_c, size_t n2, void *d_out,
+                              void *d_col_best_q, void *d_workspace, size_t workspace_bytes, void *stream);
+
+    /* ---- descriptor residency + batched pairs (LinkStage granularity) ---------------------------------
+     * Registers (copies to the calling thread's device) the packed rows of one image's subsampled features,
+     * i.e. set[indices[k]] for the indices spatially_subsample_feature_indices returned
+     * (src/pipeline/link_stage.cpp:63-65,80-81). Re-registering an id replaces it. */
+    int ocb_register_descriptors(uint64_t set_id, const uint64_t *rows, size_t n);
+    int ocb_unregister_descriptors(uint64_t set_id);
+    /* Matches n_pairs pairs in one submission. out receives the ocb_top2 records of pair p at
+     * out[out_offsets[p] .. out_offsets[p] + n_query_rows(p)); out_offsets has n_pairs entries. */
+    int ocb_match_pairs(const ocb_pair *pairs, size_t n_pairs, ocb_top2 *out, const uint64_t *out_offsets);
+
+    /* ---- K2/K3: hypotheses x correspondences MSAC scoring -------------------------------------------------
+     * Replaces the score loop of ransac<Model>, src/model_inliers/ransac.cpp:183-196 (without the SPRT
+     * early exit, which the host driver replays), and Model::evaluate
+     * (src/model_inliers/homography_model.cpp:99-118, essential_matrix_model.cpp:91-110,
+     * fundamental_matrix_model.cpp:89-108), for h hypotheses at once.
+     *   models:  [h][18] doubles: the 3x3 matrix column-major (Eigen::Matrix3d storage) followed by, for the
+     *            homography, homography_inverse; the last 9 are ignored for essential / fundamental.
+     *   corr:    [n][7] doubles = std::vector<correspondence>::data()
+     *            (include/opencalibration/types/correspondence.hpp:8-13).
+     *   order:   nullable [n] permutation: the MSAC sum of each hypothesis is accumulated sequentially in
+     *            this order (ransac.cpp's shuffled eval_order); NULL = index order (evaluate).
+     *   score:   [h] sum of 1-(e/thr)^2 over inliers (e < thr, strict), IEEE double, each operation rounded
+     *            individually (no FMA contraction), summed in `order`.
+     *   count:   [h] number of inliers.
+     *   inlier_bits: nullable [h][ceil(n/32)]: bit (i & 31) of word i/32 set iff correspondence i is an inlier. */
+    int ocb_score_models(int kind, const double *models, size_t h, const double *corr, size_t n, double thr,
+                         const uint32_t *order, double *score, uint32_t *count, uint32_t *inlier_bits);
+    /* Per-correspondence residuals e[i] = Model::error(corr[i]) of ONE model (homography_model.cpp:89-97,
+     * essential_matrix_model.cpp:112-123), index order; used by the host RANSAC driver to replay the SPRT
+     * prefix test (ransac.cpp:197-202) exactly for the rare hypotheses that beat the best score. */
+    int ocb_residuals(int kind, const double *model18, const double *corr, size_t n, double *e);
+
+    /* Device-resident variant of ocb_score_models. d_corr4: [n][4] doubles (x1,y1,x2,y2) = measurement / z,
+     * already in evaluation order; d_pos: nullable [n] uint32 correspondence index of each evaluation
+     * position (for the bit mask); everything else as above but device pointers. */
+    int ocb_score_models_device(int kind, const void *d_models, size_t h, const void *d_corr4, const void *d_pos,
+                                size_t n, double thr, void *d_score, void *d_count, void *d_inlier_bits,
+                                void *stream);
+    /* corr [n][7] (device) -> corr4 [n][4] in `order` (device, nullable) + pos. */
+    int ocb_prepare_correspondences_device(const void *d_corr7, const void *d_order, size_t n, void *d_corr4,
+                                           void *d_pos, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OCB_H */

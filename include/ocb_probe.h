@@ -1,0 +1,34 @@
+/* ocb_probe.h -- diagnostics exported by libocb.so next to the C ABI of ocb.h: issue-rate microbenchmarks
+ * that calibrate the roofline denominators (lane-operations per clock per SM) on the device in use.
+ * Not part of the drop-in boundary. */
+#ifndef OCB_PROBE_H
+#define OCB_PROBE_H
+#ifdef __cplusplus
+extern "C"
+{
+#endif
+    enum ocb_probe_slot
+    {
+        OCB_PROBE_SMS = 0,
+        OCB_PROBE_SM_MHZ,  /* SM clock held during the LOP3 probe (cycles / event time) */
+        OCB_PROBE_POPC,    /* everything below: lane-ops / clk / SM */
+        OCB_PROBE_LOP3,
+        OCB_PROBE_IMAD,
+        OCB_PROBE_IADD,
+        OCB_PROBE_IMNMX,
+        OCB_PROBE_ISETP_SEL,          /* setp+selp pairs */
+        OCB_PROBE_MIX_POPC_LOP3,      /* 2 POPC chains + 6 LOP3 chains: total ops/clk/SM */
+        OCB_PROBE_MIX_POPC_LOP3_IMAD, /* 2 POPC + 4 LOP3 + 2 IMAD chains */
+        OCB_PROBE_DADD,
+        OCB_PROBE_DMUL,
+        OCB_PROBE_DFMA,
+        OCB_PROBE_DDIV,  /* IEEE divisions */
+        OCB_PROBE_DSQRT, /* IEEE square roots (+1 add) */
+        OCB_PROBE_COUNT
+    };
+    /* Runs the probes on the current device; out must hold OCB_PROBE_COUNT doubles. 0 or a negative code. */
+    int ocb_probe_pipes(double *out, int n_out);
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,176 @@
+"""ctypes binding of include/ocb.h (libocb.so). The product path: raises if the CUDA library is missing."""
+import ctypes as C
+import os
+
+import numpy as np
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+
+TOP2_DTYPE = np.dtype([("best_k", np.uint32), ("best_d", np.uint16), ("second_d", np.uint16)])
+PAIR_DTYPE = np.dtype([("query_set", np.uint64), ("candidate_set", np.uint64)])
+DIST_INF = 0xFFFF
+NO_INDEX = 0xFFFFFFFF
+MODEL_HOMOGRAPHY, MODEL_ESSENTIAL, MODEL_FUNDAMENTAL = 0, 1, 2
+
+
+class OcbError(RuntimeError):
+    pass
+
+
+def lib_path():
+    return os.path.join(PKG, "libocb.so")
+
+
+_lib = None
+
+
+def lib():
+    """Load libocb.so (built in-tree by opencalibration_b200.build). No fallback: missing library is an error."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not os.path.exists(path):
+        raise OcbError(f"{path} not found: run `python -m opencalibration_b200.build` (there is no CPU fallback)")
+    L = C.CDLL(path)
+    vp, sz, i32, u64, dbl = C.c_void_p, C.c_size_t, C.c_int, C.c_uint64, C.c_double
+    sigs = {
+        "ocb_device_count": (i32, []),
+        "ocb_init": (i32, [i32]),
+        "ocb_set_device": (i32, [i32]),
+        "ocb_shutdown": (None, []),
+        "ocb_last_error": (C.c_char_p, []),
+        "ocb_version": (C.c_char_p, []),
+        "ocb_kernel_launches": (u64, []),
+        "ocb_set_option": (i32, [C.c_char_p, C.c_int64]),
+        "ocb_get_option": (C.c_int64, [C.c_char_p]),
+        "ocb_match_top2": (i32, [vp, sz, vp, sz, vp, vp]),
+        "ocb_match_top2_workspace_bytes": (sz, [sz, sz, i32]),
+        "ocb_match_top2_device": (i32, [vp, sz, vp, sz, vp, vp, vp, sz, vp]),
+        "ocb_register_descriptors": (i32, [u64, vp, sz]),
+        "ocb_unregister_descriptors": (i32, [u64]),
+        "ocb_match_pairs": (i32, [vp, sz, vp, vp]),
+        "ocb_score_models": (i32, [i32, vp, sz, vp, sz, dbl, vp, vp, vp, vp]),
+        "ocb_residuals": (i32, [i32, vp, vp, sz, vp]),
+        "ocb_score_models_device": (i32, [i32, vp, sz, vp, vp, sz, dbl, vp, vp, vp, vp]),
+        "ocb_prepare_correspondences_device": (i32, [vp, vp, sz, vp, vp, vp]),
+    }
+    for name, (res, args) in sigs.items():
+        f = getattr(L, name)
+        f.restype = res
+        f.argtypes = args
+    # diagnostics (include/ocb_probe.h)
+    if hasattr(L, "ocb_probe_pipes"):
+        L.ocb_probe_pipes.restype = i32
+        L.ocb_probe_pipes.argtypes = [vp, i32]
+    _lib = L
+    return L
+
+
+def exported_symbols():
+    """Names declared in include/ocb.h (used by the CPU test that checks the library exports all of them)."""
+    import re
+    hdr = open(os.path.join(os.path.dirname(PKG), "include", "ocb.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(ocb_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def check(rc):
+    if rc != 0:
+        raise OcbError(f"libocb error {rc}: {lib().ocb_last_error().decode()}")
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _rows(a):
+    a = np.ascontiguousarray(a)
+    if a.dtype != np.uint64:
+        a = a.view(np.uint64)
+    return a.reshape(-1, 8)
+
+
+def init(device=0):
+    check(lib().ocb_init(device))
+
+
+def set_option(key, value):
+    check(lib().ocb_set_option(key.encode(), int(value)))
+
+
+def get_option(key):
+    return int(lib().ocb_get_option(key.encode()))
+
+
+def kernel_launches():
+    return int(lib().ocb_kernel_launches())
+
+
+# ---- K1, host buffers (the call a user of the C ABI makes) ----
+def match_top2(q, c, cross_check=False, out=None, col_out=None):
+    q, c = _rows(q), _rows(c)
+    n1, n2 = len(q), len(c)
+    if out is None:
+        out = np.zeros(n1, TOP2_DTYPE)
+    col = None
+    if cross_check:
+        col = col_out if col_out is not None else np.zeros(n2, np.uint32)
+    check(lib().ocb_match_top2(_ptr(q), n1, _ptr(c), n2, _ptr(out), _ptr(col)))
+    return (out, col) if cross_check else out
+
+
+# ---- K1, device buffers (torch tensors; inputs resident in HBM) ----
+def match_top2_workspace_bytes(n1, n2, cross_check=False):
+    return int(lib().ocb_match_top2_workspace_bytes(n1, n2, int(cross_check)))
+
+
+def match_top2_device(d_q, n1, d_c, n2, d_out, d_col, d_ws, ws_bytes, stream):
+    """All d_* are integer device addresses (tensor.data_ptr()); stream is a cudaStream_t address."""
+    check(lib().ocb_match_top2_device(d_q, n1, d_c, n2, d_out, d_col, d_ws, ws_bytes, stream))
+
+
+# ---- descriptor residency + batched pairs ----
+def register_descriptors(set_id, rows):
+    rows = _rows(rows)
+    check(lib().ocb_register_descriptors(int(set_id), _ptr(rows), len(rows)))
+
+
+def unregister_descriptors(set_id):
+    check(lib().ocb_unregister_descriptors(int(set_id)))
+
+
+def match_pairs(pairs, n_query_rows, out=None):
+    """pairs: [(query_set, candidate_set)]; n_query_rows[p] = rows of pair p's query set. Returns (out, offsets)."""
+    pa = np.zeros(len(pairs), PAIR_DTYPE)
+    for i, (a, b) in enumerate(pairs):
+        pa[i] = (a, b)
+    offs = np.zeros(len(pairs), np.uint64)
+    if len(pairs):
+        offs[1:] = np.cumsum(np.asarray(n_query_rows[:-1], np.uint64))
+    total = int(np.sum(np.asarray(n_query_rows, np.uint64)))
+    if out is None:
+        out = np.zeros(total, TOP2_DTYPE)
+    check(lib().ocb_match_pairs(_ptr(pa), len(pa), _ptr(out), _ptr(offs)))
+    return out, offs
+
+
+# ---- K2 / K3 ----
+def score_models(kind, models, corr, thr, order=None, want_bits=True):
+    models = np.ascontiguousarray(models, np.float64).reshape(-1, 18)
+    corr = np.ascontiguousarray(corr, np.float64).reshape(-1, 7)
+    h, n = len(models), len(corr)
+    score, count = np.zeros(h, np.float64), np.zeros(h, np.uint32)
+    bits = np.zeros((h, (n + 31) // 32), np.uint32) if want_bits else None
+    order = None if order is None else np.ascontiguousarray(order, np.uint32)
+    check(lib().ocb_score_models(kind, _ptr(models), h, _ptr(corr), n, float(thr), _ptr(order), _ptr(score),
+                                 _ptr(count), _ptr(bits)))
+    return score, count, bits
+
+
+def residuals(kind, model18, corr):
+    model18 = np.ascontiguousarray(model18, np.float64).reshape(18)
+    corr = np.ascontiguousarray(corr, np.float64).reshape(-1, 7)
+    e = np.zeros(len(corr), np.float64)
+    check(lib().ocb_residuals(kind, _ptr(model18), _ptr(corr), len(corr), _ptr(e)))
+    return e

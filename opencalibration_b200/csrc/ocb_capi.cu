@@ -1,0 +1,719 @@
+// C-ABI layer of libocb.so (include/ocb.h): per-thread streams + staging, descriptor residency, launches.
+// No CPU fallback anywhere: without a device every compute entry point returns an error.
+#include "ocb_internal.cuh"
+
+#include <algorithm>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+namespace ocb
+{
+
+std::atomic<uint64_t> g_kernel_launches{0};
+
+static thread_local std::string t_last_error;
+void set_last_error(const std::string &msg)
+{
+    t_last_error = msg;
+}
+int fail_cuda(cudaError_t e, const char *what, const char *file, int line)
+{
+    char buf[512];
+    snprintf(buf, sizeof buf, "CUDA error %d (%s) in %s at %s:%d", (int)e, cudaGetErrorString(e), what, file, line);
+    set_last_error(buf);
+    cudaGetLastError(); // clear the sticky-less error state
+    return -(int)e;
+}
+int fail_invalid(const char *what)
+{
+    set_last_error(std::string("invalid argument: ") + what);
+    return OCB_E_INVALID;
+}
+
+Options &options()
+{
+    static Options o;
+    return o;
+}
+
+int sm_count(int device)
+{
+    static std::mutex mu;
+    static std::unordered_map<int, int> cache;
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(device);
+    if (it != cache.end())
+        return it->second;
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || sms <= 0)
+        sms = 148;
+    cache[device] = sms;
+    return sms;
+}
+
+namespace
+{
+
+// grow-only buffers owned by one host thread
+struct Buf
+{
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+struct ThreadCtx
+{
+    int device = 0;
+    bool ready = false;
+    cudaStream_t stream = nullptr;
+    Buf dev, pinned;
+    int ready_device = -1;
+
+    int ensure()
+    {
+        if (ready && ready_device == device)
+        {
+            OCB_CUDA(cudaSetDevice(device));
+            return 0;
+        }
+        release();
+        int n = 0;
+        cudaError_t e = cudaGetDeviceCount(&n);
+        if (e != cudaSuccess || n == 0)
+        {
+            set_last_error("no CUDA device available (libocb has no CPU fallback)");
+            cudaGetLastError();
+            return OCB_E_NO_DEVICE;
+        }
+        if (device < 0 || device >= n)
+            return fail_invalid("device index out of range");
+        OCB_CUDA(cudaSetDevice(device));
+        OCB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        ready = true;
+        ready_device = device;
+        return 0;
+    }
+    int dev_reserve(size_t bytes)
+    {
+        if (bytes <= dev.cap)
+            return 0;
+        if (dev.p)
+        {
+            OCB_CUDA(cudaStreamSynchronize(stream));
+            OCB_CUDA(cudaFree(dev.p));
+            dev.p = nullptr;
+            dev.cap = 0;
+        }
+        const size_t cap = std::max(bytes + bytes / 4, (size_t)1 << 20);
+        OCB_CUDA(cudaMalloc(&dev.p, cap));
+        dev.cap = cap;
+        return 0;
+    }
+    int pinned_reserve(size_t bytes)
+    {
+        if (bytes <= pinned.cap)
+            return 0;
+        if (pinned.p)
+        {
+            OCB_CUDA(cudaStreamSynchronize(stream));
+            OCB_CUDA(cudaFreeHost(pinned.p));
+            pinned.p = nullptr;
+            pinned.cap = 0;
+        }
+        const size_t cap = std::max(bytes + bytes / 4, (size_t)1 << 20);
+        OCB_CUDA(cudaHostAlloc(&pinned.p, cap, cudaHostAllocDefault));
+        pinned.cap = cap;
+        return 0;
+    }
+    void release()
+    {
+        if (ready)
+        {
+            cudaSetDevice(ready_device);
+            if (stream)
+                cudaStreamSynchronize(stream);
+            if (dev.p)
+                cudaFree(dev.p);
+            if (pinned.p)
+                cudaFreeHost(pinned.p);
+            if (stream)
+                cudaStreamDestroy(stream);
+        }
+        dev = Buf();
+        pinned = Buf();
+        stream = nullptr;
+        ready = false;
+        ready_device = -1;
+    }
+    ~ThreadCtx()
+    {
+        // the CUDA runtime may already be gone at thread/process exit; leak rather than crash
+    }
+};
+thread_local ThreadCtx t_ctx;
+
+inline size_t align_up(size_t v, size_t a)
+{
+    return (v + a - 1) / a * a;
+}
+
+// carve regions out of one buffer, 256-byte aligned
+struct Carver
+{
+    size_t off = 0;
+    size_t take(size_t bytes)
+    {
+        const size_t o = off;
+        off = align_up(off + bytes, 256);
+        return o;
+    }
+};
+
+// Is `p` page-locked host memory the copy engines can read directly?
+bool is_pinned_host(const void *p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess)
+    {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+}
+
+// Host -> device through the thread's pinned staging area unless the source is already pinned.
+int upload(ThreadCtx &c, void *d_dst, const void *h_src, size_t bytes, size_t staging_off)
+{
+    if (bytes == 0)
+        return 0;
+    if (is_pinned_host(h_src))
+    {
+        OCB_CUDA(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, c.stream));
+    }
+    else
+    {
+        memcpy(static_cast<char *>(c.pinned.p) + staging_off, h_src, bytes);
+        OCB_CUDA(cudaMemcpyAsync(d_dst, static_cast<char *>(c.pinned.p) + staging_off, bytes, cudaMemcpyHostToDevice,
+                                 c.stream));
+    }
+    return 0;
+}
+
+struct DescSet
+{
+    void *d_rows = nullptr;
+    size_t n = 0;
+    int device = 0;
+};
+std::mutex g_sets_mu;
+std::unordered_map<uint64_t, DescSet> g_sets; // key = set id; one device per id
+
+bool aligned16(const void *p)
+{
+    return (reinterpret_cast<uintptr_t>(p) & 15u) == 0;
+}
+
+} // namespace
+} // namespace ocb
+
+using namespace ocb;
+
+extern "C"
+{
+
+    int ocb_device_count(void)
+    {
+        int n = 0;
+        if (cudaGetDeviceCount(&n) != cudaSuccess)
+        {
+            cudaGetLastError();
+            return 0;
+        }
+        return n;
+    }
+
+    int ocb_init(int device)
+    {
+        t_ctx.device = device;
+        return t_ctx.ensure();
+    }
+
+    int ocb_set_device(int device)
+    {
+        t_ctx.device = device;
+        return 0;
+    }
+
+    void ocb_shutdown(void)
+    {
+        {
+            std::lock_guard<std::mutex> lk(g_sets_mu);
+            for (auto &kv : g_sets)
+            {
+                cudaSetDevice(kv.second.device);
+                cudaFree(kv.second.d_rows);
+            }
+            g_sets.clear();
+        }
+        t_ctx.release();
+    }
+
+    const char *ocb_last_error(void)
+    {
+        return t_last_error.c_str();
+    }
+
+    const char *ocb_version(void)
+    {
+        return "opencalibration_b200 0.1 (sm_100a)";
+    }
+
+    uint64_t ocb_kernel_launches(void)
+    {
+        return g_kernel_launches.load(std::memory_order_relaxed);
+    }
+
+    int ocb_set_option(const char *key, int64_t value)
+    {
+        if (!key)
+            return fail_invalid("key");
+        Options &o = options();
+        if (!strcmp(key, "k1_variant"))
+            o.k1_variant = (int)value;
+        else if (!strcmp(key, "k1_items_per_sm"))
+            o.k1_items_per_sm = (int)value;
+        else if (!strcmp(key, "k2_variant"))
+            o.k2_variant = (int)value;
+        else
+            return fail_invalid("unknown option");
+        return 0;
+    }
+
+    int64_t ocb_get_option(const char *key)
+    {
+        if (!key)
+            return OCB_E_INVALID;
+        Options &o = options();
+        if (!strcmp(key, "k1_variant"))
+            return o.k1_variant;
+        if (!strcmp(key, "k1_items_per_sm"))
+            return o.k1_items_per_sm;
+        if (!strcmp(key, "k2_variant"))
+            return o.k2_variant;
+        if (!strcmp(key, "k1_queries_per_cta"))
+            return k1_queries_per_cta();
+        return OCB_E_INVALID;
+    }
+
+    // ---------------------------------------------------------------------------------------------------
+    // K1
+    // ---------------------------------------------------------------------------------------------------
+    size_t ocb_match_top2_workspace_bytes(size_t n1, size_t n2, int with_col_best)
+    {
+        // worst case: every candidate tile its own split
+        K1Problem pr[2];
+        memset(pr, 0, sizeof pr);
+        pr[0].n_q = (uint32_t)n1, pr[0].n_c = (uint32_t)n2;
+        pr[1].n_q = (uint32_t)n2, pr[1].n_c = (uint32_t)n1;
+        size_t pe[2] = {0, 0};
+        k1_plan(pr, with_col_best ? 2 : 1, pe, 148 * 4);
+        Carver cv;
+        cv.take(pe[0] * sizeof(uint2));
+        if (with_col_best)
+        {
+            cv.take(n2 * sizeof(ocb_top2));
+            cv.take(pe[1] * sizeof(uint2));
+        }
+        return cv.off + 256;
+    }
+
+    int ocb_match_top2_device(const void *d_q, size_t n1, const void *d_c, size_t n2, void *d_out,
+                              void *d_col_best_q, void *d_workspace, size_t workspace_bytes, void *stream)
+    {
+        if (n1 >= 0xFFFFFFFFull || n2 >= 0xFFFFFFFFull)
+            return fail_invalid("n1/n2 must fit in 32 bits");
+        if ((n1 && (!d_q || !d_out)) || (n2 && !d_c))
+            return fail_invalid("null device pointer");
+        if (!aligned16(d_q) || !aligned16(d_c) || (reinterpret_cast<uintptr_t>(d_out) & 7u) ||
+            (reinterpret_cast<uintptr_t>(d_workspace) & 255u))
+            return fail_invalid("device pointers must be 16-byte aligned (workspace 256)");
+        int dev = 0;
+        OCB_CUDA(cudaGetDevice(&dev));
+        const bool col = d_col_best_q != nullptr;
+        K1Problem pr[2];
+        memset(pr, 0, sizeof pr);
+        pr[0].q = static_cast<const uint4 *>(d_q), pr[0].n_q = (uint32_t)n1;
+        pr[0].c = static_cast<const uint4 *>(d_c), pr[0].n_c = (uint32_t)n2;
+        pr[0].out = static_cast<ocb_top2 *>(d_out);
+        pr[1].q = pr[0].c, pr[1].n_q = (uint32_t)n2;
+        pr[1].c = pr[0].q, pr[1].n_c = (uint32_t)n1;
+        size_t pe[2] = {0, 0};
+        const size_t np = col ? 2 : 1;
+        K1Plan plan = k1_plan(pr, np, pe, sm_count(dev));
+        Carver cv;
+        char *ws = static_cast<char *>(d_workspace);
+        const size_t o_p0 = cv.take(pe[0] * sizeof(uint2));
+        size_t o_out1 = 0, o_p1 = 0;
+        if (col)
+        {
+            o_out1 = cv.take(n2 * sizeof(ocb_top2));
+            o_p1 = cv.take(pe[1] * sizeof(uint2));
+        }
+        if (cv.off > workspace_bytes)
+            return fail_invalid("workspace too small");
+        pr[0].partial = reinterpret_cast<uint2 *>(ws + o_p0);
+        if (col)
+        {
+            pr[1].out = reinterpret_cast<ocb_top2 *>(ws + o_out1);
+            pr[1].partial = reinterpret_cast<uint2 *>(ws + o_p1);
+        }
+        cudaStream_t st = static_cast<cudaStream_t>(stream);
+        int rc = k1_launch(nullptr, pr, np, plan, st);
+        if (rc)
+            return rc;
+        if (col && n2)
+        {
+            // col_best_q[j] = best_k of candidate j's own top-2 over the queries (OCB_NO_INDEX when n1 == 0)
+            rc = k1_extract_best(pr[1].out, (uint32_t)n2, n1 == 0, static_cast<uint32_t *>(d_col_best_q), st);
+            if (rc)
+                return rc;
+        }
+        return 0;
+    }
+
+    int ocb_match_top2(const uint64_t *q, size_t n1, const uint64_t *c, size_t n2, ocb_top2 *out, uint32_t *col_best_q)
+    {
+        if (n1 >= 0xFFFFFFFFull || n2 >= 0xFFFFFFFFull)
+            return fail_invalid("n1/n2 must fit in 32 bits");
+        if ((n1 && (!q || !out)) || (n2 && !c))
+            return fail_invalid("null pointer");
+        ThreadCtx &cx = t_ctx;
+        int rc = cx.ensure();
+        if (rc)
+            return rc;
+        if (n1 == 0 && (n2 == 0 || !col_best_q))
+            return 0;
+        const bool col = col_best_q != nullptr;
+        const size_t qb = n1 * OCB_ROW_BYTES, cb = n2 * OCB_ROW_BYTES;
+        const size_t ws_bytes = ocb_match_top2_workspace_bytes(n1, n2, col);
+        Carver cv;
+        const size_t o_q = cv.take(qb), o_c = cv.take(cb), o_out = cv.take(n1 * sizeof(ocb_top2));
+        const size_t o_col = cv.take(col ? n2 * sizeof(uint32_t) : 0);
+        const size_t o_ws = cv.take(ws_bytes);
+        rc = cx.dev_reserve(cv.off);
+        if (rc)
+            return rc;
+        // staging: rows in (when the caller's memory is pageable) and results out
+        Carver sv;
+        const size_t s_q = sv.take(qb), s_c = sv.take(cb), s_out = sv.take(n1 * sizeof(ocb_top2));
+        const size_t s_col = sv.take(col ? n2 * sizeof(uint32_t) : 0);
+        rc = cx.pinned_reserve(sv.off);
+        if (rc)
+            return rc;
+        char *d = static_cast<char *>(cx.dev.p);
+        if ((rc = upload(cx, d + o_q, q, qb, s_q)))
+            return rc;
+        if ((rc = upload(cx, d + o_c, c, cb, s_c)))
+            return rc;
+        rc = ocb_match_top2_device(d + o_q, n1, d + o_c, n2, d + o_out, col ? d + o_col : nullptr, d + o_ws, ws_bytes,
+                                   cx.stream);
+        if (rc)
+            return rc;
+        char *hp = static_cast<char *>(cx.pinned.p);
+        const bool out_pinned = is_pinned_host(out);
+        if (n1)
+            OCB_CUDA(cudaMemcpyAsync(out_pinned ? (void *)out : (void *)(hp + s_out), d + o_out, n1 * sizeof(ocb_top2),
+                                     cudaMemcpyDeviceToHost, cx.stream));
+        const bool col_pinned = col && is_pinned_host(col_best_q);
+        if (col && n2)
+            OCB_CUDA(cudaMemcpyAsync(col_pinned ? (void *)col_best_q : (void *)(hp + s_col), d + o_col,
+                                     n2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, cx.stream));
+        OCB_CUDA(cudaStreamSynchronize(cx.stream));
+        if (n1 && !out_pinned)
+            memcpy(out, hp + s_out, n1 * sizeof(ocb_top2));
+        if (col && n2 && !col_pinned)
+            memcpy(col_best_q, hp + s_col, n2 * sizeof(uint32_t));
+        return 0;
+    }
+
+    // ---------------------------------------------------------------------------------------------------
+    // descriptor residency + batched pairs
+    // ---------------------------------------------------------------------------------------------------
+    int ocb_register_descriptors(uint64_t set_id, const uint64_t *rows, size_t n)
+    {
+        if (n >= 0xFFFFFFFFull)
+            return fail_invalid("n must fit in 32 bits");
+        if (n && !rows)
+            return fail_invalid("rows");
+        ThreadCtx &cx = t_ctx;
+        int rc = cx.ensure();
+        if (rc)
+            return rc;
+        DescSet s;
+        s.n = n;
+        s.device = cx.device;
+        if (n)
+        {
+            OCB_CUDA(cudaMalloc(&s.d_rows, n * OCB_ROW_BYTES));
+            cudaError_t e = cudaMemcpyAsync(s.d_rows, rows, n * OCB_ROW_BYTES, cudaMemcpyHostToDevice, cx.stream);
+            if (e == cudaSuccess)
+                e = cudaStreamSynchronize(cx.stream);
+            if (e != cudaSuccess)
+            {
+                cudaFree(s.d_rows);
+                return fail_cuda(e, "upload descriptor set", __FILE__, __LINE__);
+            }
+        }
+        std::lock_guard<std::mutex> lk(g_sets_mu);
+        auto it = g_sets.find(set_id);
+        if (it != g_sets.end())
+        {
+            cudaSetDevice(it->second.device);
+            cudaFree(it->second.d_rows);
+            cudaSetDevice(cx.device);
+        }
+        g_sets[set_id] = s;
+        return 0;
+    }
+
+    int ocb_unregister_descriptors(uint64_t set_id)
+    {
+        std::lock_guard<std::mutex> lk(g_sets_mu);
+        auto it = g_sets.find(set_id);
+        if (it == g_sets.end())
+        {
+            set_last_error("unknown descriptor set");
+            return OCB_E_NOT_FOUND;
+        }
+        int cur = 0;
+        cudaGetDevice(&cur);
+        cudaSetDevice(it->second.device);
+        cudaFree(it->second.d_rows);
+        cudaSetDevice(cur);
+        g_sets.erase(it);
+        return 0;
+    }
+
+    int ocb_match_pairs(const ocb_pair *pairs, size_t n_pairs, ocb_top2 *out, const uint64_t *out_offsets)
+    {
+        if (n_pairs == 0)
+            return 0;
+        if (!pairs || !out || !out_offsets)
+            return fail_invalid("null pointer");
+        if (n_pairs >= (1ull << 31))
+            return fail_invalid("too many pairs");
+        ThreadCtx &cx = t_ctx;
+        int rc = cx.ensure();
+        if (rc)
+            return rc;
+        std::vector<K1Problem> pr(n_pairs);
+        memset(pr.data(), 0, sizeof(K1Problem) * n_pairs);
+        uint64_t out_end = 0;
+        {
+            std::lock_guard<std::mutex> lk(g_sets_mu);
+            for (size_t p = 0; p < n_pairs; p++)
+            {
+                auto a = g_sets.find(pairs[p].query_set), b = g_sets.find(pairs[p].candidate_set);
+                if (a == g_sets.end() || b == g_sets.end())
+                {
+                    set_last_error("unknown descriptor set in pair list");
+                    return OCB_E_NOT_FOUND;
+                }
+                if (a->second.device != cx.device || b->second.device != cx.device)
+                    return fail_invalid("descriptor set registered on another device");
+                pr[p].q = static_cast<const uint4 *>(a->second.d_rows), pr[p].n_q = (uint32_t)a->second.n;
+                pr[p].c = static_cast<const uint4 *>(b->second.d_rows), pr[p].n_c = (uint32_t)b->second.n;
+                out_end = std::max(out_end, out_offsets[p] + a->second.n);
+            }
+        }
+        std::vector<size_t> pe(n_pairs);
+        K1Plan plan = k1_plan(pr.data(), n_pairs, pe.data(), sm_count(cx.device));
+        if ((uint64_t)plan.total_items >= 0x7FFFFFFFull)
+            return fail_invalid("too many work items for one submission");
+        const size_t table_bytes = sizeof(K1Problem) * n_pairs + sizeof(uint32_t) * (n_pairs + 1);
+        size_t partial_total = 0;
+        for (size_t p = 0; p < n_pairs; p++)
+            partial_total += pe[p];
+        Carver cv;
+        const size_t o_tab = cv.take(table_bytes), o_out = cv.take(out_end * sizeof(ocb_top2));
+        const size_t o_part = cv.take(partial_total * sizeof(uint2));
+        rc = cx.dev_reserve(cv.off);
+        if (rc)
+            return rc;
+        Carver sv;
+        const size_t s_tab = sv.take(table_bytes), s_out = sv.take(out_end * sizeof(ocb_top2));
+        rc = cx.pinned_reserve(sv.off);
+        if (rc)
+            return rc;
+        char *d = static_cast<char *>(cx.dev.p);
+        char *hp = static_cast<char *>(cx.pinned.p);
+        size_t part_off = 0;
+        for (size_t p = 0; p < n_pairs; p++)
+        {
+            pr[p].out = reinterpret_cast<ocb_top2 *>(d + o_out) + out_offsets[p];
+            pr[p].partial = reinterpret_cast<uint2 *>(d + o_part) + part_off;
+            part_off += pe[p];
+        }
+        K1Problem *h_tab = reinterpret_cast<K1Problem *>(hp + s_tab);
+        memcpy(h_tab, pr.data(), sizeof(K1Problem) * n_pairs);
+        k1_merge_begin(pr.data(), n_pairs, reinterpret_cast<uint32_t *>(h_tab + n_pairs));
+        const K1Problem *d_tab = nullptr;
+        if (n_pairs > (size_t)K1_INLINE)
+        {
+            OCB_CUDA(cudaMemcpyAsync(d + o_tab, h_tab, table_bytes, cudaMemcpyHostToDevice, cx.stream));
+            d_tab = reinterpret_cast<const K1Problem *>(d + o_tab);
+        }
+        rc = k1_launch(d_tab, pr.data(), n_pairs, plan, cx.stream);
+        if (rc)
+            return rc;
+        const bool out_pinned = is_pinned_host(out);
+        if (out_end)
+            OCB_CUDA(cudaMemcpyAsync(out_pinned ? (void *)out : (void *)(hp + s_out), d + o_out,
+                                     out_end * sizeof(ocb_top2), cudaMemcpyDeviceToHost, cx.stream));
+        OCB_CUDA(cudaStreamSynchronize(cx.stream));
+        if (out_end && !out_pinned)
+            memcpy(out, hp + s_out, out_end * sizeof(ocb_top2));
+        return 0;
+    }
+
+    // ---------------------------------------------------------------------------------------------------
+    // K2 / K3
+    // ---------------------------------------------------------------------------------------------------
+    int ocb_prepare_correspondences_device(const void *d_corr7, const void *d_order, size_t n, void *d_corr4,
+                                           void *d_pos, void *stream)
+    {
+        if (n >= 0xFFFFFFFFull)
+            return fail_invalid("n must fit in 32 bits");
+        if (n && (!d_corr7 || !d_corr4))
+            return fail_invalid("null device pointer");
+        if (reinterpret_cast<uintptr_t>(d_corr4) & 31u)
+            return fail_invalid("d_corr4 must be 32-byte aligned");
+        return k2_prepare(static_cast<const double *>(d_corr7), static_cast<const uint32_t *>(d_order), n,
+                          static_cast<double *>(d_corr4), static_cast<uint32_t *>(d_pos),
+                          static_cast<cudaStream_t>(stream));
+    }
+
+    int ocb_score_models_device(int kind, const void *d_models, size_t h, const void *d_corr4, const void *d_pos,
+                                size_t n, double thr, void *d_score, void *d_count, void *d_inlier_bits, void *stream)
+    {
+        if (kind < 0 || kind > 2)
+            return fail_invalid("kind");
+        if (n >= 0xFFFFFFFFull || h >= 0xFFFFFFFFull)
+            return fail_invalid("sizes must fit in 32 bits");
+        if (h && (!d_models || !d_score || !d_count || (n && !d_corr4)))
+            return fail_invalid("null device pointer");
+        if (d_inlier_bits && d_pos)
+            return fail_invalid("inlier bits with an evaluation order need scratch: use ocb_score_models");
+        return k2_score(kind, static_cast<const double *>(d_models), h, static_cast<const double *>(d_corr4),
+                        static_cast<const uint32_t *>(d_pos), n, thr, static_cast<double *>(d_score),
+                        static_cast<uint32_t *>(d_count), static_cast<uint32_t *>(d_inlier_bits), nullptr,
+                        static_cast<cudaStream_t>(stream));
+    }
+
+    int ocb_score_models(int kind, const double *models, size_t h, const double *corr, size_t n, double thr,
+                         const uint32_t *order, double *score, uint32_t *count, uint32_t *inlier_bits)
+    {
+        if (kind < 0 || kind > 2)
+            return fail_invalid("kind");
+        if (n >= 0xFFFFFFFFull || h >= 0xFFFFFFFFull)
+            return fail_invalid("sizes must fit in 32 bits");
+        if (h == 0)
+            return 0;
+        if (!models || !score || !count || (n && !corr))
+            return fail_invalid("null pointer");
+        ThreadCtx &cx = t_ctx;
+        int rc = cx.ensure();
+        if (rc)
+            return rc;
+        const size_t words = (n + 31) / 32;
+        const size_t mb = h * 18 * sizeof(double), cb = n * 7 * sizeof(double), ob = order ? n * sizeof(uint32_t) : 0;
+        const size_t bb = inlier_bits ? h * words * sizeof(uint32_t) : 0;
+        Carver cv;
+        const size_t o_m = cv.take(mb), o_c7 = cv.take(cb), o_ord = cv.take(ob), o_c4 = cv.take(n * 32),
+                     o_pos = cv.take(ob), o_sc = cv.take(h * sizeof(double)), o_cnt = cv.take(h * sizeof(uint32_t)),
+                     o_bits = cv.take(bb), o_scr = cv.take(order ? bb : 0);
+        rc = cx.dev_reserve(cv.off);
+        if (rc)
+            return rc;
+        Carver sv;
+        const size_t s_m = sv.take(mb), s_c7 = sv.take(cb), s_ord = sv.take(ob), s_sc = sv.take(h * sizeof(double)),
+                     s_cnt = sv.take(h * sizeof(uint32_t)), s_bits = sv.take(bb);
+        rc = cx.pinned_reserve(sv.off);
+        if (rc)
+            return rc;
+        char *d = static_cast<char *>(cx.dev.p);
+        char *hp = static_cast<char *>(cx.pinned.p);
+        if ((rc = upload(cx, d + o_m, models, mb, s_m)))
+            return rc;
+        if ((rc = upload(cx, d + o_c7, corr, cb, s_c7)))
+            return rc;
+        if (order && (rc = upload(cx, d + o_ord, order, ob, s_ord)))
+            return rc;
+        uint32_t *d_pos = order ? reinterpret_cast<uint32_t *>(d + o_pos) : nullptr;
+        rc = k2_prepare(reinterpret_cast<double *>(d + o_c7), order ? reinterpret_cast<uint32_t *>(d + o_ord) : nullptr,
+                        n, reinterpret_cast<double *>(d + o_c4), d_pos, cx.stream);
+        if (rc)
+            return rc;
+        rc = k2_score(kind, reinterpret_cast<double *>(d + o_m), h, reinterpret_cast<double *>(d + o_c4), d_pos, n, thr,
+                      reinterpret_cast<double *>(d + o_sc), reinterpret_cast<uint32_t *>(d + o_cnt),
+                      inlier_bits ? reinterpret_cast<uint32_t *>(d + o_bits) : nullptr,
+                      reinterpret_cast<uint32_t *>(d + o_scr), cx.stream);
+        if (rc)
+            return rc;
+        OCB_CUDA(cudaMemcpyAsync(hp + s_sc, d + o_sc, h * sizeof(double), cudaMemcpyDeviceToHost, cx.stream));
+        OCB_CUDA(cudaMemcpyAsync(hp + s_cnt, d + o_cnt, h * sizeof(uint32_t), cudaMemcpyDeviceToHost, cx.stream));
+        if (bb)
+            OCB_CUDA(cudaMemcpyAsync(hp + s_bits, d + o_bits, bb, cudaMemcpyDeviceToHost, cx.stream));
+        OCB_CUDA(cudaStreamSynchronize(cx.stream));
+        memcpy(score, hp + s_sc, h * sizeof(double));
+        memcpy(count, hp + s_cnt, h * sizeof(uint32_t));
+        if (bb)
+            memcpy(inlier_bits, hp + s_bits, bb);
+        return 0;
+    }
+
+    int ocb_residuals(int kind, const double *model18, const double *corr, size_t n, double *e)
+    {
+        if (kind < 0 || kind > 2)
+            return fail_invalid("kind");
+        if (n >= 0xFFFFFFFFull)
+            return fail_invalid("n must fit in 32 bits");
+        if (n == 0)
+            return 0;
+        if (!model18 || !corr || !e)
+            return fail_invalid("null pointer");
+        ThreadCtx &cx = t_ctx;
+        int rc = cx.ensure();
+        if (rc)
+            return rc;
+        const size_t cb = n * 7 * sizeof(double), eb = n * sizeof(double);
+        Carver cv;
+        const size_t o_m = cv.take(18 * sizeof(double)), o_c7 = cv.take(cb), o_e = cv.take(eb);
+        rc = cx.dev_reserve(cv.off);
+        if (rc)
+            return rc;
+        Carver sv;
+        const size_t s_m = sv.take(18 * sizeof(double)), s_c7 = sv.take(cb), s_e = sv.take(eb);
+        rc = cx.pinned_reserve(sv.off);
+        if (rc)
+            return rc;
+        char *d = static_cast<char *>(cx.dev.p);
+        char *hp = static_cast<char *>(cx.pinned.p);
+        if ((rc = upload(cx, d + o_m, model18, 18 * sizeof(double), s_m)))
+            return rc;
+        if ((rc = upload(cx, d + o_c7, corr, cb, s_c7)))
+            return rc;
+        rc = k2_residuals(kind, reinterpret_cast<double *>(d + o_m), reinterpret_cast<double *>(d + o_c7), n,
+                          reinterpret_cast<double *>(d + o_e), cx.stream);
+        if (rc)
+            return rc;
+        OCB_CUDA(cudaMemcpyAsync(hp + s_e, d + o_e, eb, cudaMemcpyDeviceToHost, cx.stream));
+        OCB_CUDA(cudaStreamSynchronize(cx.stream));
+        memcpy(e, hp + s_e, eb);
+        return 0;
+    }
+
+} // extern "C"

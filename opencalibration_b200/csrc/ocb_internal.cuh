@@ -1,0 +1,153 @@
+// Internal helpers shared by the kernels and the C-ABI layer of libocb.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+
+#include "../../include/ocb.h"
+
+namespace ocb
+{
+
+// ---- error plumbing ---------------------------------------------------------------------------------
+void set_last_error(const std::string &msg);
+int fail_cuda(cudaError_t e, const char *what, const char *file, int line);
+int fail_invalid(const char *what);
+
+#define OCB_CUDA(call)                                                                                                 \
+    do                                                                                                                 \
+    {                                                                                                                  \
+        cudaError_t e__ = (call);                                                                                      \
+        if (e__ != cudaSuccess)                                                                                        \
+            return ::ocb::fail_cuda(e__, #call, __FILE__, __LINE__);                                                   \
+    } while (0)
+
+extern std::atomic<uint64_t> g_kernel_launches;
+inline void count_launch(uint64_t n = 1)
+{
+    g_kernel_launches.fetch_add(n, std::memory_order_relaxed);
+}
+
+// ---- tuning options -----------------------------------------------------------------------------------
+struct Options
+{
+    int k1_variant = 0;       // 0 = default (see hamming_top2.cu variant table)
+    int k1_items_per_sm = 16; // target work items per SM when splitting the candidate axis
+    int k2_variant = 0;
+};
+Options &options();
+
+int sm_count(int device);
+
+// ---- K1 launch interface (hamming_top2.cu) ----------------------------------------------------------------
+// One (query set, candidate set) problem of a launch. All pointers are device pointers.
+struct K1Problem
+{
+    const uint4 *q;        // [n_q][4] uint4 = 64-byte rows
+    const uint4 *c;        // [n_c][4]
+    ocb_top2 *out;         // [n_q]
+    uint2 *partial;        // [splits][n_q] (m1,m2) keys; used when splits > 1
+    uint32_t n_q, n_c;     //
+    uint32_t q_tiles;      // ceil(n_q / queries per CTA)
+    uint32_t splits;       // candidate-axis splits
+    uint32_t tiles_per_split; // candidate tiles (TILE_C rows) per split
+    uint32_t item_begin;   // index of this problem's first work item in the launch
+};
+
+constexpr int K1_INLINE = 2; // problems that fit in the kernel parameters
+struct K1Inline
+{
+    K1Problem p[K1_INLINE];
+    uint32_t merge_begin[K1_INLINE + 1];
+};
+
+struct K1Plan
+{
+    uint32_t total_items = 0;
+    bool any_split = false;
+};
+// Fills q_tiles / splits / tiles_per_split / item_begin of each problem; returns bytes of partial storage
+// needed per problem through partial_elems[p] (in uint2 elements; 0 when splits == 1).
+K1Plan k1_plan(K1Problem *problems, size_t n, size_t *partial_elems, int sms);
+// Enqueues the top-2 kernel (+ merge kernel when any problem is split) for `n` problems whose table
+// already lives at d_problems (device copy of `problems`).
+int k1_launch(const K1Problem *d_problems, const K1Problem *h_problems, size_t n, const K1Plan &plan,
+              cudaStream_t stream);
+int k1_extract_best(const ocb_top2 *d_top2, uint32_t n, bool empty, uint32_t *d_best, cudaStream_t stream);
+int k1_queries_per_cta();
+// merge_begin[p] = first merge slot of problem p (prefix sum of n_q over split problems), n+1 entries.
+void k1_merge_begin(const K1Problem *problems, size_t n, uint32_t *merge_begin);
+
+// ---- K2/K3 launch interface (score_models.cu) ---------------------------------------------------------------
+int k2_prepare(const double *d_corr7, const uint32_t *d_order, size_t n, double *d_corr4, uint32_t *d_pos,
+               cudaStream_t stream);
+int k2_score(int kind, const double *d_models, size_t h, const double *d_corr4, const uint32_t *d_pos, size_t n,
+             double thr, double *d_score, uint32_t *d_count, uint32_t *d_bits, uint32_t *d_bits_scratch,
+             cudaStream_t stream);
+int k2_residuals(int kind, const double *d_model18, const double *d_corr7, size_t n, double *d_e,
+                 cudaStream_t stream);
+
+// ---- PTX helpers: mbarrier + 1-D bulk (TMA) copies -----------------------------------------------------------
+#if defined(__CUDACC__)
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile("{\n"
+                 ".reg .pred p;\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+                 "selp.u32 %0, 1, 0, p;\n"
+                 "}\n"
+                 : "=r"(ok)
+                 : "r"(smem_u32(bar)), "r"(parity)
+                 : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    while (!mbar_try_wait(bar, parity))
+    {
+    }
+}
+// cp.async.bulk global -> shared::cta, completion signalled on an mbarrier (SASS: UBLKCP).
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ uint32_t lop3_xor3(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ uint32_t lop3_maj(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+#endif
+
+} // namespace ocb

@@ -1,0 +1,225 @@
+"""ctypes binding of the C++ mirror's flat shim (libocb_host.so): the reference's entry points
+(match_features_subset, spatially_subsample_feature_indices, ransac<Model>, Model::fit/fitInliers/evaluate/error,
+assembleInliers) as a Python caller sees them. Everything bulk runs on the GPU through libocb.so; no CPU fallback."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from .capi import OcbError, PKG, lib as _cuda_lib
+
+KIND_H, KIND_E, KIND_F = 0, 1, 2
+MIN_POINTS = {KIND_H: 4, KIND_E: 5, KIND_F: 8}
+
+_u64p = np.ctypeslib.ndpointer(np.uint64, flags="C_CONTIGUOUS")
+_u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
+_f64p = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
+_f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
+_szp = np.ctypeslib.ndpointer(np.uintp, flags="C_CONTIGUOUS")
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    _cuda_lib()  # libocb.so first (also the loud failure when it is missing)
+    path = os.path.join(PKG, "libocb_host.so")
+    if not os.path.exists(path):
+        raise OcbError(f"{path} not found: run `python -m opencalibration_b200.build`")
+    L = C.CDLL(path)
+    sz, i32, dbl, vp = C.c_size_t, C.c_int, C.c_double, C.c_void_p
+    L.ocbh_last_error.restype = C.c_char_p
+    for f in ("ocbh_sizeof_feature_2d", "ocbh_offsetof_descriptor", "ocbh_sizeof_feature_match",
+              "ocbh_sizeof_correspondence", "ocbh_sizeof_feature_match_denormalized"):
+        getattr(L, f).restype = sz
+    L.ocbh_match_features_subset.argtypes = [_u64p, sz, _u64p, sz, _szp, sz, _szp, sz, _szp, _szp, _f64p, vp, _szp]
+    L.ocbh_subsample.argtypes = [_f64p, _f32p, sz, dbl, sz, _szp]
+    L.ocbh_subsample.restype = sz
+    L.ocbh_ransac.argtypes = [i32, _f64p, sz, _f64p, _u8p, _f64p, _szp]
+    L.ocbh_evaluate.argtypes = [i32, _f64p, dbl, _f64p, sz, _u8p, _f64p]
+    L.ocbh_error.argtypes = [i32, _f64p, _f64p]
+    L.ocbh_error.restype = dbl
+    L.ocbh_fit.argtypes = [i32, _f64p, sz, _szp, _f64p]
+    L.ocbh_fit.restype = None
+    L.ocbh_fit_inliers.argtypes = [i32, _f64p, _f64p, sz, _u8p]
+    L.ocbh_fit_inliers.restype = None
+    L.ocbh_check_sample_degeneracy_h.argtypes = [_f64p, sz, _szp]
+    L.ocbh_check_degeneracy_f.argtypes = [_f64p, dbl, _f64p, sz, _u8p]
+    L.ocbh_decompose_essential.argtypes = [_f64p, _f64p]
+    L.ocbh_decompose_essential.restype = None
+    L.ocbh_assemble_inliers.argtypes = [_szp, _szp, _f64p, sz, _u8p, _f64p, sz, _f64p, sz, _f64p, _szp]
+    L.ocbh_assemble_inliers.restype = sz
+    L.ocbh_full_piv_lu_solve.argtypes = [_f64p, i32, i32, _f64p, _f64p]
+    L.ocbh_full_piv_lu_solve.restype = None
+    L.ocbh_invert3.argtypes = [_f64p, _f64p]
+    L.ocbh_invert3.restype = None
+    L.ocbh_jacobi_svd.argtypes = [_f64p, i32, _f64p, _f64p, _f64p]
+    L.ocbh_jacobi_svd.restype = None
+    L.ocbh_jacobi_svd_tall.argtypes = [_f64p, i32, i32, _f64p, _f64p]
+    L.ocbh_jacobi_svd_tall.restype = None
+    L.ocbh_run_parallel_match.argtypes = [_u64p, _u64p, sz, sz, sz, i32, _szp, _f64p]
+    _lib = L
+    return L
+
+
+def _check(rc):
+    if rc != 0:
+        raise OcbError("host mirror: " + lib().ocbh_last_error().decode())
+
+
+def _rows(a):
+    a = np.ascontiguousarray(a)
+    if a.dtype != np.uint64:
+        a = a.view(np.uint64)
+    return a.reshape(-1, 8)
+
+
+def _corr(c):
+    return np.ascontiguousarray(c, np.float64).reshape(-1, 7)
+
+
+def layout():
+    L = lib()
+    return dict(sizeof_feature_2d=L.ocbh_sizeof_feature_2d(), offsetof_descriptor=L.ocbh_offsetof_descriptor(),
+                sizeof_feature_match=L.ocbh_sizeof_feature_match(),
+                sizeof_correspondence=L.ocbh_sizeof_correspondence(),
+                sizeof_feature_match_denormalized=L.ocbh_sizeof_feature_match_denormalized())
+
+
+# ---- src/match ----
+def match_features_subset(desc1, desc2, idx1, idx2, cross_check=False):
+    """-> (feature_index_1, feature_index_2, distance[, mutual]) in the reference's output order."""
+    desc1, desc2 = _rows(desc1), _rows(desc2)
+    idx1 = np.ascontiguousarray(idx1, np.uintp)
+    idx2 = np.ascontiguousarray(idx2, np.uintp)
+    n1 = len(idx1)
+    o1, o2, od = np.zeros(max(n1, 1), np.uintp), np.zeros(max(n1, 1), np.uintp), np.zeros(max(n1, 1), np.float64)
+    mut = np.zeros(max(n1, 1), np.uint8) if cross_check else None
+    n = np.zeros(1, np.uintp)
+    _check(lib().ocbh_match_features_subset(desc1, len(desc1), desc2, len(desc2), idx1, n1, idx2, len(idx2), o1, o2, od,
+                                            None if mut is None else mut.ctypes.data_as(C.c_void_p), n))
+    m = int(n[0])
+    if cross_check:
+        return o1[:m].copy(), o2[:m].copy(), od[:m].copy(), mut[:m].astype(bool)
+    return o1[:m].copy(), o2[:m].copy(), od[:m].copy()
+
+
+def spatially_subsample_feature_indices(xy, strength, spacing, count=0):
+    xy = np.ascontiguousarray(xy, np.float64).reshape(-1, 2)
+    strength = np.ascontiguousarray(strength, np.float32)
+    out = np.zeros(max(len(xy), 1), np.uintp)
+    m = lib().ocbh_subsample(xy, strength, len(xy), float(spacing), int(count), out)
+    return out[:m].copy()
+
+
+# ---- src/model_inliers ----
+def ransac(kind, corr):
+    """-> (score, M18, inliers, stats)"""
+    corr = _corr(corr)
+    M18 = np.full(18, np.nan)
+    inl = np.zeros(max(len(corr), 1), np.uint8)
+    score = np.zeros(1)
+    st = np.zeros(6, np.uintp)
+    _check(lib().ocbh_ransac(kind, corr, len(corr), M18, inl, score, st))
+    stats = dict(iterations=int(st[0]), improvements=int(st[1]), rejected=int(st[2]), degenerate=int(st[3]),
+                 scored=int(st[4]), gpu_calls=int(st[5]))
+    return float(score[0]), M18, inl[:len(corr)].astype(bool), stats
+
+
+def evaluate(kind, M18, corr, thr=0.0):
+    corr = _corr(corr)
+    inl = np.zeros(max(len(corr), 1), np.uint8)
+    score = np.zeros(1)
+    _check(lib().ocbh_evaluate(kind, np.ascontiguousarray(M18, np.float64), float(thr), corr, len(corr), inl, score))
+    return float(score[0]), inl[:len(corr)].astype(bool)
+
+
+def error(kind, M18, corr7):
+    return lib().ocbh_error(kind, np.ascontiguousarray(M18, np.float64), np.ascontiguousarray(corr7, np.float64))
+
+
+def fit(kind, corr, sample):
+    corr = _corr(corr)
+    M18 = np.full(18, np.nan)
+    lib().ocbh_fit(kind, corr, len(corr), np.ascontiguousarray(sample, np.uintp), M18)
+    return M18
+
+
+def fit_inliers(kind, M18, corr, inliers):
+    corr = _corr(corr)
+    M18 = np.array(M18, np.float64)
+    lib().ocbh_fit_inliers(kind, M18, corr, len(corr), np.ascontiguousarray(inliers, np.uint8))
+    return M18
+
+
+def check_sample_degeneracy_h(corr, sample):
+    corr = _corr(corr)
+    return bool(lib().ocbh_check_sample_degeneracy_h(corr, len(corr), np.ascontiguousarray(sample, np.uintp)))
+
+
+def check_degeneracy_f(M18, corr, inliers, thr=0.01):
+    corr = _corr(corr)
+    M18 = np.array(M18, np.float64)
+    inl = np.ascontiguousarray(inliers, np.uint8).copy()
+    _check(lib().ocbh_check_degeneracy_f(M18, float(thr), corr, len(corr), inl))
+    return M18, inl.astype(bool)
+
+
+def decompose_essential(M18):
+    out = np.zeros(28)
+    lib().ocbh_decompose_essential(np.ascontiguousarray(M18, np.float64), out)
+    return out.reshape(4, 7)
+
+
+def assemble_inliers(m_i1, m_i2, m_dist, inliers, xy1, xy2):
+    m_i1 = np.ascontiguousarray(m_i1, np.uintp)
+    m_i2 = np.ascontiguousarray(m_i2, np.uintp)
+    m_dist = np.ascontiguousarray(m_dist, np.float64)
+    xy1 = np.ascontiguousarray(xy1, np.float64).reshape(-1, 2)
+    xy2 = np.ascontiguousarray(xy2, np.float64).reshape(-1, 2)
+    n = len(m_i1)
+    px, ix = np.zeros((max(n, 1), 4)), np.zeros((max(n, 1), 3), np.uintp)
+    m = lib().ocbh_assemble_inliers(m_i1, m_i2, m_dist, n, np.ascontiguousarray(inliers, np.uint8), xy1, len(xy1), xy2,
+                                    len(xy2), px, ix)
+    return px[:m].copy(), ix[:m].copy()
+
+
+# ---- host linear algebra (numpy in/out, row-major views) ----
+def full_piv_lu_solve(A, b):
+    A = np.asarray(A, np.float64)
+    x = np.zeros(A.shape[1])
+    lib().ocbh_full_piv_lu_solve(np.ascontiguousarray(A.T).ravel(), A.shape[0], A.shape[1],
+                                 np.ascontiguousarray(b, np.float64), x)
+    return x
+
+
+def invert3(M):
+    out = np.zeros(9)
+    lib().ocbh_invert3(np.ascontiguousarray(np.asarray(M, np.float64).T).ravel(), out)
+    return out.reshape(3, 3).T.copy()
+
+
+def jacobi_svd(A):
+    A = np.asarray(A, np.float64)
+    n = A.shape[0]
+    U, S, V = np.zeros(n * n), np.zeros(n), np.zeros(n * n)
+    lib().ocbh_jacobi_svd(np.ascontiguousarray(A.T).ravel(), n, U, S, V)
+    return U.reshape(n, n).T.copy(), S, V.reshape(n, n).T.copy()
+
+
+def jacobi_svd_tall(A):
+    A = np.asarray(A, np.float64)
+    r, c = A.shape
+    S, V = np.zeros(c), np.zeros(c * c)
+    lib().ocbh_jacobi_svd_tall(np.ascontiguousarray(A.T).ravel(), r, c, S, V)
+    return S, V.reshape(c, c).T.copy()
+
+
+def run_parallel_match(q, c, n_pairs, n1, n2, threads=0):
+    """The reference's run_parallel shape: one match_features_subset closure per pair on `threads` OpenMP workers."""
+    q, c = _rows(q), _rows(c)
+    nm, secs = np.zeros(1, np.uintp), np.zeros(1)
+    _check(lib().ocbh_run_parallel_match(q, c, n_pairs, n1, n2, threads, nm, secs))
+    return float(secs[0]), int(nm[0])

@@ -1,0 +1,348 @@
+// Flat C entry points over the C++ mirror, for ctypes-driven tests and bench.py (opencalibration_b200/host.py).
+// They build the reference-typed arguments (std::vector<feature_2d>, std::vector<correspondence>, model structs),
+// call the mirror exactly as src/pipeline/link_stage.cpp:80-93 would, and flatten the results.
+#include "models_detail.hpp"
+
+#include <chrono>
+#include <cstring>
+#include <omp.h>
+#include <stdexcept>
+#include <string>
+
+using namespace opencalibration;
+
+namespace
+{
+thread_local std::string t_err;
+
+std::vector<feature_2d> make_features(const double *xy, const float *strength, const uint64_t *desc, size_t n)
+{
+    std::vector<feature_2d> f(n);
+    for (size_t i = 0; i < n; i++)
+    {
+        if (xy)
+            f[i].location = Eigen::Vector2d(xy[2 * i], xy[2 * i + 1]);
+        if (strength)
+            f[i].strength = strength[i];
+        if (desc)
+            std::memcpy(static_cast<void *>(&f[i].descriptor), desc + 8 * i, 64);
+    }
+    return f;
+}
+std::vector<correspondence> make_corr(const double *corr, size_t n)
+{
+    std::vector<correspondence> c(n);
+    if (n)
+        std::memcpy(static_cast<void *>(c.data()), corr, n * sizeof(correspondence));
+    return c;
+}
+std::vector<bool> make_flags(const uint8_t *f, size_t n)
+{
+    std::vector<bool> v(n);
+    for (size_t i = 0; i < n; i++)
+        v[i] = f[i] != 0;
+    return v;
+}
+void load(homography_model &m, const double *M18)
+{
+    std::memcpy(m.homography.data(), M18, 72);
+    std::memcpy(m.homography_inverse.data(), M18 + 9, 72);
+}
+void load(essential_matrix_model &m, const double *M18)
+{
+    std::memcpy(m.essential_matrix.data(), M18, 72);
+}
+void load(fundamental_matrix_model &m, const double *M18)
+{
+    std::memcpy(m.fundamental_matrix.data(), M18, 72);
+}
+template <typename M> void store(const M &m, double *M18)
+{
+    ocb_host::detail::pack_model(m, M18);
+}
+
+// run f on a freshly built model of the requested kind
+template <typename F> auto with_model(int kind, const double *M18, double thr, F &&f)
+{
+    if (kind == OCB_MODEL_HOMOGRAPHY)
+    {
+        homography_model m;
+        if (M18)
+            load(m, M18);
+        if (thr > 0)
+            m.inlier_threshold = thr;
+        return f(m);
+    }
+    if (kind == OCB_MODEL_ESSENTIAL)
+    {
+        essential_matrix_model m;
+        if (M18)
+            load(m, M18);
+        if (thr > 0)
+            m.inlier_threshold = thr;
+        return f(m);
+    }
+    fundamental_matrix_model m;
+    if (M18)
+        load(m, M18);
+    if (thr > 0)
+        m.inlier_threshold = thr;
+    return f(m);
+}
+
+template <typename F> int guarded(F &&f)
+{
+    try
+    {
+        f();
+        return 0;
+    }
+    catch (const std::exception &e)
+    {
+        t_err = e.what();
+        return -1;
+    }
+}
+} // namespace
+
+extern "C"
+{
+    const char *ocbh_last_error() { return t_err.c_str(); }
+    size_t ocbh_sizeof_feature_2d() { return sizeof(feature_2d); }
+    size_t ocbh_offsetof_descriptor() { return offsetof(feature_2d, descriptor); }
+    size_t ocbh_sizeof_feature_match() { return sizeof(feature_match); }
+    size_t ocbh_sizeof_correspondence() { return sizeof(correspondence); }
+    size_t ocbh_sizeof_feature_match_denormalized() { return sizeof(feature_match_denormalized); }
+
+    // ---- src/match ------------------------------------------------------------------------------------
+    // n_out receives the number of matches; out_* hold up to n1 entries; mutual nullable (cross-check flags)
+    int ocbh_match_features_subset(const uint64_t *desc1, size_t nf1, const uint64_t *desc2, size_t nf2,
+                                   const size_t *idx1, size_t n1, const size_t *idx2, size_t n2, size_t *out_i1,
+                                   size_t *out_i2, double *out_dist, uint8_t *mutual, size_t *n_out)
+    {
+        return guarded([&] {
+            const std::vector<feature_2d> f1 = make_features(nullptr, nullptr, desc1, nf1);
+            const std::vector<feature_2d> f2 = make_features(nullptr, nullptr, desc2, nf2);
+            const std::vector<size_t> i1(idx1, idx1 + n1), i2(idx2, idx2 + n2);
+            std::vector<bool> mut;
+            const std::vector<feature_match> r = mutual ? ocb_host::match_features_subset_cross_checked(f1, f2, i1, i2, mut)
+                                                        : match_features_subset(f1, f2, i1, i2);
+            for (size_t i = 0; i < r.size(); i++)
+            {
+                out_i1[i] = r[i].feature_index_1;
+                out_i2[i] = r[i].feature_index_2;
+                out_dist[i] = r[i].distance;
+                if (mutual)
+                    mutual[i] = mut[i];
+            }
+            *n_out = r.size();
+        });
+    }
+
+    size_t ocbh_subsample(const double *xy, const float *strength, size_t n, double spacing, size_t count,
+                          size_t *out_idx)
+    {
+        const std::vector<feature_2d> f = make_features(xy, strength, nullptr, n);
+        const std::vector<size_t> r = spatially_subsample_feature_indices(f, spacing, count);
+        std::memcpy(out_idx, r.data(), r.size() * sizeof(size_t));
+        return r.size();
+    }
+
+    // ---- src/model_inliers ------------------------------------------------------------------------------
+    int ocbh_ransac(int kind, const double *corr, size_t n, double *M18, uint8_t *inliers, double *score,
+                    size_t *stats6)
+    {
+        return guarded([&] {
+            const std::vector<correspondence> c = make_corr(corr, n);
+            std::vector<bool> inl;
+            *score = with_model(kind, nullptr, 0, [&](auto &m) {
+                const double s = ransac(c, m, inl);
+                store(m, M18);
+                return s;
+            });
+            for (size_t i = 0; i < inl.size(); i++)
+                inliers[i] = inl[i];
+            if (stats6)
+            {
+                const ocb_host::RansacStats st = ocb_host::last_ransac_stats();
+                stats6[0] = st.iterations, stats6[1] = st.improvements, stats6[2] = st.rejected;
+                stats6[3] = st.degenerate, stats6[4] = st.scored, stats6[5] = st.gpu_calls;
+            }
+        });
+    }
+
+    int ocbh_evaluate(int kind, const double *M18, double thr, const double *corr, size_t n, uint8_t *inliers,
+                      double *score)
+    {
+        return guarded([&] {
+            const std::vector<correspondence> c = make_corr(corr, n);
+            std::vector<bool> inl;
+            *score = with_model(kind, M18, thr, [&](auto &m) { return m.evaluate(c, inl); });
+            for (size_t i = 0; i < inl.size(); i++)
+                inliers[i] = inl[i];
+        });
+    }
+
+    double ocbh_error(int kind, const double *M18, const double *corr7)
+    {
+        correspondence c;
+        std::memcpy(static_cast<void *>(&c), corr7, sizeof c);
+        return with_model(kind, M18, 0, [&](auto &m) { return m.error(c); });
+    }
+
+    void ocbh_fit(int kind, const double *corr, size_t n, const size_t *sample, double *M18)
+    {
+        const std::vector<correspondence> c = make_corr(corr, n);
+        with_model(kind, nullptr, 0, [&](auto &m) {
+            using M = std::decay_t<decltype(m)>;
+            std::array<size_t, M::MINIMUM_POINTS> s;
+            for (size_t i = 0; i < M::MINIMUM_POINTS; i++)
+                s[i] = sample[i];
+            m.fit(c, s);
+            store(m, M18);
+            return 0;
+        });
+    }
+
+    void ocbh_fit_inliers(int kind, double *M18, const double *corr, size_t n, const uint8_t *inliers)
+    {
+        const std::vector<correspondence> c = make_corr(corr, n);
+        const std::vector<bool> inl = make_flags(inliers, n);
+        with_model(kind, M18, 0, [&](auto &m) {
+            m.fitInliers(c, inl);
+            store(m, M18);
+            return 0;
+        });
+    }
+
+    int ocbh_check_sample_degeneracy_h(const double *corr, size_t n, const size_t *sample)
+    {
+        const std::vector<correspondence> c = make_corr(corr, n);
+        return homography_model::checkSampleDegeneracy(c, {sample[0], sample[1], sample[2], sample[3]}) ? 1 : 0;
+    }
+
+    int ocbh_check_degeneracy_f(double *M18, double thr, const double *corr, size_t n, uint8_t *inliers)
+    {
+        return guarded([&] {
+            const std::vector<correspondence> c = make_corr(corr, n);
+            std::vector<bool> inl = make_flags(inliers, n);
+            fundamental_matrix_model m;
+            load(m, M18);
+            if (thr > 0)
+                m.inlier_threshold = thr;
+            m.checkDegeneracy(c, inl);
+            store(m, M18);
+            for (size_t i = 0; i < n; i++)
+                inliers[i] = inl[i];
+        });
+    }
+
+    // essential_matrix_model::decompose -> 4 x (qx,qy,qz,qw, tx,ty,tz)
+    void ocbh_decompose_essential(const double *M18, double *poses28)
+    {
+        essential_matrix_model m;
+        load(m, M18);
+        std::array<decomposed_pose, 4> poses;
+        m.decompose({}, {}, poses);
+        for (int i = 0; i < 4; i++)
+        {
+            for (int k = 0; k < 4; k++)
+                poses28[7 * i + k] = poses[i].orientation.coeffs()[k];
+            for (int k = 0; k < 3; k++)
+                poses28[7 * i + 4 + k] = poses[i].position[k];
+        }
+    }
+
+    // assembleInliers -> rows of (pixel_1.x, pixel_1.y, pixel_2.x, pixel_2.y) + (idx1, idx2, match_index)
+    size_t ocbh_assemble_inliers(const size_t *m_i1, const size_t *m_i2, const double *m_dist, size_t n_matches,
+                                 const uint8_t *inliers, const double *xy1, size_t nf1, const double *xy2, size_t nf2,
+                                 double *out_pixels4, size_t *out_idx3)
+    {
+        std::vector<feature_match> matches(n_matches);
+        for (size_t i = 0; i < n_matches; i++)
+            matches[i] = feature_match{m_i1[i], m_i2[i], m_dist[i]};
+        const std::vector<feature_2d> f1 = make_features(xy1, nullptr, nullptr, nf1);
+        const std::vector<feature_2d> f2 = make_features(xy2, nullptr, nullptr, nf2);
+        std::vector<feature_match_denormalized> list;
+        assembleInliers(matches, make_flags(inliers, n_matches), f1, f2, list);
+        for (size_t i = 0; i < list.size(); i++)
+        {
+            out_pixels4[4 * i + 0] = list[i].pixel_1.x(), out_pixels4[4 * i + 1] = list[i].pixel_1.y();
+            out_pixels4[4 * i + 2] = list[i].pixel_2.x(), out_pixels4[4 * i + 3] = list[i].pixel_2.y();
+            out_idx3[3 * i + 0] = list[i].feature_index_1, out_idx3[3 * i + 1] = list[i].feature_index_2;
+            out_idx3[3 * i + 2] = list[i].match_index;
+        }
+        return list.size();
+    }
+
+    // ---- linear algebra (host only) ------------------------------------------------------------------------
+    void ocbh_full_piv_lu_solve(const double *A_colmajor, int rows, int cols, const double *b, double *x)
+    {
+        ocb_host::linalg::ColMat A(rows, cols);
+        std::memcpy(A.a.data(), A_colmajor, sizeof(double) * rows * cols);
+        const std::vector<double> r = ocb_host::linalg::full_piv_lu_solve(A, std::vector<double>(b, b + rows));
+        std::memcpy(x, r.data(), sizeof(double) * cols);
+    }
+    void ocbh_invert3(const double *m, double *out) { ocb_host::linalg::invert3(m, out); }
+    void ocbh_jacobi_svd(const double *A_colmajor, int n, double *U, double *S, double *V)
+    {
+        ocb_host::linalg::ColMat A(n, n);
+        std::memcpy(A.a.data(), A_colmajor, sizeof(double) * n * n);
+        const ocb_host::linalg::Svd s = ocb_host::linalg::jacobi_svd(A, true, true);
+        std::memcpy(U, s.U.a.data(), sizeof(double) * n * n);
+        std::memcpy(V, s.V.a.data(), sizeof(double) * n * n);
+        std::memcpy(S, s.sigma.data(), sizeof(double) * n);
+    }
+    void ocbh_jacobi_svd_tall(const double *A_colmajor, int rows, int cols, double *S, double *V)
+    {
+        ocb_host::linalg::ColMat A(rows, cols);
+        std::memcpy(A.a.data(), A_colmajor, sizeof(double) * rows * cols);
+        const ocb_host::linalg::Svd s = ocb_host::linalg::jacobi_svd_tall(A);
+        std::memcpy(V, s.V.a.data(), sizeof(double) * cols * cols);
+        std::memcpy(S, s.sigma.data(), sizeof(double) * cols);
+    }
+
+    // ---- the reference's run_parallel shape (src/pipeline/pipeline.cpp:42-49): one closure per pair executed by
+    // `threads` OpenMP workers, each closure = match_features_subset on its pair (link_stage.cpp:83-84). Every
+    // worker drives its own CUDA stream through the thread-safe C ABI. Returns wall seconds.
+    int ocbh_run_parallel_match(const uint64_t *q, const uint64_t *c, size_t n_pairs, size_t n1, size_t n2, int threads,
+                                size_t *n_matches, double *seconds)
+    {
+        if (threads <= 0)
+            threads = omp_get_num_procs();
+        std::vector<std::vector<feature_2d>> fq(n_pairs), fc(n_pairs);
+        for (size_t p = 0; p < n_pairs; p++)
+        {
+            fq[p] = make_features(nullptr, nullptr, q + p * n1 * 8, n1);
+            fc[p] = make_features(nullptr, nullptr, c + p * n2 * 8, n2);
+        }
+        std::vector<size_t> idx1(n1), idx2(n2);
+        for (size_t i = 0; i < n1; i++)
+            idx1[i] = i;
+        for (size_t i = 0; i < n2; i++)
+            idx2[i] = i;
+        size_t total = 0;
+        int failed = 0;
+        const auto t0 = std::chrono::steady_clock::now();
+#pragma omp parallel for schedule(dynamic, 1) num_threads(threads) reduction(+ : total)
+        for (size_t p = 0; p < n_pairs; p++)
+        {
+            try
+            {
+                total += match_features_subset(fq[p], fc[p], idx1, idx2).size();
+            }
+            catch (const std::exception &e)
+            {
+#pragma omp critical
+                {
+                    t_err = e.what();
+                    failed = 1;
+                }
+            }
+        }
+        const auto t1 = std::chrono::steady_clock::now();
+        *n_matches = total;
+        *seconds = std::chrono::duration<double>(t1 - t0).count();
+        return failed ? -1 : 0;
+    }
+}

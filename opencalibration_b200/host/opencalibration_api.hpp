@@ -1,0 +1,50 @@
+// The reference's C++ entry points for the matching + RANSAC path, unchanged in name, namespace, signature,
+// ownership and degenerate-input behaviour, implemented on top of the C ABI of include/ocb.h (libocb.so).
+//   include/opencalibration/match/match_features.hpp:10-16
+//   include/opencalibration/model_inliers/ransac.hpp:15-20
+// Error convention: the reference has none (no exceptions, no status codes). Here a failing GPU call throws
+// std::runtime_error carrying ocb_last_error(); there is no CPU fallback.
+#pragma once
+#include "reference_types.hpp"
+
+#include <vector>
+
+namespace opencalibration
+{
+std::vector<size_t> spatially_subsample_feature_indices(const std::vector<feature_2d> &features, double spacing_pixels,
+                                                        size_t count = 0);
+
+std::vector<feature_match> match_features_subset(const std::vector<feature_2d> &set_1,
+                                                 const std::vector<feature_2d> &set_2,
+                                                 const std::vector<size_t> &indices_1,
+                                                 const std::vector<size_t> &indices_2);
+
+template <typename Model>
+double ransac(const std::vector<correspondence> &matches, Model &model, std::vector<bool> &inliers);
+
+void assembleInliers(const std::vector<feature_match> &matches, const std::vector<bool> &inliers,
+                     const std::vector<feature_2d> &source_features, const std::vector<feature_2d> &dest_features,
+                     std::vector<feature_match_denormalized> &inlier_list);
+} // namespace opencalibration
+
+// Extensions that the reference does not have (kept out of its namespace).
+namespace ocb_host
+{
+// match_features_subset + mutual-nearest-neighbour flag per returned match (cross-check): flag[m] is true iff
+// the best query of match m's candidate (first minimum over indices_1 in order) is match m's query.
+std::vector<opencalibration::feature_match> match_features_subset_cross_checked(
+    const std::vector<opencalibration::feature_2d> &set_1, const std::vector<opencalibration::feature_2d> &set_2,
+    const std::vector<size_t> &indices_1, const std::vector<size_t> &indices_2, std::vector<bool> &mutual);
+
+// Counters of the last ransac() call on this thread (for tests: how the batched replay went).
+struct RansacStats
+{
+    size_t iterations = 0;    // value of the reference's loop counter at exit
+    size_t improvements = 0;  // times score > best_score
+    size_t rejected = 0;      // SPRT rejections replayed (only improvers are replayed)
+    size_t degenerate = 0;    // checkSampleDegeneracy skips among the executed iterations
+    size_t scored = 0;        // hypotheses scored on the GPU (>= iterations - degenerate: batches overshoot)
+    size_t gpu_calls = 0;
+};
+RansacStats last_ransac_stats();
+} // namespace ocb_host

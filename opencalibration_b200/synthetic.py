@@ -1,0 +1,114 @@
+"""Synthetic inputs of the shapes BASELINE.json names (descriptor sets, correspondence scenes, image grids).
+
+Pure numpy, seeded; used by bench.py and the tests. Nothing here touches the oracle or the reference.
+"""
+import numpy as np
+
+DESCRIPTOR_BITS = 486
+ROW_WORDS = 8
+
+
+def random_descriptors(n, rng):
+    """n rows of 486 iid Bernoulli(1/2) bits in the 64-byte std::bitset<486> image (bits 486..511 zero)."""
+    rows = rng.integers(0, 1 << 63, size=(n, ROW_WORDS), dtype=np.uint64) << np.uint64(1)
+    rows |= rng.integers(0, 2, size=(n, ROW_WORDS), dtype=np.uint64)
+    rows[:, 7] &= np.uint64((1 << (DESCRIPTOR_BITS - 7 * 64)) - 1)
+    return rows
+
+
+def flip_bits(rows, p, rng):
+    """Flip each of the 486 descriptor bits with probability p."""
+    bits = np.unpackbits(np.ascontiguousarray(rows).view(np.uint8).reshape(len(rows), 64), axis=1, bitorder="little")
+    flips = (rng.random((len(rows), 512)) < p).astype(np.uint8)
+    flips[:, DESCRIPTOR_BITS:] = 0
+    bits ^= flips
+    return np.packbits(bits, axis=1, bitorder="little").view(np.uint64).reshape(len(rows), ROW_WORDS).copy()
+
+
+def config2_pair(n1=10000, n2=10000, seed=1, match_fraction=0.5, noise=0.08):
+    """set A random; set B = noisy copies of a permutation of A for the first half (so the ratio
+    test passes for a controlled subset and there are genuine ties), fresh random rows for the rest."""
+    rng = np.random.default_rng(seed)
+    a = random_descriptors(n1, rng)
+    b = random_descriptors(n2, rng)
+    m = int(min(n1, n2) * match_fraction)
+    perm = rng.permutation(n1)[:m]
+    b[:m] = flip_bits(a[perm], noise, rng)
+    return a, b
+
+
+def homography_scene(n_inliers, n_outliers, seed=42, noise=0.0):
+    """Correspondences [n][7] (unit-depth rays + quality 0) under a fixed ground-truth homography."""
+    rng = np.random.default_rng(seed)
+    c, s = np.cos(0.1), np.sin(0.1)
+    H = np.array([[c, -s, 0.005], [s, c, -0.003], [0, 0, 1.0]])
+    p1 = np.concatenate([rng.uniform(-1, 1, (n_inliers, 2)), np.ones((n_inliers, 1))], axis=1)
+    p2 = p1 @ H.T
+    p2 /= p2[:, 2:3]
+    if noise:
+        p2[:, :2] += rng.normal(0, noise, (n_inliers, 2))
+    o1 = np.concatenate([rng.uniform(-2, 2, (n_outliers, 2)), np.ones((n_outliers, 1))], axis=1)
+    o2 = np.concatenate([rng.uniform(-2, 2, (n_outliers, 2)), np.ones((n_outliers, 1))], axis=1)
+    corr = np.zeros((n_inliers + n_outliers, 7))
+    corr[:n_inliers, 0:3], corr[:n_inliers, 3:6] = p1, p2
+    corr[n_inliers:, 0:3], corr[n_inliers:, 3:6] = o1, o2
+    return corr, H
+
+
+def random_models(kind, h, seed=3, base=None):
+    """h random 3x3 models as [h][18] (matrix column-major + inverse for the homography)."""
+    rng = np.random.default_rng(seed)
+    out = np.zeros((h, 18))
+    for i in range(h):
+        if kind == 0:
+            M = (np.eye(3) if base is None else base) + rng.normal(0, 0.02, (3, 3))
+            M /= M[2, 2]
+            out[i, :9] = M.T.ravel()
+            out[i, 9:] = np.linalg.inv(M).T.ravel()
+        else:
+            M = rng.normal(0, 1, (3, 3))
+            out[i, :9] = M.T.ravel()
+    return out
+
+
+def grid_survey(rows, cols, n_desc, seed=7, k_nn=10, noise=0.08, overlap=0.6):
+    """a rows x cols grid of camera positions; every image holds n_desc descriptors drawn from a
+    shared pool of world points by footprint overlap (+ bit noise) so neighbours genuinely match; directed pairs =
+    k_nn nearest in position minus self (mirrors src/pipeline/link_stage.cpp:26-34). Returns (list of descriptor
+    arrays, positions, pairs)."""
+    rng = np.random.default_rng(seed)
+    n_img = rows * cols
+    pos = np.stack(np.meshgrid(np.arange(cols, dtype=np.float64), np.arange(rows, dtype=np.float64)), -1).reshape(-1, 2)
+    # world points live on a lattice of cells; an image sees the cells within its footprint
+    per_cell = max(1, int(n_desc * (1 - overlap) ** 2 / 1.0))
+    foot = 1.0 / (1 - overlap)  # footprint width in grid units
+    half = foot / 2
+    cell_cache = {}
+
+    def cell_points(cx, cy):
+        key = (cx, cy)
+        if key not in cell_cache:
+            r = np.random.default_rng([seed, cx + 1000, cy + 1000])
+            cell_cache[key] = random_descriptors(per_cell, r)
+        return cell_cache[key]
+
+    images = []
+    for i in range(n_img):
+        x, y = pos[i]
+        cells = [(cx, cy) for cx in range(int(np.floor(x - half)), int(np.ceil(x + half)))
+                 for cy in range(int(np.floor(y - half)), int(np.ceil(y + half)))]
+        pool = np.concatenate([cell_points(cx, cy) for cx, cy in cells])
+        if len(pool) >= n_desc:
+            sel = rng.permutation(len(pool))[:n_desc]
+            d = pool[sel]
+        else:
+            d = np.concatenate([pool, random_descriptors(n_desc - len(pool), rng)])
+        images.append(flip_bits(d, noise, rng))
+    pairs = []
+    for i in range(n_img):
+        d2 = ((pos - pos[i]) ** 2).sum(1)
+        nn = np.argsort(d2, kind="stable")[:k_nn]
+        for j in nn:
+            if j != i:
+                pairs.append((i, int(j)))
+    return images, pos, pairs
