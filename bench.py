@@ -1,0 +1,281 @@
+#!/usr/bin/env python
+"""Headline benchmark: Hamming comparisons/s of the matching hot path (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2]
+
+Workload at every N = BASELINE.json configs[1]: one synthetic pair of 10 000 x 10 000 512-bit descriptors per GPU,
+top-2 search + ratio test + cross-check. One "step" = one pass of the hot path over that pair: the forward top-2
+(queries -> candidates) and the cross-check pass (candidates -> queries) in ONE K1 launch (+ merge + extract), i.e.
+2 x n1 x n2 row comparisons. Ranks are independent (pairs shard embarrassingly; no data-path collective): weak scaling,
+value = comparisons of all ranks / max-over-ranks device time.
+
+  value  device-resident: descriptors already in HBM, CUDA events on the launching stream around each step, the L2
+         flushed (256 MiB write) between timed steps;
+  e2e    the same step through the reference-facing C++ entry point (match_features_subset on std::vector<feature_2d>
+         held on the host + cross-check flags): row packing, H2D, kernels, D2H, double ratio test, std::sort - wall clock;
+  cpu_baseline / --impl reference: the reference's own match_features.cpp object code (oracle/_ref, -mpopcnt build;
+         the as-shipped build is reported next to it) under the reference's OpenMP-over-pairs driver on the box's host cores.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N1 = N2 = 10000
+METRIC = "hamming_comparisons_per_s"
+UNIT = "Gcmp/s"
+WORKLOAD = "configs[1]: synthetic pair 10000x10000 512-bit descriptors, top-2 + ratio test + cross-check"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)), "measured"
+    return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock + throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.mhz, self.reasons, self.max_mhz = index, False, [], set(), None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:  # noqa: BLE001
+            self.nv = None
+
+    def run(self):
+        if not self.nv:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        while not self.stop_flag:
+            try:
+                self.mhz.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.004)
+
+    def result(self):
+        self.stop_flag = True
+        self.join(timeout=2)
+        return {"sm_mhz": float(np.median(self.mhz)) if self.mhz else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.mhz)}
+
+
+def cpu_reference_run(steps, warmup, threads=0, n2_sample=2500):
+    """The reference's CPU path: `threads` pairs per step (one pair per OpenMP worker, pipeline.cpp:42-49), each
+    N1 queries x n2_sample candidates of the same synthetic workload (bounded sample of the 10k x 10k pair)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oc_oracle as O
+    from opencalibration_b200 import synthetic
+    kind = "reference"
+    try:
+        ref, ref_shipped = O.Reference(popcnt=True), O.Reference(popcnt=False)
+    except (FileNotFoundError, OSError):
+        ref, ref_shipped, kind = O.Oracle(), None, "port"
+    cores = ref.num_procs() if threads <= 0 else threads
+    qs, cs = [], []
+    for t in range(cores):
+        a, b = synthetic.config2_pair(N1, N2, seed=100 + t)
+        qs.append(a)
+        cs.append(b[:n2_sample])
+    q, c = np.concatenate(qs), np.concatenate(cs)
+    cmp_per_step = cores * N1 * n2_sample
+    for _ in range(warmup):
+        ref.bench_match_pairs(q[:cores * 500], c[:cores * 500], cores, 500, 500, cores)
+    secs = [ref.bench_match_pairs(q, c, cores, N1, n2_sample, cores)[0] for _ in range(steps)]
+    value = cmp_per_step / (sum(secs) / len(secs)) / 1e9
+    shipped = None
+    if ref_shipped is not None:
+        s = ref_shipped.bench_match_pairs(q[:cores * N1 // 4], c, cores, N1 // 4, n2_sample, cores)[0]
+        shipped = cores * (N1 // 4) * n2_sample / s / 1e9
+    return dict(value=value, unit=UNIT, cores=cores, kind=kind,
+                sample=f"{cores} pairs/step (one per OpenMP thread) of {N1}x{n2_sample} rows of the workload, -mpopcnt build",
+                as_shipped_flags_value=shipped, ms_per_step=1e3 * sum(secs) / len(secs))
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_reference_run(args.steps, max(args.warmup, 1))
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "n1": N1, "n2": N2},
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "as_shipped_flags_value")},
+            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    from opencalibration_b200 import capi, host, synthetic
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    capi.init(local_rank)
+    peaks, peak_src = measured_peaks()
+
+    # ---- inputs: this rank's pair, resident in HBM
+    a, b = synthetic.config2_pair(N1, N2, seed=1 + rank)
+    dq = torch.from_numpy(a.view(np.int64)).cuda()
+    dc = torch.from_numpy(b.view(np.int64)).cuda()
+    dout = torch.zeros(N1, dtype=torch.int64, device="cuda")
+    dcol = torch.zeros(N2, dtype=torch.int32, device="cuda")
+    wsb = capi.match_top2_workspace_bytes(N1, N2, True)
+    ws = torch.zeros(wsb + 512, dtype=torch.uint8, device="cuda")
+    wsp = (ws.data_ptr() + 255) // 256 * 256
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    cmp_per_step = 2 * N1 * N2  # forward + cross-check pass, both n1 x n2 row comparisons
+
+    def step():
+        capi.match_top2_device(dq.data_ptr(), N1, dc.data_ptr(), N2, dout.data_ptr(), dcol.data_ptr(), wsp, wsb, stream)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    launches0 = capi.kernel_launches()
+    barrier()
+    for e0, e1 in ev:
+        flush.fill_(1)  # evict L2 between timed steps (outside the event bracket)
+        e0.record()
+        step()
+        e1.record()
+    barrier()
+    launches = capi.kernel_launches() - launches0
+    clocks = sampler.result()
+    dev_ms = sum(e0.elapsed_time(e1) for e0, e1 in ev)
+    t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
+    if dist:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = world * cmp_per_step / (ms_per_step * 1e-3) / 1e9
+
+    # ---- e2e: the reference-facing C++ entry point on host vectors (pack, H2D, kernels, D2H, ratio test, sort)
+    fa, fb = host.FeatureSet(a), host.FeatureSet(b)
+    idx1, idx2 = np.arange(N1, dtype=np.uintp), np.arange(N2, dtype=np.uintp)
+    matcher = host.Matcher(N1)
+    for _ in range(3):
+        n_matches = matcher(fa, fb, idx1, idx2, cross_check=True)
+    e2e_steps = max(3, min(args.steps, 50))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        n_matches = matcher(fa, fb, idx1, idx2, cross_check=True)
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if dist:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_ms = float(e2e_s.item()) * 1e3 / e2e_steps
+    e2e_value = world * cmp_per_step / (e2e_ms * 1e-3) / 1e9
+
+    if rank != 0:
+        if dist:
+            dist.destroy_process_group()
+        return
+
+    # ---- parity spot check of what was timed (sampled rows against the checker) + CPU baseline on this box
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oc_oracle as O
+    orc = O.Oracle()
+    r = dout.cpu().numpy().view(capi.TOP2_DTYPE)
+    pick = np.random.default_rng(0).permutation(N1)[:64]
+    bk, bd, sd = orc.match_top2(a[pick], b)
+    parity = bool(np.array_equal(r["best_k"][pick], bk) and np.array_equal(r["best_d"][pick], bd) and
+                  np.array_equal(r["second_d"][pick], sd))
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cb = cpu_reference_run(steps=4, warmup=1)
+        cpu = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "as_shipped_flags_value")}
+
+    sm_max = float(peaks.get("sm_max_mhz", 1965.0))
+    popc_peak = 148 * 16 * sm_max * 1e6 / 16 / 1e9  # G comparisons/s: 16 POPC/clk/SM, 16 POPC per comparison
+    achieved = cmp_per_step / (ms_per_step * 1e-3) / 1e9 if world == 1 else value / world
+    held = clocks.get("sm_mhz") or sm_max
+    algo_bytes = 2 * (N1 + N2) * 64 + N1 * 8 + N2 * 8 + N2 * 4
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "n1": N1, "n2": N2, "comparisons_per_step": cmp_per_step,
+                   "cross_check": "second K1 pass with the roles swapped, same launch",
+                   "pairs_per_s": world / (ms_per_step * 1e-3), "l2": "flushed between timed steps (256 MiB write)",
+                   "k1_variant": capi.get_option("k1_variant"), "parity_spot_check": parity,
+                   "ratio_test_survivors": int(n_matches)},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": (N1 + N2) * 64,
+                "d2h_bytes_per_step": N1 * 8 + N2 * 4, "ms_per_step": e2e_ms, "steps": e2e_steps,
+                "api": "match_features_subset(std::vector<feature_2d>...) + cross-check flags via libocb_host.so",
+                "pairs_per_s": world / (e2e_ms * 1e-3)},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "popc", "achieved": achieved, "peak": popc_peak, "unit": UNIT,
+                     "frac": achieved / popc_peak, "traffic": None,
+                     "peak_source": f"148 SMs x 16 POPC/clk/SM (probed on this pool: 16.0) x {sm_max:.0f} MHz "
+                                    f"({peak_src} sm_max_mhz) / 16 POPC per comparison",
+                     "frac_at_held_clock": achieved / (148 * 16 * held * 1e6 / 16 / 1e9),
+                     "note": "K1 trades POPCs for LOP3 carry-save adders, so it can exceed the plain-POPC roofline",
+                     "hbm": {"achieved_gbs": algo_bytes / (ms_per_step * 1e-3) / 1e9,
+                             "peak_gbs": peaks.get("hbm_gbs"), "algorithmic_bytes_per_step": algo_bytes}},
+    }
+    if cpu:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line), flush=True)
+    if dist:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -35,6 +35,11 @@ def lib():
               "ocbh_sizeof_correspondence", "ocbh_sizeof_feature_match_denormalized"):
         getattr(L, f).restype = sz
     L.ocbh_match_features_subset.argtypes = [_u64p, sz, _u64p, sz, _szp, sz, _szp, sz, _szp, _szp, _f64p, vp, _szp]
+    L.ocbh_features_create.argtypes = [vp, vp, _u64p, sz]
+    L.ocbh_features_create.restype = vp
+    L.ocbh_features_destroy.argtypes = [vp]
+    L.ocbh_features_destroy.restype = None
+    L.ocbh_match_handles.argtypes = [vp, vp, _szp, sz, _szp, sz, _szp, _szp, _f64p, vp, _szp]
     L.ocbh_subsample.argtypes = [_f64p, _f32p, sz, dbl, sz, _szp]
     L.ocbh_subsample.restype = sz
     L.ocbh_ransac.argtypes = [i32, _f64p, sz, _f64p, _u8p, _f64p, _szp]
@@ -104,6 +109,42 @@ def match_features_subset(desc1, desc2, idx1, idx2, cross_check=False):
     if cross_check:
         return o1[:m].copy(), o2[:m].copy(), od[:m].copy(), mut[:m].astype(bool)
     return o1[:m].copy(), o2[:m].copy(), od[:m].copy()
+
+
+class FeatureSet:
+    """A std::vector<feature_2d> living on the C++ side (what the pipeline holds per image)."""
+
+    def __init__(self, desc, xy=None, strength=None):
+        desc = _rows(desc)
+        self.n = len(desc)
+        xyp = None if xy is None else np.ascontiguousarray(xy, np.float64).ctypes.data_as(C.c_void_p)
+        stp = None if strength is None else np.ascontiguousarray(strength, np.float32).ctypes.data_as(C.c_void_p)
+        self.handle = lib().ocbh_features_create(xyp, stp, desc, self.n)
+
+    def close(self):
+        if self.handle:
+            lib().ocbh_features_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+
+class Matcher:
+    """match_features_subset(set_1, set_2, indices_1, indices_2) on two FeatureSets with preallocated outputs."""
+
+    def __init__(self, max_queries):
+        m = max(int(max_queries), 1)
+        self.o1, self.o2 = np.zeros(m, np.uintp), np.zeros(m, np.uintp)
+        self.od, self.mut, self.n = np.zeros(m, np.float64), np.zeros(m, np.uint8), np.zeros(1, np.uintp)
+
+    def __call__(self, set_1, set_2, idx1, idx2, cross_check=False):
+        _check(lib().ocbh_match_handles(set_1.handle, set_2.handle, idx1, len(idx1), idx2, len(idx2), self.o1, self.o2,
+                                        self.od, self.mut.ctypes.data_as(C.c_void_p) if cross_check else None, self.n))
+        return int(self.n[0])
 
 
 def spatially_subsample_feature_indices(xy, strength, spacing, count=0):

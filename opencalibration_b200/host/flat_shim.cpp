@@ -139,6 +139,35 @@ extern "C"
         });
     }
 
+    // Persistent feature sets: the caller-side std::vector<feature_2d> the pipeline already holds in memory
+    // (image::features). Matching two handles is exactly the reference call on existing vectors.
+    void *ocbh_features_create(const double *xy, const float *strength, const uint64_t *desc, size_t n)
+    {
+        return new std::vector<feature_2d>(make_features(xy, strength, desc, n));
+    }
+    void ocbh_features_destroy(void *h) { delete static_cast<std::vector<feature_2d> *>(h); }
+    int ocbh_match_handles(const void *h1, const void *h2, const size_t *idx1, size_t n1, const size_t *idx2,
+                           size_t n2, size_t *out_i1, size_t *out_i2, double *out_dist, uint8_t *mutual, size_t *n_out)
+    {
+        return guarded([&] {
+            const auto &f1 = *static_cast<const std::vector<feature_2d> *>(h1);
+            const auto &f2 = *static_cast<const std::vector<feature_2d> *>(h2);
+            const std::vector<size_t> i1(idx1, idx1 + n1), i2(idx2, idx2 + n2);
+            std::vector<bool> mut;
+            const std::vector<feature_match> r = mutual ? ocb_host::match_features_subset_cross_checked(f1, f2, i1, i2, mut)
+                                                        : match_features_subset(f1, f2, i1, i2);
+            for (size_t i = 0; i < r.size(); i++)
+            {
+                out_i1[i] = r[i].feature_index_1;
+                out_i2[i] = r[i].feature_index_2;
+                out_dist[i] = r[i].distance;
+                if (mutual)
+                    mutual[i] = mut[i];
+            }
+            *n_out = r.size();
+        });
+    }
+
     size_t ocbh_subsample(const double *xy, const float *strength, size_t n, double spacing, size_t count,
                           size_t *out_idx)
     {

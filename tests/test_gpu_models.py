@@ -1,0 +1,213 @@
+"""GPU parity tests for K2/K3 (MSAC scoring) and the RANSAC driver of the C++ mirror.
+Bar: inlier sets, counts and MSAC scores bit-exact versus the CPU oracle (same canonical operation order, IEEE
+double, sums in evaluation order); fitted models bit-exact versus the oracle's restatement and within 1e-9
+(relative Frobenius) of what the reference's tests require."""
+import numpy as np
+import pytest
+
+import oc_oracle as O
+from opencalibration_b200 import synthetic
+
+pytestmark = pytest.mark.gpu
+
+THR = {0: 0.005, 1: 0.01, 2: 0.01}
+
+
+def stream_models(oracle, kind, corr, count):
+    eo, samples = oracle.hypothesis_stream(kind, corr, count)
+    models = np.zeros((count, 18))
+    for i, s in enumerate(samples):
+        models[i] = np.nan_to_num(oracle.fit(kind, corr, s), nan=0.0)
+    return eo, samples, models
+
+
+@pytest.mark.parametrize("kind", [0, 1, 2])
+@pytest.mark.parametrize("n", [1, 31, 224, 225, 1000, 3333])
+def test_scores_bit_exact(gpu, oracle, kind, n):
+    n_in = int(n * 0.7)
+    corr = (oracle.scene_homography(n_in, n - n_in, 5)[0] if kind == 0 else
+            oracle.scene_fundamental(n_in, n - n_in, 0.0, 5)[0])
+    if n < O.MIN_POINTS[kind]:
+        models = synthetic.random_models(kind, 9, seed=n)
+        eo = np.random.default_rng(0).permutation(n)
+    else:
+        eo, _, models = stream_models(oracle, kind, corr, 19)
+    for order in (None, eo):
+        s, c, bits = gpu.score_models(kind, models, corr, THR[kind], order=order)
+        so, co, bo = oracle.score_hypotheses(kind, models, corr, order=order, thr=THR[kind])
+        assert np.array_equal(s, so)          # sequential double sum, bit for bit
+        assert np.array_equal(c, co) and np.array_equal(bits, bo)
+
+
+def test_residuals_bit_exact_and_special_values(gpu, oracle):
+    corr, _ = oracle.scene_homography(500, 200, 3)
+    corr[10, 2] = 0.0       # measurement1.z == 0
+    corr[11, 5] = np.inf    # measurement2.z == inf
+    corr[12, 0] = np.nan
+    corr[13, 0:6] *= -3.5   # homogeneous scale (incl. negative z) must not matter after m / m.z
+    for kind in (0, 2):
+        _, _, models = stream_models(oracle, kind, corr[20:], 3)
+        for m in models:
+            e = gpu.residuals(kind, m, corr)
+            eo = np.array([oracle.error(kind, m, c) for c in corr])
+            assert np.array_equal(e, eo, equal_nan=True)
+            assert np.isnan(e[10]) and np.isnan(e[11]) and np.isnan(e[12])
+        s, c, bits = gpu.score_models(kind, models, corr, THR[kind])
+        so, co, bo = oracle.score_hypotheses(kind, models, corr, thr=THR[kind])
+        assert np.array_equal(s, so) and np.array_equal(c, co) and np.array_equal(bits, bo)
+        assert not (bits[:, 0] >> 10 & 1).any()  # NaN residuals are never inliers
+    zero = np.zeros((1, 18))  # epipolar denominator < 1e-20 -> DBL_MAX -> no inliers
+    s, c, bits = gpu.score_models(1, zero, corr, 0.01)
+    assert s[0] == 0 and c[0] == 0
+    assert gpu.residuals(1, zero[0], corr[:5]).tolist() == [np.finfo(np.float64).max] * 5
+
+
+def test_threshold_is_strict(gpu, oracle):
+    # e < t (ransac.cpp:189): move the threshold onto an observed residual and just above it
+    corr, gt = oracle.scene_homography(50, 50, 8)
+    _, _, models = stream_models(oracle, 0, corr, 4)
+    e = gpu.residuals(0, models[0], corr)
+    t = np.sort(e[np.isfinite(e)])[30]
+    for thr in (t, np.nextafter(t, np.inf)):
+        s, c, bits = gpu.score_models(0, models[:1], corr, thr)
+        so, co, bo = oracle.score_hypotheses(0, models[:1], corr, thr=thr)
+        assert np.array_equal(c, co) and np.array_equal(s, so) and np.array_equal(bits, bo)
+    assert gpu.score_models(0, models[:1], corr, t)[1][0] + 1 == gpu.score_models(0, models[:1], corr,
+                                                                                   np.nextafter(t, np.inf))[1][0]
+
+
+def test_many_hypotheses_ragged_groups(gpu, oracle):
+    corr, _ = oracle.scene_homography(700, 300, 11)
+    eo, _, models = stream_models(oracle, 0, corr, 61)  # 61 = 7 full groups of 8 + 5
+    s, c, bits = gpu.score_models(0, models, corr, 0.005, order=eo)
+    so, co, bo = oracle.score_hypotheses(0, models, corr, order=eo, thr=0.005)
+    assert np.array_equal(s, so) and np.array_equal(c, co) and np.array_equal(bits, bo)
+    s2, c2, _ = gpu.score_models(0, models, corr, 0.005, order=eo, want_bits=False)
+    assert np.array_equal(s2, s) and np.array_equal(c2, c)
+
+
+def test_config3_full_size_sampled(gpu, oracle):
+    # BASELINE configs[2]: 4k hypotheses x 20k correspondences from the reference's seeded stream
+    corr, gt = oracle.scene_homography(14000, 6000, 42)
+    eo, samples, models = stream_models(oracle, 0, corr, 4096)
+    s, c, _ = gpu.score_models(0, models, corr, 0.005, order=eo, want_bits=False)
+    pick = np.concatenate([np.arange(8), np.random.default_rng(0).permutation(4096)[:24], [4095]])
+    so, co, _ = oracle.score_hypotheses(0, models[pick], corr, order=eo, thr=0.005, want_bits=False)
+    assert np.array_equal(s[pick], so) and np.array_equal(c[pick], co)
+    # size-independent properties: a sample drawn from inliers only scores >= 14000 * small, counts bound scores
+    assert np.all(s <= c) and np.all(s >= 0) and c.max() >= 14000
+    all_inlier_samples = np.all(samples < 14000, axis=1)
+    assert c[all_inlier_samples].min() >= 13990
+    # evaluation order changes neither counts nor (beyond rounding) scores
+    s_nat, c_nat, _ = gpu.score_models(0, models[:64], corr, 0.005, want_bits=False)
+    assert np.array_equal(c_nat, c[:64]) and np.allclose(s_nat, s[:64], rtol=1e-12)
+
+
+def test_evaluate_through_the_mirror(gpu, hostlib, oracle):
+    for kind in (0, 1, 2):
+        corr = (oracle.scene_homography(300, 100, 2)[0] if kind == 0 else oracle.scene_fundamental(300, 100, 0, 2)[0])
+        _, _, models = stream_models(oracle, kind, corr, 5)
+        for m in models:
+            s, inl = hostlib.evaluate(kind, m, corr)
+            so, io = oracle.evaluate(kind, m, corr)
+            assert s == so and np.array_equal(inl, io)
+    s, inl = hostlib.evaluate(0, models[0], np.zeros((0, 7)))
+    assert s == 0 and len(inl) == 0
+
+
+# ---- the RANSAC driver -------------------------------------------------------------------------------------------------
+def m33(M18):
+    return np.asarray(M18[:9]).reshape(3, 3).T
+
+
+def check_ransac_equal(hostlib, oracle, kind, corr):
+    s, M, inl, st = hostlib.ransac(kind, corr)
+    so, Mo, io, tr = oracle.ransac(kind, corr)
+    assert s == so
+    assert np.array_equal(inl, io)
+    n = 18 if kind == 0 else 9
+    assert np.array_equal(M[:n], Mo[:n], equal_nan=True)
+    assert st["iterations"] == tr["iterations"] and st["improvements"] == tr["improvements"]
+    assert st["degenerate"] == tr["degenerate"]
+    return s, M, inl, st
+
+
+def test_ransac_unit_cases(gpu, hostlib, oracle):
+    # test/test_ransac_unit.cpp: empty, too few, identity
+    for kind in (0, 1, 2):
+        s, M, inl, st = hostlib.ransac(kind, np.zeros((0, 7)))
+        assert s == 0 and len(inl) == 0
+    sq = np.zeros((4, 7))
+    sq[:, 0:3] = [(1, 2, 1), (2, 2, 1), (2, 1, 1), (1, 1, 1)]
+    sq[:, 3:6] = sq[:, 0:3]
+    s, M, inl, st = check_ransac_equal(hostlib, oracle, 0, sq)
+    assert s == pytest.approx(1.0, abs=1e-15) and inl.sum() == 4 and np.linalg.norm(m33(M) - np.eye(3)) < 1e-14
+    s, M, inl, st = hostlib.ransac(0, sq[:3])
+    assert s == 0 and len(inl) == 3 and not inl.any() and np.isnan(M[:9]).all()
+    pts = [(1, 2, 1), (2, 2, 1), (2, 1, 1), (1, 1, 1), (1, 2, 3), (2, 2, 2), (2, 1, 3), (1, 1, 2)]
+    c = np.zeros((8, 7))
+    c[:, 0:3] = pts
+    c[:, 0:3] /= np.linalg.norm(c[:, 0:3], axis=1, keepdims=True)
+    c[:, 3:6] = c[:, 0:3]
+    s, M, inl, st = check_ransac_equal(hostlib, oracle, 2, c)
+    assert s == pytest.approx(1.0, abs=1e-15) and inl.sum() == 8 and abs(np.linalg.norm(m33(M)) - 1) < 1e-14
+    s, M, inl, st = check_ransac_equal(hostlib, oracle, 1, c[:6])
+    assert s >= 0.16 and inl.sum() >= 1
+
+
+@pytest.mark.parametrize("name", ["h30", "h80", "hdeg", "f30", "fplane", "e0", "h30q", "c1"])
+def test_ransac_equals_reference_driver_golden(gpu, hostlib, golden, name):
+    # golden = the reference's own ransac.cpp (driver) over the restated model functions
+    kind = int(golden[f"rs_{name}_kind"]) if f"rs_{name}_kind" in golden.files else 0
+    s, M, inl, st = hostlib.ransac(kind, golden[f"rs_{name}_corr"])
+    assert s == float(golden[f"rs_{name}_score"])
+    assert np.array_equal(M[:9], golden[f"rs_{name}_M"][:9])
+    assert np.array_equal(inl, golden[f"rs_{name}_inl"])
+    assert st["scored"] >= st["iterations"] - st["degenerate"] and st["gpu_calls"] >= 1
+
+
+def test_ransac_benchmark_floors(gpu, hostlib, oracle):
+    # test/test_ransac_benchmark.cpp floors, through the GPU driver
+    def pr(inl, n_true):
+        gt = np.arange(len(inl)) < n_true
+        tp, fp, fn = (inl & gt).sum(), (inl & ~gt).sum(), (~inl & gt).sum()
+        return tp / max(tp + fp, 1), tp / max(tp + fn, 1)
+
+    def merr(M, gt):
+        a, b = M / np.linalg.norm(M), gt / np.linalg.norm(gt)
+        return min(np.linalg.norm(a - b), np.linalg.norm(a + b))
+
+    for n_in, n_out, pmin, rmin in ((200, 0, .99, .99), (140, 60, .90, .85), (80, 120, .80, .70), (40, 160, .70, .60)):
+        corr, gt = oracle.scene_homography(n_in, n_out, 42)
+        s, M, inl, st = check_ransac_equal(hostlib, oracle, 0, corr)
+        p, r = pr(inl, n_in)
+        assert p >= pmin and r >= rmin
+        if n_out == 0:
+            assert merr(m33(M), gt) < 1e-6
+    for n_in, n_out, planar, pmin, rmin in ((200, 0, 0.0, .95, .80), (140, 60, 0.0, .85, .70), (200, 0, 0.8, .95, .95)):
+        corr, gt = oracle.scene_fundamental(n_in, n_out, planar, 42)
+        s, M, inl, st = check_ransac_equal(hostlib, oracle, 2, corr)
+        p, r = pr(inl, n_in)
+        assert p >= pmin and r >= rmin
+
+
+def test_ransac_prosac_and_large(gpu, hostlib, oracle):
+    corr, _ = oracle.scene_homography(1500, 1000, 3)
+    corr[:, 6] = np.random.default_rng(43).uniform(0.05, 0.4, len(corr))  # PROSAC branch
+    check_ransac_equal(hostlib, oracle, 0, corr)
+    corr, _ = oracle.scene_homography(600, 5400, 4)  # 10 % inliers: thousands of iterations, SPRT rejections
+    s, M, inl, st = check_ransac_equal(hostlib, oracle, 0, corr)
+    assert st["iterations"] > 1000
+    corr, _ = oracle.scene_fundamental(500, 300, 0.5, 9)  # DEGENSAC path
+    check_ransac_equal(hostlib, oracle, 2, corr)
+    check_ransac_equal(hostlib, oracle, 1, corr)
+
+
+def test_degensac_through_the_mirror(gpu, hostlib, oracle):
+    corr, _ = oracle.scene_fundamental(200, 0, 0.8, 42)
+    eo, samples = oracle.hypothesis_stream(2, corr, 4)
+    M = oracle.fit(2, corr, samples[0])
+    s, inl = oracle.evaluate(2, M, corr)
+    a = hostlib.check_degeneracy_f(M, corr, inl)
+    b = oracle.check_degeneracy_f(M, corr, inl)
+    assert np.array_equal(a[0][:9], b[0][:9]) and np.array_equal(a[1], b[1])
