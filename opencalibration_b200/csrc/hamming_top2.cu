@@ -1,8 +1,9 @@
-// K1 -- brute-force Hamming top-2 over 512-bit descriptor rows (sm_100a).
+// K1 -- brute-force Hamming top-2 over 512-bit descriptor rows (sm_100a), one kernel launch per submission.
 //
 // Replaces the loop nest of match_features_subset (reference src/match/match_features.cpp:71-93):
 // for every query row the first candidate position at minimum Hamming distance, that distance, and the
-// second-smallest distance counted with multiplicity (tie rule of :80-92).
+// second-smallest distance counted with multiplicity (tie rule of :80-92). Optionally, in the same sweep, the
+// column-wise best query of every candidate (cross-check; not in the reference).
 //
 // Mapping to the hardware
 //   * one work item = one CTA = (query tile of 128*Q rows) x (a contiguous range of candidate rows);
@@ -10,18 +11,27 @@
 //   * candidate rows stream through shared memory in TILE_C-row tiles, copied by 1-D bulk TMA
 //     (cp.async.bulk + mbarrier, SASS UBLKCP) into a K1_STAGES-deep ring, and are read back as warp-uniform
 //     LDS.128 broadcasts, so one shared-memory read feeds 32 lanes x Q comparisons;
-//   * distance = XOR + POPC on the integer pipes. POPC issues on the quarter-rate XU pipe, LOP3 on the ALU pipe
-//     and IMAD on the FMA pipe, so part of the 16 popcounts per comparison is traded for carry-save adders
-//     (F full adders = 2 LOP3 each, each removes one POPC) to balance the three pipes; the weighted sum of the
-//     remaining popcounts is accumulated with IMADs straight into a packed key
-//           key = (distance << 20) | candidate_index_within_item
-//     whose unsigned order is exactly the reference's (distance, position) order;
-//   * per query the two smallest keys are kept: m1 gives best distance + first position, m2's distance is the
-//     reference's second_best (a later equal distance has a larger key, i.e. multiplicity is preserved).
-//     Updates are rare after the first few candidates, so the common path is one compare per comparison and a
-//     warp-uniform branch around the 3-op min/max update;
-//   * when a single pair cannot fill 148 SMs the candidate axis is split across CTAs; every split writes its
-//     (m1,m2) per query and a small merge kernel takes the top-2 of the union in position order.
+//   * distance = XOR + POPC on the integer pipes. POPC issues on the quarter-rate XU pipe (16/clk/SM), LOP3 on
+//     the ALU pipe (64/clk/SM) and IMAD on the FMA pipe (64/clk/SM), and the three overlap, so part of the 16
+//     popcounts per comparison is traded for carry-save adders (F full adders = 2 LOP3 each, each removes one
+//     POPC) and the weighted sum of the remaining popcounts is accumulated with IMADs (runtime multiplier, so
+//     ptxas cannot turn them back into ALU shifts/adds) into a packed value
+//           v = (distance << 20) | query_slot_in_tile
+//     Within one query, v orders by distance alone (the low bits are that query's constant), which is what the
+//     reference's strict-less-than updates need because candidates arrive in position order; across the queries
+//     of a column it orders by (distance, query position), which is what the cross-check needs;
+//   * per query the two smallest values (s1 <= s2) and the position of the first minimum are kept. Updates are
+//     rare after the first few candidates: the common path is one compare per comparison and a warp-uniform
+//     branch around the update;
+//   * cross-check: per candidate the warp-wide minimum of v (REDUX) goes to a 64-bit atomic max on the
+//     complemented (distance, query) key in global memory (complemented so that the zero-initialised workspace
+//     means "nothing yet");
+//   * when a single pair cannot fill 148 SMs the candidate axis is split across CTAs; every CTA folds its
+//     per-query (d1, position, d2) into a global per-query state with two atomics (64-bit max on the
+//     complemented (distance, position) key; 32-bit max on the complemented distance of every key that loses) and
+//     takes a ticket per query tile; the CTA that draws the last ticket converts the state to the final records.
+//     A second ticket per candidate split lets the last CTA of a split convert the column keys to query
+//     indices. No second kernel, no serial merge.
 #include "ocb_internal.cuh"
 
 #include <algorithm>
@@ -34,18 +44,28 @@ namespace ocb
 constexpr int K1_THREADS = 128;
 constexpr int K1_TILE_C = 64; // candidate rows per shared-memory tile (4 KB)
 constexpr int K1_STAGES = 4;
-constexpr int K1_KEY_SHIFT = 20; // candidates per work item < 2^20
-constexpr uint32_t K1_KEY_IDX_MASK = (1u << K1_KEY_SHIFT) - 1;
-constexpr uint32_t K1_MAX_TILES_PER_SPLIT = (1u << K1_KEY_SHIFT) / K1_TILE_C;
+constexpr int K1_SHIFT = 20;  // v = distance << 20 | slot ; candidates per work item < 2^20 (index kept apart)
+constexpr uint32_t K1_SLOT_MASK = (1u << K1_SHIFT) - 1;
+constexpr uint32_t K1_MIN_ROWS_PER_SPLIT = 32; // do not split finer than this
+constexpr uint32_t K1_NONE = 0xFFFFFFFFu;
+
+__device__ __forceinline__ uint32_t mad_u32(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
 
 // ----------------------------------------------------------------------------------------------------------
-// distance key: key0 + (popcount(q ^ c) << 20), with F carry-save full adders in front of the popcounts
+// v = v0 + (popcount(q ^ c) << 20), with F carry-save full adders in front of the popcounts.
+// IMADACC: accumulate with IMAD on the FMA pipe (w = 1 << 20 arrives as a kernel parameter).
 // ----------------------------------------------------------------------------------------------------------
-template <int F> __device__ __forceinline__ uint32_t hamming_key(const uint32_t (&q)[16], const uint4 (&c)[4], uint32_t key0)
+template <int F, bool IMADACC>
+__device__ __forceinline__ uint32_t hamming_value(const uint32_t (&q)[16], const uint4 (&c)[4], uint32_t v0, uint32_t w)
 {
-    constexpr int F1 = F < 7 ? F : 7;                      // adders on weight-1 words (16 -> 16-2*F1)
+    constexpr int F1 = F < 7 ? F : 7;                        // adders on weight-1 words
     constexpr int F2 = F <= 7 ? 0 : (F - 7 < 3 ? F - 7 : 3); // adders on weight-2 words
-    constexpr int F4 = F <= 10 ? 0 : 1;                    // adder on weight-4 words
+    constexpr int F4 = F <= 10 ? 0 : 1;                      // adder on weight-4 words
     uint32_t w1[16 + 7];
     uint32_t w2[7 + 3 + 1];
     uint32_t w4[3 + 1 + 1];
@@ -76,20 +96,39 @@ template <int F> __device__ __forceinline__ uint32_t hamming_key(const uint32_t 
         w8[t8++] = lop3_maj(w4[h4], w4[h4 + 1], w4[h4 + 2]);
         h4 += 3;
     }
-    uint32_t key = key0;
+    uint32_t v = v0;
+    if constexpr (IMADACC)
+    {
+        const uint32_t wa = w, wb = w * 2, wc = w * 4, wd = w * 8;
 #pragma unroll
-    for (int i = h1; i < t1; i++)
-        key += (uint32_t)__popc(w1[i]) * (1u << K1_KEY_SHIFT);
+        for (int i = h1; i < t1; i++)
+            v = mad_u32((uint32_t)__popc(w1[i]), wa, v);
 #pragma unroll
-    for (int i = h2; i < t2; i++)
-        key += (uint32_t)__popc(w2[i]) * (2u << K1_KEY_SHIFT);
+        for (int i = h2; i < t2; i++)
+            v = mad_u32((uint32_t)__popc(w2[i]), wb, v);
 #pragma unroll
-    for (int i = h4; i < t4; i++)
-        key += (uint32_t)__popc(w4[i]) * (4u << K1_KEY_SHIFT);
+        for (int i = h4; i < t4; i++)
+            v = mad_u32((uint32_t)__popc(w4[i]), wc, v);
 #pragma unroll
-    for (int i = 0; i < t8; i++)
-        key += (uint32_t)__popc(w8[i]) * (8u << K1_KEY_SHIFT);
-    return key;
+        for (int i = 0; i < t8; i++)
+            v = mad_u32((uint32_t)__popc(w8[i]), wd, v);
+    }
+    else
+    {
+#pragma unroll
+        for (int i = h1; i < t1; i++)
+            v += (uint32_t)__popc(w1[i]) * (1u << K1_SHIFT);
+#pragma unroll
+        for (int i = h2; i < t2; i++)
+            v += (uint32_t)__popc(w2[i]) * (2u << K1_SHIFT);
+#pragma unroll
+        for (int i = h4; i < t4; i++)
+            v += (uint32_t)__popc(w4[i]) * (4u << K1_SHIFT);
+#pragma unroll
+        for (int i = 0; i < t8; i++)
+            v += (uint32_t)__popc(w8[i]) * (8u << K1_SHIFT);
+    }
+    return v;
 }
 
 __device__ __forceinline__ const K1Problem *find_problem(const K1Problem *__restrict__ problems, uint32_t n, uint32_t item)
@@ -106,29 +145,28 @@ __device__ __forceinline__ const K1Problem *find_problem(const K1Problem *__rest
     return problems + lo;
 }
 
-__device__ __forceinline__ ocb_top2 finish_keys(uint32_t m1, uint32_t m2, uint32_t c_begin)
+__device__ __forceinline__ uint32_t dist_of(uint32_t v)
+{
+    return v == K1_NONE ? (uint32_t)OCB_DIST_INF : (v >> K1_SHIFT);
+}
+
+__device__ __forceinline__ ocb_top2 make_record(uint32_t d1, uint32_t d2, uint32_t idx)
 {
     ocb_top2 r;
-    if (m1 == 0xFFFFFFFFu)
-    {
-        r.best_k = 0; // feature_match best_match{i, 0, inf} (match_features.cpp:74)
-        r.best_d = OCB_DIST_INF;
-    }
-    else
-    {
-        r.best_k = c_begin + (m1 & K1_KEY_IDX_MASK);
-        r.best_d = (uint16_t)(m1 >> K1_KEY_SHIFT);
-    }
-    r.second_d = m2 == 0xFFFFFFFFu ? (uint16_t)OCB_DIST_INF : (uint16_t)(m2 >> K1_KEY_SHIFT);
+    r.best_k = d1 == OCB_DIST_INF ? 0u : idx; // feature_match best_match{i, 0, inf} (match_features.cpp:74)
+    r.best_d = (uint16_t)d1;
+    r.second_d = (uint16_t)d2;
     return r;
 }
 
-template <int Q, int F, int MINB>
+template <int Q, int F, bool IMADACC, bool COL, int MINB>
 __global__ void __launch_bounds__(K1_THREADS, MINB)
-    k1_top2_kernel(const __grid_constant__ K1Inline inl, const K1Problem *__restrict__ problems, uint32_t n_problems)
+    k1_top2_kernel(const __grid_constant__ K1Inline inl, const K1Problem *__restrict__ problems, uint32_t n_problems,
+                   uint32_t w)
 {
     __shared__ alignas(128) uint4 tile[K1_STAGES][K1_TILE_C * 4];
     __shared__ alignas(8) uint64_t full_bar[K1_STAGES];
+    __shared__ uint32_t ticket[2];
 
     const uint32_t tid = threadIdx.x;
     // <= K1_INLINE problems travel in the kernel parameters (no table upload on the single-pair path)
@@ -138,12 +176,13 @@ __global__ void __launch_bounds__(K1_THREADS, MINB)
     const uint32_t local = blockIdx.x - pp->item_begin;
     const uint32_t split = local / q_tiles;
     const uint32_t qtile = local - split * q_tiles;
-    const uint32_t tiles_per_split = pp->tiles_per_split;
-    const uint32_t c_begin = split * tiles_per_split * K1_TILE_C;
-    const uint32_t c_end = min(n_c, c_begin + tiles_per_split * K1_TILE_C);
+    const uint32_t rows_per_split = pp->rows_per_split;
+    const uint32_t c_begin = split * rows_per_split;
+    const uint32_t c_end = min(n_c, c_begin + rows_per_split);
     const uint32_t c_cnt = c_end > c_begin ? c_end - c_begin : 0;
     const uint32_t ntiles = (c_cnt + K1_TILE_C - 1) / K1_TILE_C;
     const uint4 *__restrict__ cand = pp->c + (size_t)c_begin * 4;
+    unsigned long long *__restrict__ col64 = COL ? pp->col64 : nullptr;
 
     if (tid == 0)
     {
@@ -167,7 +206,8 @@ __global__ void __launch_bounds__(K1_THREADS, MINB)
             issue(t);
     }
 
-    // query rows -> registers (coalesced 128-bit loads; rows past n_q read row n_q-1 and are never written back)
+    // query rows -> registers (128-bit loads; rows past n_q read row n_q-1: same distances as the real last row
+    // but a larger slot, so they never win a column and are never written back)
     uint32_t q[Q][16];
     const uint32_t q_base = qtile * (K1_THREADS * Q);
 #pragma unroll
@@ -183,10 +223,10 @@ __global__ void __launch_bounds__(K1_THREADS, MINB)
             q[j][4 * v + 0] = x.x, q[j][4 * v + 1] = x.y, q[j][4 * v + 2] = x.z, q[j][4 * v + 3] = x.w;
         }
     }
-    uint32_t m1[Q], m2[Q];
+    uint32_t s1[Q], s2[Q], bi[Q]; // two smallest values, candidate position (within this item) of the first minimum
 #pragma unroll
     for (int j = 0; j < Q; j++)
-        m1[j] = m2[j] = 0xFFFFFFFFu;
+        s1[j] = s2[j] = K1_NONE, bi[j] = 0;
 
     for (uint32_t t = 0; t < ntiles; t++)
     {
@@ -200,22 +240,38 @@ __global__ void __launch_bounds__(K1_THREADS, MINB)
         {
             uint4 c[4];
             c[0] = tl[cc * 4 + 0], c[1] = tl[cc * 4 + 1], c[2] = tl[cc * 4 + 2], c[3] = tl[cc * 4 + 3];
-            uint32_t key[Q];
+            uint32_t v[Q];
             bool any = false;
 #pragma unroll
             for (int j = 0; j < Q; j++)
             {
-                key[j] = hamming_key<F>(q[j], c, k0 + cc);
-                any |= key[j] < m2[j];
+                v[j] = hamming_value<F, IMADACC>(q[j], c, (uint32_t)(j * K1_THREADS) + tid, w);
+                any |= v[j] < s2[j];
             }
             if (__any_sync(0xFFFFFFFFu, any))
             {
 #pragma unroll
                 for (int j = 0; j < Q; j++)
                 {
-                    const uint32_t hi = max(m1[j], key[j]);
-                    m1[j] = min(m1[j], key[j]);
-                    m2[j] = min(m2[j], hi);
+                    // match_features.cpp:80-92 on values that differ only by distance within one query
+                    const bool better = v[j] < s1[j];
+                    s2[j] = min(s2[j], max(s1[j], v[j]));
+                    s1[j] = min(s1[j], v[j]);
+                    bi[j] = better ? k0 + cc : bi[j];
+                }
+            }
+            if constexpr (COL)
+            {
+                uint32_t cm = v[0];
+#pragma unroll
+                for (int j = 1; j < Q; j++)
+                    cm = min(cm, v[j]);
+                cm = __reduce_min_sync(0xFFFFFFFFu, cm);
+                if ((tid & 31) == 0)
+                {
+                    const unsigned long long key =
+                        ((unsigned long long)(cm >> K1_SHIFT) << 32) | (unsigned long long)(q_base + (cm & K1_SLOT_MASK));
+                    atomicMax(&col64[c_begin + k0 + cc], ~key);
                 }
             }
         }
@@ -225,122 +281,123 @@ __global__ void __launch_bounds__(K1_THREADS, MINB)
     }
 
     const uint32_t splits = pp->splits;
+    if (splits == 1)
+    {
 #pragma unroll
-    for (int j = 0; j < Q; j++)
-    {
-        const uint32_t qi = q_base + j * K1_THREADS + tid;
-        if (qi < n_q)
+        for (int j = 0; j < Q; j++)
         {
-            if (splits == 1)
-                pp->out[qi] = finish_keys(m1[j], m2[j], 0);
-            else
-                pp->partial[(size_t)split * n_q + qi] = make_uint2(m1[j], m2[j]);
+            const uint32_t qi = q_base + j * K1_THREADS + tid;
+            if (qi < n_q)
+                pp->out[qi] = make_record(dist_of(s1[j]), dist_of(s2[j]), bi[j]);
         }
-    }
-}
-
-// Top-2 of the union of the per-split (m1,m2) keys, in candidate-position order.
-__global__ void __launch_bounds__(256)
-    k1_merge_kernel(const __grid_constant__ K1Inline inl, const K1Problem *__restrict__ problems, uint32_t n_problems,
-                    const uint32_t *__restrict__ merge_begin_g)
-{
-    const uint32_t *merge_begin = problems ? merge_begin_g : inl.merge_begin;
-    if (!problems)
-        problems = inl.p;
-    // merge_begin[p] = first global query slot of problem p (prefix sum of n_q over split problems, 0 for
-    // unsplit ones which own no slots); merge_begin[n_problems] = total
-    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= merge_begin[n_problems])
-        return;
-    uint32_t lo = 0, hi = n_problems - 1;
-    while (lo < hi)
-    {
-        const uint32_t mid = (lo + hi + 1) >> 1;
-        if (merge_begin[mid] <= g)
-            lo = mid;
-        else
-            hi = mid - 1;
-    }
-    const K1Problem *pp = problems + lo;
-    const uint32_t qi = g - merge_begin[lo];
-    const uint32_t n_q = pp->n_q, splits = pp->splits;
-    const uint32_t span = pp->tiles_per_split * K1_TILE_C;
-    uint64_t a = ~0ull, b = ~0ull; // two smallest (distance, global position) keys
-    for (uint32_t s = 0; s < splits; s++)
-    {
-        const uint2 m = pp->partial[(size_t)s * n_q + qi];
-#pragma unroll
-        for (int w = 0; w < 2; w++)
-        {
-            const uint32_t k = w == 0 ? m.x : m.y;
-            if (k == 0xFFFFFFFFu)
-                continue;
-            const uint64_t key = ((uint64_t)(k >> K1_KEY_SHIFT) << 32) | (uint64_t)(s * span + (k & K1_KEY_IDX_MASK));
-            const uint64_t hi2 = key > a ? key : a;
-            a = key < a ? key : a;
-            b = hi2 < b ? hi2 : b;
-        }
-    }
-    ocb_top2 r;
-    if (a == ~0ull)
-    {
-        r.best_k = 0;
-        r.best_d = OCB_DIST_INF;
+        if (!COL)
+            return;
     }
     else
     {
-        r.best_k = (uint32_t)a;
-        r.best_d = (uint16_t)(a >> 32);
+        // Merge this split into the per-query global state with atomics (no serial tail):
+        //   best64[q] = max over splits of ~((d1 << 32) | position)   == the smallest (distance, position) key
+        //   sec32[q]  = max of ~d over every key that is not the final best: each split's d2, each split's d1 that
+        //               loses on arrival, and each former best at the moment it is displaced.
+        unsigned long long *__restrict__ best64 = pp->best64;
+        uint32_t *__restrict__ sec32 = pp->sec32;
+        unsigned long long old[Q];
+#pragma unroll
+        for (int j = 0; j < Q; j++)
+        {
+            const uint32_t qi = q_base + j * K1_THREADS + tid;
+            old[j] = 0;
+            if (qi < n_q && s1[j] != K1_NONE)
+            {
+                const unsigned long long key =
+                    ((unsigned long long)(s1[j] >> K1_SHIFT) << 32) | (unsigned long long)(c_begin + bi[j]);
+                old[j] = atomicMax(&best64[qi], ~key);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < Q; j++)
+        {
+            const uint32_t qi = q_base + j * K1_THREADS + tid;
+            if (qi < n_q && s1[j] != K1_NONE)
+            {
+                const unsigned long long key =
+                    ((unsigned long long)(s1[j] >> K1_SHIFT) << 32) | (unsigned long long)(c_begin + bi[j]);
+                const unsigned long long oldkey = ~old[j];
+                uint32_t loser = K1_NONE; // distance that becomes a second-best candidate
+                if (oldkey < key)
+                    loser = s1[j] >> K1_SHIFT; // an earlier split already holds a better (distance, position)
+                else if (old[j] != 0)
+                    loser = (uint32_t)(oldkey >> 32); // we displaced the former best
+                if (s2[j] != K1_NONE)
+                    loser = min(loser, s2[j] >> K1_SHIFT);
+                if (loser != K1_NONE)
+                    atomicMax(&sec32[qi], ~loser);
+            }
+        }
     }
-    r.second_d = b == ~0ull ? (uint16_t)OCB_DIST_INF : (uint16_t)(b >> 32);
-    pp->out[qi] = r;
-}
 
-// col_best_q[j] = best_k of row j's own top-2 (second pass of the cross-check), OCB_NO_INDEX if nothing was seen
-__global__ void __launch_bounds__(256)
-    k1_extract_best_kernel(const ocb_top2 *__restrict__ top2, uint32_t n, bool empty, uint32_t *__restrict__ best)
-{
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n)
-        best[i] = (empty || top2[i].best_d == OCB_DIST_INF) ? OCB_NO_INDEX : top2[i].best_k;
-}
-
-int k1_extract_best(const ocb_top2 *d_top2, uint32_t n, bool empty, uint32_t *d_best, cudaStream_t stream)
-{
-    if (n == 0)
-        return 0;
-    k1_extract_best_kernel<<<(n + 255) / 256, 256, 0, stream>>>(d_top2, n, empty, d_best);
-    count_launch();
-    OCB_CUDA(cudaGetLastError());
-    return 0;
+    // ---- tickets: last CTA of a query tile writes its records, last CTA of a split converts its columns ----
+    __threadfence();
+    __syncthreads();
+    if (tid == 0)
+    {
+        ticket[0] = splits > 1 ? atomicAdd(&pp->counters[qtile], 1u) : 0u;
+        ticket[1] = COL ? atomicAdd(&pp->counters[q_tiles + split], 1u) : 0u;
+    }
+    __syncthreads();
+    if (splits > 1 && ticket[0] == splits - 1)
+    {
+        __threadfence();
+#pragma unroll
+        for (int j = 0; j < Q; j++)
+        {
+            const uint32_t qi = q_base + j * K1_THREADS + tid;
+            if (qi < n_q)
+            {
+                const unsigned long long b = ~__ldcg(&pp->best64[qi]); // ~0 (none) when the state is still zero
+                const uint32_t sd = ~__ldcg(&pp->sec32[qi]);
+                const uint32_t d1 = b == ~0ull ? (uint32_t)OCB_DIST_INF : (uint32_t)(b >> 32);
+                pp->out[qi] = make_record(d1, sd == K1_NONE ? (uint32_t)OCB_DIST_INF : sd, (uint32_t)b);
+            }
+        }
+    }
+    if (COL && ticket[1] == q_tiles - 1)
+    {
+        __threadfence();
+        uint32_t *__restrict__ col_out = pp->col_out;
+        for (uint32_t k = c_begin + tid; k < c_end; k += K1_THREADS)
+            col_out[k] = (uint32_t)(~__ldcg(&col64[k])); // zero (nothing seen) -> OCB_NO_INDEX
+    }
 }
 
 // ----------------------------------------------------------------------------------------------------------
 // variants + host-side planning / launch
 // ----------------------------------------------------------------------------------------------------------
+typedef void (*K1Kernel)(const K1Inline, const K1Problem *, uint32_t, uint32_t);
 struct K1Variant
 {
     int q, f;
-    void (*kernel)(const K1Inline, const K1Problem *, uint32_t);
+    K1Kernel plain, col;
     const char *name;
 };
-#define K1V(Q_, F_, MINB_)                                                                                             \
+#define K1V(Q_, F_, A_, MINB_)                                                                                         \
     {                                                                                                                  \
-        Q_, F_, k1_top2_kernel<Q_, F_, MINB_>, "q" #Q_ "f" #F_                                                         \
+        Q_, F_, k1_top2_kernel<Q_, F_, A_, false, MINB_>, k1_top2_kernel<Q_, F_, A_, true, MINB_>,                     \
+            "q" #Q_ "f" #F_ "a" #A_                                                                                    \
     }
 static const K1Variant k1_variants[] = {
-    K1V(4, 7, 4),  // 0: default
-    K1V(4, 0, 4),  // 1: plain 16-POPC form (the "naive POPC roofline" shape)
-    K1V(4, 5, 4),  // 2
-    K1V(4, 6, 4),  // 3
-    K1V(4, 8, 4),  // 4
-    K1V(4, 9, 4),  // 5
-    K1V(4, 11, 4), // 6
-    K1V(2, 7, 6),  // 7
-    K1V(2, 8, 6),  // 8
-    K1V(3, 7, 5),  // 9
-    K1V(3, 8, 5),  // 10
-    K1V(2, 0, 6),  // 11
+    K1V(4, 7, true, 4),   // 0: default (best with the fused cross-check on B200)
+    K1V(4, 0, false, 4),  // 1: plain 16-POPC form (the "naive POPC roofline" shape)
+    K1V(4, 7, false, 4),  // 2: compiler-chosen accumulation (IADD3/LEA on the ALU pipe)
+    K1V(4, 8, true, 4),   // 3
+    K1V(4, 8, false, 4),  // 4
+    K1V(4, 9, true, 4),   // 5
+    K1V(4, 6, true, 4),   // 6
+    K1V(4, 11, true, 4),  // 7
+    K1V(3, 8, true, 4),   // 8
+    K1V(2, 8, true, 5),   // 9
+    K1V(3, 9, true, 4),   // 10
+    K1V(4, 10, true, 4),  // 11
 };
 constexpr int K1_NUM_VARIANTS = sizeof(k1_variants) / sizeof(k1_variants[0]);
 
@@ -357,49 +414,85 @@ int k1_queries_per_cta()
     return current_variant().q * K1_THREADS;
 }
 
-K1Plan k1_plan(K1Problem *problems, size_t n, size_t *partial_elems, int sms)
+static int resident_ctas_per_sm(const K1Variant &v)
+{
+    static int cache[K1_NUM_VARIANTS] = {0};
+    const int idx = (int)(&v - k1_variants);
+    if (cache[idx] == 0)
+    {
+        int n = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, v.col, K1_THREADS, 0) != cudaSuccess || n <= 0)
+        {
+            cudaGetLastError();
+            n = 4;
+        }
+        cache[idx] = n;
+    }
+    return cache[idx];
+}
+
+K1Plan k1_plan(K1Problem *problems, size_t n, int sms, int items_per_sm)
 {
     K1Plan plan;
-    const uint32_t tq = (uint32_t)k1_queries_per_cta();
+    const K1Variant &v = current_variant();
+    const uint32_t tq = (uint32_t)(v.q * K1_THREADS);
     uint64_t base_items = 0;
     for (size_t p = 0; p < n; p++)
     {
         problems[p].q_tiles = (problems[p].n_q + tq - 1) / tq;
         base_items += problems[p].q_tiles;
     }
-    // Split the candidate axis only as far as needed to give every SM `k1_items_per_sm` work items.
-    const uint64_t target = (uint64_t)sms * (uint64_t)std::max(1, options().k1_items_per_sm);
-    const uint32_t want_splits = base_items == 0 ? 1 : (uint32_t)std::min<uint64_t>((target + base_items - 1) / base_items, 1u << 16);
+    // Split the candidate axis (at row granularity) only as far as needed to give every SM ~items_per_sm work
+    // items, and so that the equal-sized items fill a whole number of waves of resident CTAs (no ragged tail).
+    if (items_per_sm <= 0)
+        items_per_sm = std::max(1, options().k1_items_per_sm);
+    uint64_t target = (uint64_t)sms * (uint64_t)items_per_sm;
+    const uint64_t slots = (uint64_t)sms * (uint64_t)(items_per_sm >= (1 << 20) ? 1 : resident_ctas_per_sm(v));
+    if (target >= slots)
+        target = target / slots * slots;
+    const uint32_t want_splits =
+        base_items == 0 ? 1 : (uint32_t)std::min<uint64_t>(std::max<uint64_t>(target / base_items, 1), 1u << 16);
     uint32_t item = 0;
     for (size_t p = 0; p < n; p++)
     {
         K1Problem &P = problems[p];
-        const uint32_t ctiles = (P.n_c + K1_TILE_C - 1) / K1_TILE_C;
-        uint32_t splits = std::max(1u, std::min(want_splits, ctiles));
-        uint32_t tps = ctiles == 0 ? 1 : (ctiles + splits - 1) / splits;
-        if (tps > K1_MAX_TILES_PER_SPLIT - 1)
-            tps = K1_MAX_TILES_PER_SPLIT - 1;
-        splits = ctiles == 0 ? 1 : (ctiles + tps - 1) / tps;
+        uint32_t rps = P.n_c == 0 ? 1 : (P.n_c + want_splits - 1) / want_splits;
+        rps = std::max(rps, std::min<uint32_t>(P.n_c, K1_MIN_ROWS_PER_SPLIT));
+        rps = std::max(1u, std::min(rps, (1u << K1_SHIFT) - 1));
+        const uint32_t splits = P.n_c == 0 ? 1 : (P.n_c + rps - 1) / rps;
         P.splits = splits;
-        P.tiles_per_split = tps;
+        P.rows_per_split = rps;
         P.item_begin = item;
         item += P.q_tiles * splits;
-        partial_elems[p] = splits > 1 ? (size_t)splits * P.n_q : 0;
-        plan.any_split |= splits > 1;
+        plan.any_col |= P.col_out != nullptr;
     }
     plan.total_items = item;
     return plan;
 }
 
-void k1_merge_begin(const K1Problem *problems, size_t n, uint32_t *merge_begin)
+size_t k1_state_bytes(const K1Problem &P)
 {
-    uint32_t acc = 0;
-    for (size_t p = 0; p < n; p++)
-    {
-        merge_begin[p] = acc;
-        acc += problems[p].splits > 1 ? problems[p].n_q : 0;
-    }
-    merge_begin[n] = acc;
+    // [tickets: q_tiles + splits u32][best64: n_q u64][sec32: n_q u32][col64: n_c u64], each 8-byte aligned
+    size_t b = 0;
+    if (P.splits > 1 || P.col_out)
+        b += ((size_t)P.q_tiles + P.splits + 1) / 2 * 8;
+    if (P.splits > 1)
+        b += (size_t)P.n_q * 8 + ((size_t)P.n_q + 1) / 2 * 8;
+    if (P.col_out)
+        b += (size_t)P.n_c * 8;
+    return b;
+}
+void k1_bind_state(K1Problem &P, void *d_state)
+{
+    char *p = static_cast<char *>(d_state);
+    P.counters = reinterpret_cast<uint32_t *>(p);
+    if (P.splits > 1 || P.col_out)
+        p += ((size_t)P.q_tiles + P.splits + 1) / 2 * 8;
+    P.best64 = reinterpret_cast<unsigned long long *>(p);
+    P.sec32 = reinterpret_cast<uint32_t *>(p + (P.splits > 1 ? (size_t)P.n_q * 8 : 0));
+    if (P.splits > 1)
+        p += (size_t)P.n_q * 8 + ((size_t)P.n_q + 1) / 2 * 8;
+    P.col64 = P.col_out ? reinterpret_cast<unsigned long long *>(p) : nullptr;
 }
 
 int k1_launch(const K1Problem *d_problems, const K1Problem *h_problems, size_t n, const K1Plan &plan,
@@ -410,32 +503,16 @@ int k1_launch(const K1Problem *d_problems, const K1Problem *h_problems, size_t n
     const K1Variant &v = current_variant();
     K1Inline inl;
     memset(&inl, 0, sizeof inl);
-    const bool use_inline = n <= (size_t)K1_INLINE;
-    if (use_inline)
+    if (n <= (size_t)K1_INLINE)
     {
         for (size_t p = 0; p < n; p++)
             inl.p[p] = h_problems[p];
-        k1_merge_begin(h_problems, n, inl.merge_begin);
         d_problems = nullptr;
     }
-    v.kernel<<<plan.total_items, K1_THREADS, 0, stream>>>(inl, d_problems, (uint32_t)n);
+    K1Kernel k = plan.any_col ? v.col : v.plain;
+    k<<<plan.total_items, K1_THREADS, 0, stream>>>(inl, d_problems, (uint32_t)n, 1u << K1_SHIFT);
     count_launch();
     OCB_CUDA(cudaGetLastError());
-    if (plan.any_split)
-    {
-        // for uploaded tables merge_begin lives right behind the n problems (the C-ABI layer lays it out so)
-        const uint32_t *d_merge_begin = use_inline ? nullptr : reinterpret_cast<const uint32_t *>(d_problems + n);
-        uint64_t total = 0;
-        for (size_t p = 0; p < n; p++)
-            total += h_problems[p].splits > 1 ? h_problems[p].n_q : 0;
-        if (total > 0)
-        {
-            const uint32_t blocks = (uint32_t)((total + 255) / 256);
-            k1_merge_kernel<<<blocks, 256, 0, stream>>>(inl, d_problems, (uint32_t)n, d_merge_begin);
-            count_launch();
-            OCB_CUDA(cudaGetLastError());
-        }
-    }
     return 0;
 }
 

@@ -313,21 +313,13 @@ extern "C"
     // ---------------------------------------------------------------------------------------------------
     size_t ocb_match_top2_workspace_bytes(size_t n1, size_t n2, int with_col_best)
     {
-        // worst case: every candidate tile its own split
-        K1Problem pr[2];
-        memset(pr, 0, sizeof pr);
-        pr[0].n_q = (uint32_t)n1, pr[0].n_c = (uint32_t)n2;
-        pr[1].n_q = (uint32_t)n2, pr[1].n_c = (uint32_t)n1;
-        size_t pe[2] = {0, 0};
-        k1_plan(pr, with_col_best ? 2 : 1, pe, 148 * 4);
-        Carver cv;
-        cv.take(pe[0] * sizeof(uint2));
-        if (with_col_best)
-        {
-            cv.take(n2 * sizeof(ocb_top2));
-            cv.take(pe[1] * sizeof(uint2));
-        }
-        return cv.off + 256;
+        // worst case of the planner: every candidate tile its own split
+        K1Problem pr;
+        memset(&pr, 0, sizeof pr);
+        pr.n_q = (uint32_t)n1, pr.n_c = (uint32_t)n2;
+        pr.col_out = with_col_best ? reinterpret_cast<uint32_t *>(16) : nullptr;
+        k1_plan(&pr, 1, 148, 1 << 20);
+        return align_up(k1_state_bytes(pr), 256) + 256;
     }
 
     int ocb_match_top2_device(const void *d_q, size_t n1, const void *d_c, size_t n2, void *d_out,
@@ -342,46 +334,28 @@ extern "C"
             return fail_invalid("device pointers must be 16-byte aligned (workspace 256)");
         int dev = 0;
         OCB_CUDA(cudaGetDevice(&dev));
-        const bool col = d_col_best_q != nullptr;
-        K1Problem pr[2];
-        memset(pr, 0, sizeof pr);
-        pr[0].q = static_cast<const uint4 *>(d_q), pr[0].n_q = (uint32_t)n1;
-        pr[0].c = static_cast<const uint4 *>(d_c), pr[0].n_c = (uint32_t)n2;
-        pr[0].out = static_cast<ocb_top2 *>(d_out);
-        pr[1].q = pr[0].c, pr[1].n_q = (uint32_t)n2;
-        pr[1].c = pr[0].q, pr[1].n_c = (uint32_t)n1;
-        size_t pe[2] = {0, 0};
-        const size_t np = col ? 2 : 1;
-        K1Plan plan = k1_plan(pr, np, pe, sm_count(dev));
-        Carver cv;
-        char *ws = static_cast<char *>(d_workspace);
-        const size_t o_p0 = cv.take(pe[0] * sizeof(uint2));
-        size_t o_out1 = 0, o_p1 = 0;
-        if (col)
-        {
-            o_out1 = cv.take(n2 * sizeof(ocb_top2));
-            o_p1 = cv.take(pe[1] * sizeof(uint2));
-        }
-        if (cv.off > workspace_bytes)
-            return fail_invalid("workspace too small");
-        pr[0].partial = reinterpret_cast<uint2 *>(ws + o_p0);
-        if (col)
-        {
-            pr[1].out = reinterpret_cast<ocb_top2 *>(ws + o_out1);
-            pr[1].partial = reinterpret_cast<uint2 *>(ws + o_p1);
-        }
         cudaStream_t st = static_cast<cudaStream_t>(stream);
-        int rc = k1_launch(nullptr, pr, np, plan, st);
-        if (rc)
-            return rc;
-        if (col && n2)
+        const bool col = d_col_best_q != nullptr && n2 > 0;
+        if (col && n1 == 0) // no query: every column is empty and no CTA runs
         {
-            // col_best_q[j] = best_k of candidate j's own top-2 over the queries (OCB_NO_INDEX when n1 == 0)
-            rc = k1_extract_best(pr[1].out, (uint32_t)n2, n1 == 0, static_cast<uint32_t *>(d_col_best_q), st);
-            if (rc)
-                return rc;
+            OCB_CUDA(cudaMemsetAsync(d_col_best_q, 0xFF, n2 * sizeof(uint32_t), st));
+            return 0;
         }
-        return 0;
+        K1Problem pr;
+        memset(&pr, 0, sizeof pr);
+        pr.q = static_cast<const uint4 *>(d_q), pr.n_q = (uint32_t)n1;
+        pr.c = static_cast<const uint4 *>(d_c), pr.n_c = (uint32_t)n2;
+        pr.out = static_cast<ocb_top2 *>(d_out);
+        pr.col_out = col ? static_cast<uint32_t *>(d_col_best_q) : nullptr;
+        K1Plan plan = k1_plan(&pr, 1, sm_count(dev));
+        // workspace = the kernel's state block (tickets, merge state, column keys), zeroed every call
+        const size_t zero_bytes = k1_state_bytes(pr);
+        if (zero_bytes > workspace_bytes)
+            return fail_invalid("workspace too small");
+        k1_bind_state(pr, d_workspace);
+        if (zero_bytes)
+            OCB_CUDA(cudaMemsetAsync(d_workspace, 0, zero_bytes, st));
+        return k1_launch(nullptr, &pr, 1, plan, st);
     }
 
     int ocb_match_top2(const uint64_t *q, size_t n1, const uint64_t *c, size_t n2, ocb_top2 *out, uint32_t *col_best_q)
@@ -529,17 +503,16 @@ extern "C"
                 out_end = std::max(out_end, out_offsets[p] + a->second.n);
             }
         }
-        std::vector<size_t> pe(n_pairs);
-        K1Plan plan = k1_plan(pr.data(), n_pairs, pe.data(), sm_count(cx.device));
+        K1Plan plan = k1_plan(pr.data(), n_pairs, sm_count(cx.device));
         if ((uint64_t)plan.total_items >= 0x7FFFFFFFull)
             return fail_invalid("too many work items for one submission");
-        const size_t table_bytes = sizeof(K1Problem) * n_pairs + sizeof(uint32_t) * (n_pairs + 1);
-        size_t partial_total = 0;
+        const size_t table_bytes = sizeof(K1Problem) * n_pairs;
+        size_t state_total = 0;
         for (size_t p = 0; p < n_pairs; p++)
-            partial_total += pe[p];
+            state_total += align_up(k1_state_bytes(pr[p]), 16);
         Carver cv;
         const size_t o_tab = cv.take(table_bytes), o_out = cv.take(out_end * sizeof(ocb_top2));
-        const size_t o_part = cv.take(partial_total * sizeof(uint2));
+        const size_t o_state = cv.take(state_total);
         rc = cx.dev_reserve(cv.off);
         if (rc)
             return rc;
@@ -550,20 +523,20 @@ extern "C"
             return rc;
         char *d = static_cast<char *>(cx.dev.p);
         char *hp = static_cast<char *>(cx.pinned.p);
-        size_t part_off = 0;
+        size_t state_off = 0;
         for (size_t p = 0; p < n_pairs; p++)
         {
             pr[p].out = reinterpret_cast<ocb_top2 *>(d + o_out) + out_offsets[p];
-            pr[p].partial = reinterpret_cast<uint2 *>(d + o_part) + part_off;
-            part_off += pe[p];
+            k1_bind_state(pr[p], d + o_state + state_off);
+            state_off += align_up(k1_state_bytes(pr[p]), 16);
         }
-        K1Problem *h_tab = reinterpret_cast<K1Problem *>(hp + s_tab);
-        memcpy(h_tab, pr.data(), sizeof(K1Problem) * n_pairs);
-        k1_merge_begin(pr.data(), n_pairs, reinterpret_cast<uint32_t *>(h_tab + n_pairs));
+        if (state_total)
+            OCB_CUDA(cudaMemsetAsync(d + o_state, 0, state_total, cx.stream));
         const K1Problem *d_tab = nullptr;
         if (n_pairs > (size_t)K1_INLINE)
         {
-            OCB_CUDA(cudaMemcpyAsync(d + o_tab, h_tab, table_bytes, cudaMemcpyHostToDevice, cx.stream));
+            memcpy(hp + s_tab, pr.data(), table_bytes);
+            OCB_CUDA(cudaMemcpyAsync(d + o_tab, hp + s_tab, table_bytes, cudaMemcpyHostToDevice, cx.stream));
             d_tab = reinterpret_cast<const K1Problem *>(d + o_tab);
         }
         rc = k1_launch(d_tab, pr.data(), n_pairs, plan, cx.stream);

@@ -46,40 +46,42 @@ int sm_count(int device);
 // One (query set, candidate set) problem of a launch. All pointers are device pointers.
 struct K1Problem
 {
-    const uint4 *q;        // [n_q][4] uint4 = 64-byte rows
-    const uint4 *c;        // [n_c][4]
-    ocb_top2 *out;         // [n_q]
-    uint2 *partial;        // [splits][n_q] (m1,m2) keys; used when splits > 1
-    uint32_t n_q, n_c;     //
-    uint32_t q_tiles;      // ceil(n_q / queries per CTA)
-    uint32_t splits;       // candidate-axis splits
-    uint32_t tiles_per_split; // candidate tiles (TILE_C rows) per split
-    uint32_t item_begin;   // index of this problem's first work item in the launch
+    const uint4 *q;             // [n_q][4] uint4 = 64-byte rows
+    const uint4 *c;             // [n_c][4]
+    ocb_top2 *out;              // [n_q]
+    // state, zero before the launch (see k1_state_bytes / k1_bind_state):
+    uint32_t *counters;         // [q_tiles + splits] tickets; used when splits > 1 or col_out
+    unsigned long long *best64; // [n_q] complemented (distance, position) of the best so far; splits > 1
+    uint32_t *sec32;            // [n_q] complemented second-best distance; splits > 1
+    unsigned long long *col64;  // [n_c] complemented (distance, query) keys; cross-check only
+    uint32_t *col_out;          // [n_c] best query position per candidate (cross-check), or nullptr
+    uint32_t n_q, n_c;          //
+    uint32_t q_tiles;           // ceil(n_q / queries per CTA)
+    uint32_t splits;            // candidate-axis splits
+    uint32_t rows_per_split;    // candidate rows per split
+    uint32_t item_begin;        // index of this problem's first work item in the launch
 };
 
 constexpr int K1_INLINE = 2; // problems that fit in the kernel parameters
 struct K1Inline
 {
     K1Problem p[K1_INLINE];
-    uint32_t merge_begin[K1_INLINE + 1];
 };
 
 struct K1Plan
 {
     uint32_t total_items = 0;
-    bool any_split = false;
+    bool any_col = false;
 };
-// Fills q_tiles / splits / tiles_per_split / item_begin of each problem; returns bytes of partial storage
-// needed per problem through partial_elems[p] (in uint2 elements; 0 when splits == 1).
-K1Plan k1_plan(K1Problem *problems, size_t n, size_t *partial_elems, int sms);
-// Enqueues the top-2 kernel (+ merge kernel when any problem is split) for `n` problems whose table
-// already lives at d_problems (device copy of `problems`).
+// Fills q_tiles / splits / rows_per_split / item_begin of each problem (n_q, n_c, col_out must be set).
+K1Plan k1_plan(K1Problem *problems, size_t n, int sms, int items_per_sm = 0); // 0: options().k1_items_per_sm
+size_t k1_state_bytes(const K1Problem &P);          // bytes of zero-initialised state a planned problem needs
+void k1_bind_state(K1Problem &P, void *d_state);    // point counters / best64 / sec32 / col64 into that block
+// Enqueues the single K1 kernel for `n` problems. d_problems = device copy of the table (ignored when
+// n <= K1_INLINE: the table then travels in the kernel parameters).
 int k1_launch(const K1Problem *d_problems, const K1Problem *h_problems, size_t n, const K1Plan &plan,
               cudaStream_t stream);
-int k1_extract_best(const ocb_top2 *d_top2, uint32_t n, bool empty, uint32_t *d_best, cudaStream_t stream);
 int k1_queries_per_cta();
-// merge_begin[p] = first merge slot of problem p (prefix sum of n_q over split problems), n+1 entries.
-void k1_merge_begin(const K1Problem *problems, size_t n, uint32_t *merge_begin);
 
 // ---- K2/K3 launch interface (score_models.cu) ---------------------------------------------------------------
 int k2_prepare(const double *d_corr7, const uint32_t *d_order, size_t n, double *d_corr4, uint32_t *d_pos,

@@ -103,7 +103,7 @@ def test_device_resident_entry_point(gpu, oracle):
     gpu.match_top2_device(dq.data_ptr(), n1, dc.data_ptr(), n2, dout.data_ptr(), dcol.data_ptr(), wsp, wsb,
                           torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
-    assert gpu.kernel_launches() - before >= 2  # our kernels ran (top-2 [+ merge] + extract)
+    assert gpu.kernel_launches() - before == 1  # one fused kernel: top-2, split merge and cross-check
     r = dout.cpu().numpy().view(gpu.TOP2_DTYPE)
     assert_top2_equal(r, oracle.match_top2(a, b))
     assert np.array_equal(dcol.cpu().numpy().view(np.uint32), oracle.match_col_best(a, b))

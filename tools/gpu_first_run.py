@@ -49,7 +49,7 @@ ws = torch.zeros(ws_bytes + 4096, dtype=torch.uint8, device="cuda")
 wsp = (ws.data_ptr() + 255) // 256 * 256
 st = torch.cuda.current_stream().cuda_stream
 res = {}
-for items in (4, 8, 16, 32):
+for items in (8, 16, 24):
     capi.set_option("k1_items_per_sm", items)
     for v in range(12):
         capi.set_option("k1_variant", v)
@@ -64,8 +64,18 @@ for items in (4, 8, 16, 32):
         ms = e0.elapsed_time(e1) / 10
         r = dout.cpu().numpy().view(capi.TOP2_DTYPE)
         good = np.array_equal(r["best_k"][:512], bk) and np.array_equal(r["best_d"][:512], bd) and np.array_equal(r["second_d"][:512], sd)
-        res[f"v{v}_i{items}"] = dict(ms=ms, gcmp=1e8 / ms / 1e6, ok=bool(good))
-        print(f"K1 variant {v} items/SM {items}: {ms:.4f} ms  {1e8/ms/1e6:.1f} Gcmp/s ok={good}", flush=True)
+        dcol = torch.zeros(10000, dtype=torch.int32, device="cuda")
+        wsb2 = capi.match_top2_workspace_bytes(10000, 10000, True)
+        ws2 = torch.zeros(wsb2 + 4096, dtype=torch.uint8, device="cuda"); wsp2 = (ws2.data_ptr() + 255) // 256 * 256
+        for _ in range(3):
+            capi.match_top2_device(dq.data_ptr(), 10000, dc.data_ptr(), 10000, dout.data_ptr(), dcol.data_ptr(), wsp2, wsb2, st)
+        torch.cuda.synchronize(); e0.record()
+        for _ in range(10):
+            capi.match_top2_device(dq.data_ptr(), 10000, dc.data_ptr(), 10000, dout.data_ptr(), dcol.data_ptr(), wsp2, wsb2, st)
+        e1.record(); torch.cuda.synchronize()
+        msc = e0.elapsed_time(e1) / 10
+        res[f"v{v}_i{items}"] = dict(ms=ms, gcmp=1e8 / ms / 1e6, ok=bool(good), ms_col=msc)
+        print(f"K1 variant {v} items/SM {items}: {ms:.4f} ms  {1e8/ms/1e6:.1f} Gcmp/s ok={good} | with cross-check {msc:.4f} ms {1e8/msc/1e6:.1f} Gcmp/s", flush=True)
 out["k1_sweep"] = res
 
 # ---- K2 parity + timing
