@@ -131,6 +131,99 @@ __device__ __forceinline__ uint32_t hamming_value(const uint32_t (&q)[16], const
     return v;
 }
 
+// ----------------------------------------------------------------------------------------------------------
+// Prefix form. Both rows are first mapped by the same invertible GF(2)-linear map T (prefix_transform below):
+//     T(r)[2k] = r[0] ^ r[1] ^ ... ^ r[2k]   (k = 1..7),  every other word unchanged.
+// XOR commutes with T, so with x = q ^ c:  T(q)[2k] ^ T(c)[2k] = x[0] ^ ... ^ x[2k] =: s_k, i.e. the SUM output of a
+// chain of 7 full adders (x0,x1,x2), (s_1,x3,x4), ..., (s_6,x13,x14) costs ONE XOR each instead of three XORs and
+// a 3-input XOR. The CARRY of adder k needs its three inputs, but the third is implied by the sum:
+//     maj(a, b, a^b^s) = (a & b) | ((a ^ b) & ~s)            -> one LOP3 (0xD4) on (a, b, s)
+// Level 1 therefore costs 9 + 7 + 7 = 23 LOP3 for 16 words (16 + 14 = 30 in the plain form) and leaves two
+// weight-1 words (s_7, x15) and seven weight-2 words; G further adders reduce the weight-2/4 words as before.
+// ----------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t lop3_carry_implied(uint32_t a, uint32_t b, uint32_t s)
+{
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xD4;" : "=r"(d) : "r"(a), "r"(b), "r"(s));
+    return d;
+}
+
+__device__ __forceinline__ void prefix_transform(uint32_t (&r)[16])
+{
+    r[2] = lop3_xor3(r[0], r[1], r[2]);
+#pragma unroll
+    for (int k = 2; k <= 7; k++)
+        r[2 * k] = lop3_xor3(r[2 * k - 2], r[2 * k - 1], r[2 * k]);
+}
+
+template <int G, bool IMADACC>
+__device__ __forceinline__ uint32_t hamming_value_pfx(const uint32_t (&q)[16], const uint4 (&c4)[4], uint32_t v0, uint32_t w)
+{
+    constexpr int G2 = G < 3 ? G : 3;     // adders on weight-2 words
+    constexpr int G4 = G <= 3 ? 0 : 1;    // adder on weight-4 words
+    const uint32_t c[16] = {c4[0].x, c4[0].y, c4[0].z, c4[0].w, c4[1].x, c4[1].y, c4[1].z, c4[1].w,
+                            c4[2].x, c4[2].y, c4[2].z, c4[2].w, c4[3].x, c4[3].y, c4[3].z, c4[3].w};
+    uint32_t w2[7 + 3];
+    uint32_t w4[3 + 1];
+    uint32_t w8[1];
+    uint32_t a = q[0] ^ c[0];
+    uint32_t s = a; // running sum word
+#pragma unroll
+    for (int k = 1; k <= 7; k++)
+    {
+        const uint32_t b = q[2 * k - 1] ^ c[2 * k - 1];
+        const uint32_t sn = q[2 * k] ^ c[2 * k];
+        w2[k - 1] = lop3_carry_implied(s, b, sn);
+        s = sn;
+    }
+    const uint32_t x15 = q[15] ^ c[15];
+    int h2 = 0, t2 = 7, h4 = 0, t4 = 0, t8 = 0;
+#pragma unroll
+    for (int f = 0; f < G2; f++)
+    {
+        w2[t2++] = lop3_xor3(w2[h2], w2[h2 + 1], w2[h2 + 2]);
+        w4[t4++] = lop3_maj(w2[h2], w2[h2 + 1], w2[h2 + 2]);
+        h2 += 3;
+    }
+#pragma unroll
+    for (int f = 0; f < G4; f++)
+    {
+        w4[t4++] = lop3_xor3(w4[h4], w4[h4 + 1], w4[h4 + 2]);
+        w8[t8++] = lop3_maj(w4[h4], w4[h4 + 1], w4[h4 + 2]);
+        h4 += 3;
+    }
+    uint32_t v = v0;
+    if constexpr (IMADACC)
+    {
+        const uint32_t wa = w, wb = w * 2, wc = w * 4, wd = w * 8;
+        v = mad_u32((uint32_t)__popc(s), wa, v);
+        v = mad_u32((uint32_t)__popc(x15), wa, v);
+#pragma unroll
+        for (int i = h2; i < t2; i++)
+            v = mad_u32((uint32_t)__popc(w2[i]), wb, v);
+#pragma unroll
+        for (int i = h4; i < t4; i++)
+            v = mad_u32((uint32_t)__popc(w4[i]), wc, v);
+#pragma unroll
+        for (int i = 0; i < t8; i++)
+            v = mad_u32((uint32_t)__popc(w8[i]), wd, v);
+    }
+    else
+    {
+        v += ((uint32_t)__popc(s) + (uint32_t)__popc(x15)) * (1u << K1_SHIFT);
+#pragma unroll
+        for (int i = h2; i < t2; i++)
+            v += (uint32_t)__popc(w2[i]) * (2u << K1_SHIFT);
+#pragma unroll
+        for (int i = h4; i < t4; i++)
+            v += (uint32_t)__popc(w4[i]) * (4u << K1_SHIFT);
+#pragma unroll
+        for (int i = 0; i < t8; i++)
+            v += (uint32_t)__popc(w8[i]) * (8u << K1_SHIFT);
+    }
+    return v;
+}
+
 __device__ __forceinline__ const K1Problem *find_problem(const K1Problem *__restrict__ problems, uint32_t n, uint32_t item)
 {
     uint32_t lo = 0, hi = n - 1;
@@ -159,11 +252,12 @@ __device__ __forceinline__ ocb_top2 make_record(uint32_t d1, uint32_t d2, uint32
     return r;
 }
 
-template <int Q, int F, bool IMADACC, bool COL, int MINB>
+template <int Q, int F, bool IMADACC, bool COL, int MINB, bool PFX, bool BF>
 __global__ void __launch_bounds__(K1_THREADS, MINB)
     k1_top2_kernel(const __grid_constant__ K1Inline inl, const K1Problem *__restrict__ problems, uint32_t n_problems,
                    uint32_t w)
 {
+    static_assert(!PFX || F >= 7, "the prefix form starts from the 7-adder chain");
     __shared__ alignas(128) uint4 tile[K1_STAGES][K1_TILE_C * 4];
     __shared__ alignas(8) uint64_t full_bar[K1_STAGES];
     __shared__ uint32_t ticket[2];
@@ -222,16 +316,47 @@ __global__ void __launch_bounds__(K1_THREADS, MINB)
             const uint4 x = __ldg(row + v);
             q[j][4 * v + 0] = x.x, q[j][4 * v + 1] = x.y, q[j][4 * v + 2] = x.z, q[j][4 * v + 3] = x.w;
         }
+        if constexpr (PFX)
+            prefix_transform(q[j]);
     }
     uint32_t s1[Q], s2[Q], bi[Q]; // two smallest values, candidate position (within this item) of the first minimum
 #pragma unroll
     for (int j = 0; j < Q; j++)
         s1[j] = s2[j] = K1_NONE, bi[j] = 0;
 
+    // Prefix form: candidate tile t is mapped by T in place, one row per thread, while tile t-1 is still being
+    // consumed by the other warps; the __syncthreads that retires a stage also publishes the next mapped tile.
+    auto transform_tile = [&](uint32_t t) {
+        const uint32_t rows = min((uint32_t)K1_TILE_C, c_cnt - t * K1_TILE_C);
+        if (tid < rows)
+        {
+            const uint32_t s = t % K1_STAGES;
+            mbar_wait(&full_bar[s], (t / K1_STAGES) & 1);
+            uint4 *row = &tile[s][tid * 4];
+            uint4 a = row[0], b = row[1], c = row[2], d = row[3];
+            a.z = lop3_xor3(a.x, a.y, a.z);
+            b.x = lop3_xor3(a.z, a.w, b.x);
+            b.z = lop3_xor3(b.x, b.y, b.z);
+            c.x = lop3_xor3(b.z, b.w, c.x);
+            c.z = lop3_xor3(c.x, c.y, c.z);
+            d.x = lop3_xor3(c.z, c.w, d.x);
+            d.z = lop3_xor3(d.x, d.y, d.z);
+            row[0] = a, row[1] = b, row[2] = c, row[3] = d;
+            fence_proxy_async_smem(); // these generic-proxy writes precede the next bulk copy into this stage
+        }
+    };
+    if constexpr (PFX)
+    {
+        if (ntiles)
+            transform_tile(0);
+        __syncthreads();
+    }
+
     for (uint32_t t = 0; t < ntiles; t++)
     {
         const uint32_t s = t % K1_STAGES;
-        mbar_wait(&full_bar[s], (t / K1_STAGES) & 1);
+        if constexpr (!PFX)
+            mbar_wait(&full_bar[s], (t / K1_STAGES) & 1);
         const uint32_t rows = min((uint32_t)K1_TILE_C, c_cnt - t * K1_TILE_C);
         const uint4 *__restrict__ tl = &tile[s][0];
         const uint32_t k0 = t * K1_TILE_C;
@@ -241,23 +366,54 @@ __global__ void __launch_bounds__(K1_THREADS, MINB)
             uint4 c[4];
             c[0] = tl[cc * 4 + 0], c[1] = tl[cc * 4 + 1], c[2] = tl[cc * 4 + 2], c[3] = tl[cc * 4 + 3];
             uint32_t v[Q];
-            bool any = false;
-#pragma unroll
-            for (int j = 0; j < Q; j++)
+            if constexpr (BF)
             {
-                v[j] = hamming_value<F, IMADACC>(q[j], c, (uint32_t)(j * K1_THREADS) + tid, w);
-                any |= v[j] < s2[j];
-            }
-            if (__any_sync(0xFFFFFFFFu, any))
-            {
+                // Branch-free form for short candidate runs (a warp carries 32*Q independent minima, so with runs of
+                // a few hundred rows some lane updates at almost every candidate and the vote never skips):
+                // v = distance << 20 | position, so the two smallest values ARE (first minimum, second with
+                // multiplicity) and the position rides along in s1.
+                const uint32_t kidx = k0 + cc;
 #pragma unroll
                 for (int j = 0; j < Q; j++)
                 {
-                    // match_features.cpp:80-92 on values that differ only by distance within one query
-                    const bool better = v[j] < s1[j];
+                    if constexpr (PFX)
+                        v[j] = hamming_value_pfx<F - 7, IMADACC>(q[j], c, kidx, w);
+                    else
+                        v[j] = hamming_value<F, IMADACC>(q[j], c, kidx, w);
                     s2[j] = min(s2[j], max(s1[j], v[j]));
                     s1[j] = min(s1[j], v[j]);
-                    bi[j] = better ? k0 + cc : bi[j];
+                }
+                if constexpr (COL)
+                {
+                    const uint32_t nk = tid - kidx; // position bits -> query slot bits
+#pragma unroll
+                    for (int j = 0; j < Q; j++)
+                        v[j] = v[j] + nk + (uint32_t)(j * K1_THREADS);
+                }
+            }
+            else
+            {
+                bool any = false;
+#pragma unroll
+                for (int j = 0; j < Q; j++)
+                {
+                    if constexpr (PFX)
+                        v[j] = hamming_value_pfx<F - 7, IMADACC>(q[j], c, (uint32_t)(j * K1_THREADS) + tid, w);
+                    else
+                        v[j] = hamming_value<F, IMADACC>(q[j], c, (uint32_t)(j * K1_THREADS) + tid, w);
+                    any |= v[j] < s2[j];
+                }
+                if (__any_sync(0xFFFFFFFFu, any))
+                {
+#pragma unroll
+                    for (int j = 0; j < Q; j++)
+                    {
+                        // match_features.cpp:80-92 on values that differ only by distance within one query
+                        const bool better = v[j] < s1[j];
+                        s2[j] = min(s2[j], max(s1[j], v[j]));
+                        s1[j] = min(s1[j], v[j]);
+                        bi[j] = better ? k0 + cc : bi[j];
+                    }
                 }
             }
             if constexpr (COL)
@@ -271,15 +427,26 @@ __global__ void __launch_bounds__(K1_THREADS, MINB)
                 {
                     const unsigned long long key =
                         ((unsigned long long)(cm >> K1_SHIFT) << 32) | (unsigned long long)(q_base + (cm & K1_SLOT_MASK));
-                    atomicMax(&col64[c_begin + k0 + cc], ~key);
+                    red_max_u64_global(&col64[c_begin + k0 + cc], ~key);
                 }
             }
         }
-        __syncthreads(); // every warp is done with stage s
+        if constexpr (PFX)
+        {
+            if (t + 1 < ntiles)
+                transform_tile(t + 1);
+        }
+        __syncthreads(); // every warp is done with stage s (and, prefix form, tile t+1 is mapped)
         if (tid == 0 && t + K1_STAGES < ntiles)
             issue(t + K1_STAGES);
     }
 
+    if constexpr (BF)
+    {
+#pragma unroll
+        for (int j = 0; j < Q; j++)
+            bi[j] = s1[j] & K1_SLOT_MASK;
+    }
     const uint32_t splits = pp->splits;
     if (splits == 1)
     {
@@ -311,7 +478,7 @@ __global__ void __launch_bounds__(K1_THREADS, MINB)
             {
                 const unsigned long long key =
                     ((unsigned long long)(s1[j] >> K1_SHIFT) << 32) | (unsigned long long)(c_begin + bi[j]);
-                old[j] = atomicMax(&best64[qi], ~key);
+                old[j] = atom_max_u64_global(&best64[qi], ~key);
             }
         }
 #pragma unroll
@@ -331,7 +498,7 @@ __global__ void __launch_bounds__(K1_THREADS, MINB)
                 if (s2[j] != K1_NONE)
                     loser = min(loser, s2[j] >> K1_SHIFT);
                 if (loser != K1_NONE)
-                    atomicMax(&sec32[qi], ~loser);
+                    red_max_u32_global(&sec32[qi], ~loser);
             }
         }
     }
@@ -377,27 +544,27 @@ typedef void (*K1Kernel)(const K1Inline, const K1Problem *, uint32_t, uint32_t);
 struct K1Variant
 {
     int q, f;
-    K1Kernel plain, col;
+    K1Kernel kern[2][2]; // [branch-free update][cross-check]
     const char *name;
 };
-#define K1V(Q_, F_, A_, MINB_)                                                                                         \
+#define K1V(Q_, F_, A_, MINB_, P_)                                                                                     \
     {                                                                                                                  \
-        Q_, F_, k1_top2_kernel<Q_, F_, A_, false, MINB_>, k1_top2_kernel<Q_, F_, A_, true, MINB_>,                     \
-            "q" #Q_ "f" #F_ "a" #A_                                                                                    \
+        Q_, F_,                                                                                                        \
+            {{k1_top2_kernel<Q_, F_, A_, false, MINB_, P_, false>, k1_top2_kernel<Q_, F_, A_, true, MINB_, P_, false>},\
+             {k1_top2_kernel<Q_, F_, A_, false, MINB_, P_, true>, k1_top2_kernel<Q_, F_, A_, true, MINB_, P_, true>}}, \
+            "q" #Q_ "f" #F_ "a" #A_ "p" #P_                                                                            \
     }
 static const K1Variant k1_variants[] = {
-    K1V(4, 7, true, 4),   // 0: default (best with the fused cross-check on B200)
-    K1V(4, 0, false, 4),  // 1: plain 16-POPC form (the "naive POPC roofline" shape)
-    K1V(4, 7, false, 4),  // 2: compiler-chosen accumulation (IADD3/LEA on the ALU pipe)
-    K1V(4, 8, true, 4),   // 3
-    K1V(4, 8, false, 4),  // 4
-    K1V(4, 9, true, 4),   // 5
-    K1V(4, 6, true, 4),   // 6
-    K1V(4, 11, true, 4),  // 7
-    K1V(3, 8, true, 4),   // 8
-    K1V(2, 8, true, 5),   // 9
-    K1V(3, 9, true, 4),   // 10
-    K1V(4, 10, true, 4),  // 11
+    K1V(4, 9, true, 4, true),    // 0: default: prefix form, 9 adders (27 LOP3 + 7 POPC + 7 IMAD per comparison)
+    K1V(4, 0, false, 4, false),  // 1: plain 16-POPC form (the "naive POPC roofline" shape)
+    K1V(4, 7, true, 4, false),   // 2: first-round default: plain carry-save form, 7 adders (30 LOP3 + 9 POPC)
+    K1V(4, 8, true, 4, true),    // 3
+    K1V(4, 10, true, 4, true),   // 4
+    K1V(4, 9, false, 4, true),   // 5: compiler-chosen accumulation (IADD3/LEA on the ALU pipe)
+    K1V(3, 9, true, 4, true),    // 6
+    K1V(3, 9, true, 5, true),    // 7
+    K1V(2, 9, true, 6, true),    // 8
+    K1V(4, 11, true, 4, true),   // 9
 };
 constexpr int K1_NUM_VARIANTS = sizeof(k1_variants) / sizeof(k1_variants[0]);
 
@@ -421,7 +588,7 @@ static int resident_ctas_per_sm(const K1Variant &v)
     if (cache[idx] == 0)
     {
         int n = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, v.col, K1_THREADS, 0) != cudaSuccess || n <= 0)
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, v.kern[1][1], K1_THREADS, 0) != cudaSuccess || n <= 0)
         {
             cudaGetLastError();
             n = 4;
@@ -509,7 +676,15 @@ int k1_launch(const K1Problem *d_problems, const K1Problem *h_problems, size_t n
             inl.p[p] = h_problems[p];
         d_problems = nullptr;
     }
-    K1Kernel k = plan.any_col ? v.col : v.plain;
+    // update form: branch-free while the candidate runs are short (every candidate then updates some lane of a warp),
+    // vote-and-skip when they are long (updates become rare). option k1_update: 0 = by run length, 1 = vote, 2 = branch-free
+    uint32_t min_run = 0xFFFFFFFFu;
+    for (size_t p = 0; p < n; p++)
+        if (h_problems[p].n_c)
+            min_run = std::min(min_run, h_problems[p].rows_per_split);
+    const int upd = options().k1_update;
+    const bool bf = upd == 2 || (upd == 0 && min_run < (uint32_t)std::max(1, options().k1_bf_rows));
+    K1Kernel k = v.kern[bf ? 1 : 0][plan.any_col ? 1 : 0];
     k<<<plan.total_items, K1_THREADS, 0, stream>>>(inl, d_problems, (uint32_t)n, 1u << K1_SHIFT);
     count_launch();
     OCB_CUDA(cudaGetLastError());

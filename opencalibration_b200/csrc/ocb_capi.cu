@@ -287,6 +287,10 @@ extern "C"
             o.k1_items_per_sm = (int)value;
         else if (!strcmp(key, "k2_variant"))
             o.k2_variant = (int)value;
+        else if (!strcmp(key, "k1_update"))
+            o.k1_update = (int)value;
+        else if (!strcmp(key, "k1_bf_rows"))
+            o.k1_bf_rows = (int)value;
         else
             return fail_invalid("unknown option");
         return 0;
@@ -303,6 +307,10 @@ extern "C"
             return o.k1_items_per_sm;
         if (!strcmp(key, "k2_variant"))
             return o.k2_variant;
+        if (!strcmp(key, "k1_update"))
+            return o.k1_update;
+        if (!strcmp(key, "k1_bf_rows"))
+            return o.k1_bf_rows;
         if (!strcmp(key, "k1_queries_per_cta"))
             return k1_queries_per_cta();
         return OCB_E_INVALID;

@@ -37,6 +37,8 @@ struct Options
     int k1_variant = 0;       // 0 = default (see hamming_top2.cu variant table)
     int k1_items_per_sm = 16; // target work items per SM when splitting the candidate axis
     int k2_variant = 0;
+    int k1_update = 0;      // 0 = choose by candidate-run length, 1 = vote-and-skip, 2 = branch-free
+    int k1_bf_rows = 2048;  // runs shorter than this use the branch-free update
 };
 Options &options();
 
@@ -137,6 +139,27 @@ __device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, u
                      smem_u32(smem_dst)),
                  "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
+}
+// orders this thread's generic-proxy shared-memory writes before later async-proxy (bulk copy) accesses
+__device__ __forceinline__ void fence_proxy_async_smem()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+// atomics on addresses known to be global (a generic-address atomicMax compiles to an address-space test plus a
+// shared-memory CAS loop next to the global ATOM)
+__device__ __forceinline__ void red_max_u64_global(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("red.global.max.u64 [%0], %1;" ::"l"(__cvta_generic_to_global(p)), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long atom_max_u64_global(unsigned long long *p, unsigned long long v)
+{
+    unsigned long long old;
+    asm volatile("atom.global.max.u64 %0, [%1], %2;" : "=l"(old) : "l"(__cvta_generic_to_global(p)), "l"(v) : "memory");
+    return old;
+}
+__device__ __forceinline__ void red_max_u32_global(uint32_t *p, uint32_t v)
+{
+    asm volatile("red.global.max.u32 [%0], %1;" ::"l"(__cvta_generic_to_global(p)), "r"(v) : "memory");
 }
 __device__ __forceinline__ uint32_t lop3_xor3(uint32_t a, uint32_t b, uint32_t c)
 {

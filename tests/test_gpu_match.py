@@ -7,7 +7,7 @@ from opencalibration_b200 import synthetic
 
 pytestmark = pytest.mark.gpu
 
-N_VARIANTS = 12
+N_VARIANTS = 10
 
 
 def assert_top2_equal(r, oracle_out):

@@ -9,12 +9,13 @@ from opencalibration_b200 import capi, synthetic
 import oc_oracle as O
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--variants", default="0,1,2,3,4,5,6,7,8,9,10,11")
+ap.add_argument("--variants", default="0,1,2,3,4,5,6,7,8,9")
 ap.add_argument("--items", default="16")
 ap.add_argument("--reps", type=int, default=20)
 ap.add_argument("--col", type=int, default=2)
 ap.add_argument("--n", type=int, default=10000)
 ap.add_argument("--check", type=int, default=1)
+ap.add_argument("--update", default="0")
 args = ap.parse_args()
 capi.init(0)
 n = args.n
@@ -26,11 +27,12 @@ ws = torch.zeros(wsb + 4096, dtype=torch.uint8, device="cuda"); wsp = (ws.data_p
 st = torch.cuda.current_stream().cuda_stream
 if args.check:
     o = O.Oracle(); bk, bd, sd = o.match_top2(a[:256], b); cb = o.match_col_best(a, b[:128])
-for items in [int(x) for x in args.items.split(",")]:
+for upd, items in [(int(u), int(x)) for u in args.update.split(",") for x in args.items.split(",")]:
     capi.set_option("k1_items_per_sm", items)
+    capi.set_option("k1_update", upd)
     for v in [int(x) for x in args.variants.split(",")]:
         capi.set_option("k1_variant", v)
-        line = f"variant {v:2d} items/SM {items:3d}:"
+        line = f"variant {v:2d} items/SM {items:3d} upd {upd}:"
         for col in ([False, True] if args.col == 2 else [bool(args.col)]):
             dcp = dcol.data_ptr() if col else None
             for _ in range(3):
