@@ -82,6 +82,100 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(self.mhz)}
 
 
+# K1 instruction mix of the default variant: per comparison 27 LOP3 + 3 VIMNMX on the ALU pipe
+# (64 lanes/clk/SM), 7 POPC on the XU pipe (16 lanes/clk/SM); the fused cross-check adds ~2.3 ALU ops.
+K1_ALU_OPS, K1_XU_OPS = 32.3, 7.0
+# dram__bytes_read.sum + dram__bytes_write.sum of one K1 launch of this workload, from the committed
+# `ncu --set full` capture (profiles/r1_k1_pfx_ncu_full.csv); null would mean "not captured"
+K1_NCU_DRAM_BYTES = 1508608
+
+
+def roofline(achieved, sm_max, held, peak_src, ms_per_step, peaks):
+    """Bound = the integer pipes (north_star: XOR + POPC, not HBM, not tensor cores). `peak` is the PLAIN form's
+    POPC-pipe roofline (16 XOR + 16 POPC per comparison) so that numbers stay comparable between
+    variants; `mix_peak` is the tighter pipe bound of the instruction mix that actually runs."""
+    popc_peak = 148 * 16 * sm_max * 1e6 / 16 / 1e9  # G comparisons/s: 16 POPC/clk/SM, 16 POPC per comparison
+    mix_clk = max(K1_ALU_OPS / 64.0, K1_XU_OPS / 16.0)  # SM clocks per comparison of the carry-save form
+    mix_peak = 148 * sm_max * 1e6 / mix_clk / 1e9
+    algo_bytes = (N1 + N2) * 64 + N1 * 8 + N2 * 4
+    return {"bound": "int-pipe (popc/alu)", "achieved": achieved, "peak": popc_peak, "unit": UNIT,
+            "frac": achieved / popc_peak, "traffic": K1_NCU_DRAM_BYTES,
+            "peak_source": f"148 SMs x 16 POPC/clk/SM (probed on this pool: 16.0) x {sm_max:.0f} MHz "
+                           f"({peak_src} sm_max_mhz) / 16 POPC per comparison (plain XOR+POPC form)",
+            "frac_at_held_clock": achieved / (148 * 16 * held * 1e6 / 16 / 1e9),
+            "mix_peak": mix_peak, "mix_frac": achieved / mix_peak,
+            "mix": {"alu_ops_per_cmp": K1_ALU_OPS, "xu_ops_per_cmp": K1_XU_OPS,
+                    "note": "prefix carry-save form trades POPCs for LOP3s, so it exceeds the plain-POPC roofline; "
+                            "mix_peak = 148 SMs x clock / max(alu/64, xu/16)"},
+            "hbm": {"achieved_gbs": algo_bytes / (ms_per_step * 1e-3) / 1e9, "peak_gbs": peaks.get("hbm_gbs"),
+                    "algorithmic_bytes_per_step": algo_bytes, "measured_dram_bytes_per_step": K1_NCU_DRAM_BYTES}}
+
+
+def _timed(torch, fn, reps):
+    fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def secondary_measurements(torch, capi, synthetic, stream):
+    """The other configurations of BASELINE.json, reported next to the headline (not bench lines of their own):
+    configs[2] RANSAC scoring 4096 hypotheses x 20000 correspondences (K2/K3, device resident), and a slice of
+    configs[3]: batched pairs of a synthetic aerial grid through ocb_match_pairs (descriptors resident, result
+    lists copied back)."""
+    out = {}
+    # ---- configs[2]
+    H, N = 4096, 20000
+    from opencalibration_b200 import host
+    corr, _H = synthetic.homography_scene(14000, 6000, seed=42)
+    d_corr7 = torch.from_numpy(corr).cuda()
+    d_corr4 = torch.zeros(N * 4, dtype=torch.float64, device="cuda")
+    order = np.random.default_rng(0).permutation(N).astype(np.uint32)
+    d_order = torch.from_numpy(order.view(np.int32)).cuda()
+    d_pos = torch.zeros(N, dtype=torch.int32, device="cuda")
+    capi.prepare_correspondences_device(d_corr7.data_ptr(), d_order.data_ptr(), N, d_corr4.data_ptr(), d_pos.data_ptr(),
+                                        stream)
+    d_score = torch.zeros(H, dtype=torch.float64, device="cuda")
+    d_count = torch.zeros(H, dtype=torch.int32, device="cuda")
+    for kind, name, thr in ((0, "homography", 0.005), (1, "epipolar", 0.01)):
+        if kind == 0:  # hypotheses fitted to random 4-samples, as the RANSAC driver produces them (~24% all-inlier)
+            rng = np.random.default_rng(5)
+            models = np.stack([host.fit(0, corr, rng.choice(N, 4, replace=False).astype(np.uintp)) for _ in range(H)])
+        else:
+            models = synthetic.random_models(kind, H, seed=3)
+        d_models = torch.from_numpy(np.ascontiguousarray(models)).cuda()
+        ms = _timed(torch, lambda: capi.score_models_device(kind, d_models.data_ptr(), H, d_corr4.data_ptr(), None, N,
+                                                            thr, d_score.data_ptr(), d_count.data_ptr(), None, stream), 5)
+        out[f"ransac_scoring_{name}"] = {"workload": "configs[2]: 4096 hypotheses x 20000 correspondences, MSAC in "
+                                                     "evaluation order, fp64 bit-exact", "ms": ms,
+                                         "M_residuals_per_s": H * N / (ms * 1e-3) / 1e6}
+    # ---- configs[3] slice
+    rows, cols, n_desc = 6, 8, 8192
+    images, _pos, pairs = synthetic.grid_survey(rows, cols, n_desc, seed=7)
+    for i, im in enumerate(images):
+        capi.register_descriptors(1000 + i, im)
+    plist = [(1000 + a, 1000 + b) for a, b in pairs]
+    nq = [n_desc] * len(plist)
+    res = np.zeros(len(plist) * n_desc, capi.TOP2_DTYPE)
+    capi.match_pairs(plist[:8], nq[:8], out=res)
+    t0 = time.perf_counter()
+    capi.match_pairs(plist, nq, out=res)
+    secs = time.perf_counter() - t0
+    for i in range(len(images)):
+        capi.unregister_descriptors(1000 + i)
+    out["grid_pairs_batched"] = {"workload": f"configs[3] slice: {rows}x{cols} image grid, {len(plist)} directed pairs "
+                                             f"x {n_desc}x{n_desc} rows, one ocb_match_pairs submission, results to host",
+                                 "pairs_per_s": len(plist) / secs, "Gcmp_per_s": len(plist) * n_desc * n_desc / secs / 1e9,
+                                 "ms": secs * 1e3}
+    return out
+
+
+
 def cpu_reference_run(steps, warmup, threads=0, n2_sample=2500):
     """The reference's CPU path: `threads` pairs per step (one pair per OpenMP worker, pipeline.cpp:42-49), each
     N1 queries x n2_sample candidates of the same synthetic workload (bounded sample of the 10k x 10k pair)."""
@@ -190,7 +284,10 @@ def run_ours(args):
     ms_per_step = total_ms / args.steps
     value = world * cmp_per_step / (ms_per_step * 1e-3) / 1e9
 
-    # ---- e2e: the reference-facing C++ entry point on host vectors (pack, H2D, kernels, D2H, ratio test, sort)
+    # ---- e2e: the reference-facing C++ entry point on host vectors (gather, H2D, kernel, D2H, ratio test, sort).
+    # (a) one caller, one pair at a time; (b) the reference's calling convention: run_parallel executes one
+    # match_features_subset closure per pair on OpenMP workers (src/pipeline/pipeline.cpp:42-49), so several calls
+    # are in flight and one call's host work overlaps another's kernel. Every call copies its inputs and results.
     fa, fb = host.FeatureSet(a), host.FeatureSet(b)
     idx1, idx2 = np.arange(N1, dtype=np.uintp), np.arange(N2, dtype=np.uintp)
     matcher = host.Matcher(N1)
@@ -205,8 +302,22 @@ def run_ours(args):
     e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
     if dist:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_ms = float(e2e_s.item()) * 1e3 / e2e_steps
+    e2e_single_ms = float(e2e_s.item()) * 1e3 / e2e_steps
+    callers = max(1, min(args.callers, (os.cpu_count() or 1) // max(world, 1)))
+    host.run_parallel_handles([fa] * callers, [fb] * callers, threads=callers, cross_check=True, reps=2)
+    conc_steps = max(callers * 2, min(args.steps, 200) // callers * callers)
+    barrier()
+    conc_secs, _ = host.run_parallel_handles([fa] * callers, [fb] * callers, threads=callers, cross_check=True,
+                                             reps=conc_steps // callers)
+    barrier()
+    e2e_s = torch.tensor([conc_secs], dtype=torch.float64, device="cuda")
+    if dist:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_ms = float(e2e_s.item()) * 1e3 / conc_steps
     e2e_value = world * cmp_per_step / (e2e_ms * 1e-3) / 1e9
+    secondary = None
+    if rank == 0 and world == 1 and not args.no_secondary:
+        secondary = secondary_measurements(torch, capi, synthetic, stream)
 
     if rank != 0:
         if dist:
@@ -228,10 +339,8 @@ def run_ours(args):
         cpu = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "as_shipped_flags_value")}
 
     sm_max = float(peaks.get("sm_max_mhz", 1965.0))
-    popc_peak = 148 * 16 * sm_max * 1e6 / 16 / 1e9  # G comparisons/s: 16 POPC/clk/SM, 16 POPC per comparison
     achieved = cmp_per_step / (ms_per_step * 1e-3) / 1e9 if world == 1 else value / world
     held = clocks.get("sm_mhz") or sm_max
-    algo_bytes = (N1 + N2) * 64 + N1 * 8 + N2 * 4
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
@@ -243,21 +352,22 @@ def run_ours(args):
                    "ratio_test_survivors": int(n_matches)},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": (N1 + N2) * 64,
-                "d2h_bytes_per_step": N1 * 8 + N2 * 4, "ms_per_step": e2e_ms, "steps": e2e_steps,
-                "api": "match_features_subset(std::vector<feature_2d>...) + cross-check flags via libocb_host.so",
-                "pairs_per_s": world / (e2e_ms * 1e-3)},
+                "d2h_bytes_per_step": N1 * 8 + N2 * 4, "ms_per_step": e2e_ms, "steps": conc_steps,
+                "api": "match_features_subset(std::vector<feature_2d>...) + cross-check flags via libocb_host.so; "
+                       "one step = one call on one pair, inputs in pageable host vectors, copies inside the call",
+                "concurrent_callers": callers,
+                "calling_convention": "OpenMP workers, one closure per pair, like the reference's run_parallel "
+                                      "(src/pipeline/pipeline.cpp:42-49)",
+                "pairs_per_s": world / (e2e_ms * 1e-3),
+                "single_caller": {"value": world * cmp_per_step / (e2e_single_ms * 1e-3) / 1e9,
+                                  "ms_per_step": e2e_single_ms, "steps": e2e_steps}},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "popc", "achieved": achieved, "peak": popc_peak, "unit": UNIT,
-                     "frac": achieved / popc_peak, "traffic": None,
-                     "peak_source": f"148 SMs x 16 POPC/clk/SM (probed on this pool: 16.0) x {sm_max:.0f} MHz "
-                                    f"({peak_src} sm_max_mhz) / 16 POPC per comparison",
-                     "frac_at_held_clock": achieved / (148 * 16 * held * 1e6 / 16 / 1e9),
-                     "note": "K1 trades POPCs for LOP3 carry-save adders, so it can exceed the plain-POPC roofline",
-                     "hbm": {"achieved_gbs": algo_bytes / (ms_per_step * 1e-3) / 1e9,
-                             "peak_gbs": peaks.get("hbm_gbs"), "algorithmic_bytes_per_step": algo_bytes}},
+        "roofline": roofline(achieved, sm_max, held, peak_src, ms_per_step, peaks),
     }
     if cpu:
         line["cpu_baseline"] = cpu
+    if secondary:
+        line["secondary"] = secondary
     print(json.dumps(line), flush=True)
     if dist:
         dist.destroy_process_group()
@@ -270,6 +380,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true")
+    ap.add_argument("--callers", type=int, default=4, help="concurrent host callers of the e2e measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -93,6 +93,15 @@ extern "C"
     int ocb_match_top2(const uint64_t *q, size_t n1, const uint64_t *c, size_t n2, ocb_top2 *out,
                        uint32_t *col_best_q);
 
+    /* Same search on rows that are NOT contiguous: row k of the query side is the 64 bytes at
+     * rows1 + idx1[k] * stride1 (idx1 == NULL: k * stride1), likewise the candidate side. This is the access
+     * pattern of match_features_subset itself -- set[indices[k]].descriptor inside std::vector<feature_2d>
+     * (sizeof 96, descriptor at +24; src/match/match_features.cpp:62-66,71) -- so the adapter passes the vectors
+     * as they are and the rows are gathered once, straight into page-locked staging. best_k / col_best_q are
+     * POSITIONS k in idx2 / idx1. */
+    int ocb_match_top2_strided(const void *rows1, size_t stride1, const size_t *idx1, size_t n1, const void *rows2,
+                               size_t stride2, const size_t *idx2, size_t n2, ocb_top2 *out, uint32_t *col_best_q);
+
     /* Device-resident variant. d_q, d_c, d_out, d_col_best_q, d_workspace are device pointers;
      * workspace_bytes >= ocb_match_top2_workspace_bytes(n1, n2, d_col_best_q != NULL). */
     size_t ocb_match_top2_workspace_bytes(size_t n1, size_t n2, int with_col_best);

@@ -45,6 +45,7 @@ def lib():
         "ocb_set_option": (i32, [C.c_char_p, C.c_int64]),
         "ocb_get_option": (C.c_int64, [C.c_char_p]),
         "ocb_match_top2": (i32, [vp, sz, vp, sz, vp, vp]),
+        "ocb_match_top2_strided": (i32, [vp, sz, vp, sz, vp, sz, vp, sz, vp, vp]),
         "ocb_match_top2_workspace_bytes": (sz, [sz, sz, i32]),
         "ocb_match_top2_device": (i32, [vp, sz, vp, sz, vp, vp, vp, sz, vp]),
         "ocb_register_descriptors": (i32, [u64, vp, sz]),
@@ -120,6 +121,19 @@ def match_top2(q, c, cross_check=False, out=None, col_out=None):
     return (out, col) if cross_check else out
 
 
+def match_top2_strided(base1, stride1, idx1, base2, stride2, idx2, cross_check=False):
+    """Rows gathered from strided records: base*: uint8 arrays, row k = base[idx[k] * stride : +64] (idx None: k)."""
+    n1 = len(idx1) if idx1 is not None else len(base1) // stride1
+    n2 = len(idx2) if idx2 is not None else len(base2) // stride2
+    i1 = None if idx1 is None else np.ascontiguousarray(idx1, dtype=np.uintp)
+    i2 = None if idx2 is None else np.ascontiguousarray(idx2, dtype=np.uintp)
+    out = np.zeros(n1, TOP2_DTYPE)
+    col = np.zeros(n2, np.uint32) if cross_check else None
+    check(lib().ocb_match_top2_strided(_ptr(base1), stride1, _ptr(i1), n1, _ptr(base2), stride2, _ptr(i2), n2,
+                                       _ptr(out), _ptr(col)))
+    return (out, col) if cross_check else out
+
+
 # ---- K1, device buffers (torch tensors; inputs resident in HBM) ----
 def match_top2_workspace_bytes(n1, n2, cross_check=False):
     return int(lib().ocb_match_top2_workspace_bytes(n1, n2, int(cross_check)))
@@ -174,3 +188,13 @@ def residuals(kind, model18, corr):
     e = np.zeros(len(corr), np.float64)
     check(lib().ocb_residuals(kind, _ptr(model18), _ptr(corr), len(corr), _ptr(e)))
     return e
+
+
+# ---- K2 / K3, device buffers ----
+def prepare_correspondences_device(d_corr7, d_order, n, d_corr4, d_pos, stream):
+    check(lib().ocb_prepare_correspondences_device(d_corr7, d_order, n, d_corr4, d_pos, stream))
+
+
+def score_models_device(kind, d_models, h, d_corr4, d_pos, n, thr, d_score, d_count, d_bits, stream):
+    check(lib().ocb_score_models_device(kind, d_models, h, d_corr4, d_pos, n, float(thr), d_score, d_count, d_bits,
+                                        stream))

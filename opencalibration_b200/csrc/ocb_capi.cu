@@ -421,6 +421,79 @@ extern "C"
         return 0;
     }
 
+    // Gathers rows base[idx[k] * stride .. +64) (idx == NULL: k * stride) into dst.
+    static void gather_rows(char *dst, const void *base, size_t stride, const size_t *idx, size_t n)
+    {
+        const char *b = static_cast<const char *>(base);
+        if (!idx && stride == OCB_ROW_BYTES)
+        {
+            memcpy(dst, b, n * OCB_ROW_BYTES);
+            return;
+        }
+        for (size_t k = 0; k < n; k++)
+            memcpy(dst + k * OCB_ROW_BYTES, b + (idx ? idx[k] : k) * stride, OCB_ROW_BYTES);
+    }
+
+    int ocb_match_top2_strided(const void *rows1, size_t stride1, const size_t *idx1, size_t n1, const void *rows2,
+                               size_t stride2, const size_t *idx2, size_t n2, ocb_top2 *out, uint32_t *col_best_q)
+    {
+        if (n1 >= 0xFFFFFFFFull || n2 >= 0xFFFFFFFFull)
+            return fail_invalid("n1/n2 must fit in 32 bits");
+        if ((n1 && (!rows1 || !out)) || (n2 && !rows2))
+            return fail_invalid("null pointer");
+        if (stride1 < OCB_ROW_BYTES || stride2 < OCB_ROW_BYTES)
+            return fail_invalid("row stride below 64 bytes");
+        ThreadCtx &cx = t_ctx;
+        int rc = cx.ensure();
+        if (rc)
+            return rc;
+        if (n1 == 0 && (n2 == 0 || !col_best_q))
+            return 0;
+        const bool col = col_best_q != nullptr;
+        const size_t qb = n1 * OCB_ROW_BYTES, cb = n2 * OCB_ROW_BYTES;
+        const size_t ws_bytes = ocb_match_top2_workspace_bytes(n1, n2, col);
+        Carver cv;
+        const size_t o_q = cv.take(qb), o_c = cv.take(cb), o_out = cv.take(n1 * sizeof(ocb_top2));
+        const size_t o_col = cv.take(col ? n2 * sizeof(uint32_t) : 0);
+        const size_t o_ws = cv.take(ws_bytes);
+        rc = cx.dev_reserve(cv.off);
+        if (rc)
+            return rc;
+        Carver sv;
+        const size_t s_q = sv.take(qb), s_c = sv.take(cb), s_out = sv.take(n1 * sizeof(ocb_top2));
+        const size_t s_col = sv.take(col ? n2 * sizeof(uint32_t) : 0);
+        rc = cx.pinned_reserve(sv.off);
+        if (rc)
+            return rc;
+        char *d = static_cast<char *>(cx.dev.p);
+        char *hp = static_cast<char *>(cx.pinned.p);
+        // the candidate copy is in flight while the query rows are gathered
+        if (n2)
+        {
+            gather_rows(hp + s_c, rows2, stride2, idx2, n2);
+            OCB_CUDA(cudaMemcpyAsync(d + o_c, hp + s_c, cb, cudaMemcpyHostToDevice, cx.stream));
+        }
+        if (n1)
+        {
+            gather_rows(hp + s_q, rows1, stride1, idx1, n1);
+            OCB_CUDA(cudaMemcpyAsync(d + o_q, hp + s_q, qb, cudaMemcpyHostToDevice, cx.stream));
+        }
+        rc = ocb_match_top2_device(d + o_q, n1, d + o_c, n2, d + o_out, col ? d + o_col : nullptr, d + o_ws, ws_bytes,
+                                   cx.stream);
+        if (rc)
+            return rc;
+        if (n1)
+            OCB_CUDA(cudaMemcpyAsync(hp + s_out, d + o_out, n1 * sizeof(ocb_top2), cudaMemcpyDeviceToHost, cx.stream));
+        if (col && n2)
+            OCB_CUDA(cudaMemcpyAsync(hp + s_col, d + o_col, n2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, cx.stream));
+        OCB_CUDA(cudaStreamSynchronize(cx.stream));
+        if (n1)
+            memcpy(out, hp + s_out, n1 * sizeof(ocb_top2));
+        if (col && n2)
+            memcpy(col_best_q, hp + s_col, n2 * sizeof(uint32_t));
+        return 0;
+    }
+
     // ---------------------------------------------------------------------------------------------------
     // descriptor residency + batched pairs
     // ---------------------------------------------------------------------------------------------------

@@ -65,6 +65,7 @@ def lib():
     L.ocbh_jacobi_svd_tall.argtypes = [_f64p, i32, i32, _f64p, _f64p]
     L.ocbh_jacobi_svd_tall.restype = None
     L.ocbh_run_parallel_match.argtypes = [_u64p, _u64p, sz, sz, sz, i32, _szp, _f64p]
+    L.ocbh_run_parallel_handles.argtypes = [C.c_void_p, C.c_void_p, sz, i32, i32, i32, _szp, _f64p]
     _lib = L
     return L
 
@@ -263,4 +264,15 @@ def run_parallel_match(q, c, n_pairs, n1, n2, threads=0):
     q, c = _rows(q), _rows(c)
     nm, secs = np.zeros(1, np.uintp), np.zeros(1)
     _check(lib().ocbh_run_parallel_match(q, c, n_pairs, n1, n2, threads, nm, secs))
+    return float(secs[0]), int(nm[0])
+
+
+def run_parallel_handles(sets_q, sets_c, threads=0, cross_check=False, reps=1):
+    """reps * len(sets_q) match_features_subset closures over FeatureSets on `threads` OpenMP workers ->
+    (wall seconds, total matches)."""
+    n = len(sets_q)
+    hq = (C.c_void_p * n)(*[s.handle for s in sets_q])
+    hc = (C.c_void_p * n)(*[s.handle for s in sets_c])
+    nm, secs = np.zeros(1, np.uintp), np.zeros(1)
+    _check(lib().ocbh_run_parallel_handles(hq, hc, n, int(threads), int(cross_check), int(reps), nm, secs))
     return float(secs[0]), int(nm[0])

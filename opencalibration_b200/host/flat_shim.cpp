@@ -374,4 +374,56 @@ extern "C"
         *seconds = std::chrono::duration<double>(t1 - t0).count();
         return failed ? -1 : 0;
     }
+    // Same driver on feature sets that already live in host memory (ocbh_features_create), repeated `reps` times:
+    // reps * n_pairs closures, each one match_features_subset (or its cross-checked variant) on all features of
+    // its pair. Used by bench.py for the concurrent-callers end-to-end number.
+    int ocbh_run_parallel_handles(const void *const *hq, const void *const *hc, size_t n_pairs, int threads,
+                                  int cross_check, int reps, size_t *n_matches, double *seconds)
+    {
+        if (threads <= 0)
+            threads = omp_get_num_procs();
+        std::vector<std::vector<size_t>> idx1(n_pairs), idx2(n_pairs);
+        for (size_t p = 0; p < n_pairs; p++)
+        {
+            idx1[p].resize(static_cast<const std::vector<feature_2d> *>(hq[p])->size());
+            idx2[p].resize(static_cast<const std::vector<feature_2d> *>(hc[p])->size());
+            for (size_t i = 0; i < idx1[p].size(); i++)
+                idx1[p][i] = i;
+            for (size_t i = 0; i < idx2[p].size(); i++)
+                idx2[p][i] = i;
+        }
+        size_t total = 0;
+        int failed = 0;
+        const size_t jobs = n_pairs * (size_t)std::max(reps, 1);
+        const auto t0 = std::chrono::steady_clock::now();
+#pragma omp parallel for schedule(dynamic, 1) num_threads(threads) reduction(+ : total)
+        for (size_t job = 0; job < jobs; job++)
+        {
+            const size_t p = job % n_pairs;
+            const auto &f1 = *static_cast<const std::vector<feature_2d> *>(hq[p]);
+            const auto &f2 = *static_cast<const std::vector<feature_2d> *>(hc[p]);
+            try
+            {
+                if (cross_check)
+                {
+                    std::vector<bool> mutual;
+                    total += ocb_host::match_features_subset_cross_checked(f1, f2, idx1[p], idx2[p], mutual).size();
+                }
+                else
+                    total += match_features_subset(f1, f2, idx1[p], idx2[p]).size();
+            }
+            catch (const std::exception &e)
+            {
+#pragma omp critical
+                {
+                    t_err = e.what();
+                    failed = 1;
+                }
+            }
+        }
+        const auto t1 = std::chrono::steady_clock::now();
+        *n_matches = total;
+        *seconds = std::chrono::duration<double>(t1 - t0).count();
+        return failed ? -1 : 0;
+    }
 }

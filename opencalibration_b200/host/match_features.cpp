@@ -15,15 +15,6 @@ namespace
 using opencalibration::feature_2d;
 using opencalibration::feature_match;
 
-// set[indices[k]].descriptor -> contiguous 64-byte rows (what match_features.cpp:62-66 does for set_2)
-std::vector<uint64_t> pack_rows(const std::vector<feature_2d> &set, const std::vector<size_t> &indices)
-{
-    std::vector<uint64_t> rows(indices.size() * OCB_ROW_WORDS);
-    for (size_t k = 0; k < indices.size(); k++)
-        std::memcpy(&rows[k * OCB_ROW_WORDS], static_cast<const void *>(&set[indices[k]].descriptor), OCB_ROW_BYTES);
-    return rows;
-}
-
 inline double as_distance(uint16_t d)
 {
     // distance = count * (1.0 / DESCRIPTOR_BITS)  (match_features.cpp:79); OCB_DIST_INF stands for +infinity
@@ -35,40 +26,45 @@ std::vector<feature_match> run_match(const std::vector<feature_2d> &set_1, const
                                      const std::vector<size_t> &indices_1, const std::vector<size_t> &indices_2,
                                      std::vector<bool> *mutual)
 {
-    const std::vector<uint64_t> q = pack_rows(set_1, indices_1), c = pack_rows(set_2, indices_2);
-    std::vector<ocb_top2> top(indices_1.size());
-    std::vector<uint32_t> col(mutual ? indices_2.size() : 0);
-    ocb_host::detail::gpu_check(ocb_match_top2(q.data(), indices_1.size(), c.data(), indices_2.size(), top.data(),
-                                               mutual ? col.data() : nullptr),
-                                "ocb_match_top2");
-    // Records carry the cross-check flag along; std::sort's sequence of moves depends only on the comparator's
-    // answers, so sorting these by the reference's comparator gives the reference's (unstable) order.
+    // set[indices[k]].descriptor is gathered by the library straight into its page-locked staging area
+    // (what match_features.cpp:62-66 does for set_2 into `packed_2`)
+    static_assert(sizeof(feature_2d::descriptor) == OCB_ROW_BYTES, "bitset<486> is 8 x 64-bit words");
+    const size_t n1 = indices_1.size(), n2 = indices_2.size();
+    std::vector<ocb_top2> top(n1);
+    std::vector<uint32_t> col(mutual ? n2 : 0);
+    const void *rows1 = set_1.empty() ? nullptr : static_cast<const void *>(&set_1[0].descriptor);
+    const void *rows2 = set_2.empty() ? nullptr : static_cast<const void *>(&set_2[0].descriptor);
+    ocb_host::detail::gpu_check(ocb_match_top2_strided(rows1, sizeof(feature_2d), indices_1.data(), n1, rows2,
+                                                       sizeof(feature_2d), indices_2.data(), n2, top.data(),
+                                                       mutual ? col.data() : nullptr),
+                                "ocb_match_top2_strided");
+    // Ratio test in double like the reference (:94), then the reference's std::sort (:100-101). The sort runs on
+    // compact (query position, integer distance) records: std::sort's sequence of comparisons and moves depends
+    // only on the comparator's answers, and a.d > b.d <=> a.d * (1.0 / 486) > b.d * (1.0 / 486) for these
+    // integers, so the permutation is the one the reference's sort produces on its 24-byte records.
     struct Rec
     {
-        feature_match m;
-        bool mutual;
+        uint32_t a;
+        uint32_t d;
     };
     std::vector<Rec> recs;
-    recs.reserve(indices_1.size());
-    for (size_t a = 0; a < indices_1.size(); a++)
+    recs.reserve(n1);
+    for (size_t a = 0; a < n1; a++)
     {
         const double best = as_distance(top[a].best_d), second = as_distance(top[a].second_d);
-        if (best < 0.8 * second) // match_features.cpp:94, in double like the reference
-        {
-            const uint32_t k = top[a].best_k;
-            recs.push_back(Rec{feature_match{indices_1[a], indices_2[k], best}, mutual && col[k] == (uint32_t)a});
-        }
+        if (best < 0.8 * second)
+            recs.push_back(Rec{(uint32_t)a, top[a].best_d});
     }
-    std::sort(recs.begin(), recs.end(),
-              [](const Rec &f1, const Rec &f2) -> bool { return f1.m.distance > f2.m.distance; }); // :100-101
+    std::sort(recs.begin(), recs.end(), [](const Rec &f1, const Rec &f2) -> bool { return f1.d > f2.d; });
     std::vector<feature_match> results(recs.size());
     if (mutual)
         mutual->resize(recs.size());
     for (size_t i = 0; i < recs.size(); i++)
     {
-        results[i] = recs[i].m;
+        const uint32_t a = recs[i].a, k = top[a].best_k;
+        results[i] = feature_match{indices_1[a], indices_2[k], as_distance(top[a].best_d)};
         if (mutual)
-            (*mutual)[i] = recs[i].mutual;
+            (*mutual)[i] = col[k] == a;
     }
     return results;
 }

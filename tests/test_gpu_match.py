@@ -111,6 +111,26 @@ def test_device_resident_entry_point(gpu, oracle):
         gpu.match_top2_device(dq.data_ptr() + 8, n1 - 1, dc.data_ptr(), n2, dout.data_ptr(), None, wsp, wsb, 0)
 
 
+def test_strided_gather_entry_point(gpu, oracle):
+    # rows embedded in 96-byte records at offset 24 (the layout of std::vector<feature_2d>), picked by index lists
+    # with repeats and in arbitrary order -- what match_features_subset hands to the library
+    a, b = synthetic.config2_pair(900, 1100, seed=21)
+    rec1 = np.zeros((900, 96), np.uint8)
+    rec2 = np.zeros((1100, 96), np.uint8)
+    rec1[:, 24:88] = a.view(np.uint8).reshape(900, 64)
+    rec2[:, 24:88] = b.view(np.uint8).reshape(1100, 64)
+    rng = np.random.default_rng(3)
+    idx1 = rng.integers(0, 900, 700).astype(np.uintp)
+    idx2 = rng.permutation(1100)[:1000].astype(np.uintp)
+    r, col = gpu.match_top2_strided(rec1.reshape(-1)[24:], 96, idx1, rec2.reshape(-1)[24:], 96, idx2, cross_check=True)
+    assert_top2_equal(r, oracle.match_top2(a[idx1], b[idx2]))
+    assert np.array_equal(col, oracle.match_col_best(a[idx1], b[idx2]))
+    r = gpu.match_top2_strided(a.view(np.uint8).reshape(-1), 64, None, b.view(np.uint8).reshape(-1), 64, None)
+    assert_top2_equal(r, oracle.match_top2(a, b))
+    r = gpu.match_top2_strided(rec1.reshape(-1)[24:], 96, idx1[:0], rec2.reshape(-1)[24:], 96, idx2)
+    assert len(r) == 0
+
+
 def test_batched_pairs_match_single_calls(gpu, oracle):
     images, pos, pairs = synthetic.grid_survey(3, 3, 700, seed=5)
     images[4] = images[4][:333]  # ragged set sizes
