@@ -219,7 +219,7 @@ def run_reference(args):
             "config": {"workload": WORKLOAD, "n1": N1, "n2": N2},
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "as_shipped_flags_value")},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_ours(args):
@@ -368,12 +368,35 @@ def run_ours(args):
         line["cpu_baseline"] = cpu
     if secondary:
         line["secondary"] = secondary
-    print(json.dumps(line), flush=True)
+    emit(line)
     if dist:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Libraries (NCCL's version banner, for one) write to fd 1; the contract is ONE JSON line on stdout. Everything
+    else goes to stderr: fd 1 is pointed at fd 2 for the duration of the run and emit() writes to the saved fd."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.buffer.write(data)
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)

@@ -54,6 +54,10 @@ def lib():
     L.ocbh_check_degeneracy_f.argtypes = [_f64p, dbl, _f64p, sz, _u8p]
     L.ocbh_decompose_essential.argtypes = [_f64p, _f64p]
     L.ocbh_decompose_essential.restype = None
+    L.ocbh_decompose_homography.argtypes = [_f64p, _f64p, sz, _u8p, _f64p]
+    L.ocbh_decompose_homography.restype = i32
+    L.ocbh_decompose_homography_mat.argtypes = [_f64p, _f64p, _f64p, _f64p]
+    L.ocbh_decompose_homography_mat.restype = i32
     L.ocbh_assemble_inliers.argtypes = [_szp, _szp, _f64p, sz, _u8p, _f64p, sz, _f64p, sz, _f64p, _szp]
     L.ocbh_assemble_inliers.restype = sz
     L.ocbh_full_piv_lu_solve.argtypes = [_f64p, i32, i32, _f64p, _f64p]
@@ -213,6 +217,23 @@ def decompose_essential(M18):
     out = np.zeros(28)
     lib().ocbh_decompose_essential(np.ascontiguousarray(M18, np.float64), out)
     return out.reshape(4, 7)
+
+
+def decompose_homography(M18, corr, inliers):
+    """homography_model::decompose -> (ok, poses [4][8] = qx,qy,qz,qw, tx,ty,tz, score) in the reference's order."""
+    corr = _corr(corr)
+    out = np.full(32, np.nan)
+    inl = np.ascontiguousarray(inliers, np.uint8)
+    ok = lib().ocbh_decompose_homography(np.ascontiguousarray(M18, np.float64), corr, len(corr), inl, out)
+    return bool(ok), out.reshape(4, 8)
+
+
+def decompose_homography_mat(H):
+    """cv::decomposeHomographyMat(H, I) restated: -> (Rs [k][3][3], ts [k][3], ns [k][3])"""
+    H9 = np.ascontiguousarray(np.asarray(H, np.float64).T).ravel()
+    R, t, n = np.zeros(36), np.zeros(12), np.zeros(12)
+    k = lib().ocbh_decompose_homography_mat(H9, R, t, n)
+    return R.reshape(4, 3, 3).transpose(0, 2, 1)[:k].copy(), t.reshape(4, 3)[:k].copy(), n.reshape(4, 3)[:k].copy()
 
 
 def assemble_inliers(m_i1, m_i2, m_dist, inliers, xy1, xy2):

@@ -282,6 +282,30 @@ extern "C"
         }
     }
 
+    // homography_model::decompose -> 4 x (qx,qy,qz,qw, tx,ty,tz, score); returns the reference's bool
+    int ocbh_decompose_homography(const double *M18, const double *corr, size_t n, const uint8_t *inliers,
+                                  double *poses32)
+    {
+        homography_model m;
+        load(m, M18);
+        const std::vector<correspondence> c = make_corr(corr, n);
+        std::array<decomposed_pose, 4> poses;
+        const bool ok = m.decompose(c, make_flags(inliers, n), poses);
+        for (int i = 0; i < 4; i++)
+        {
+            for (int k = 0; k < 4; k++)
+                poses32[8 * i + k] = poses[i].orientation.coeffs()[k];
+            for (int k = 0; k < 3; k++)
+                poses32[8 * i + 4 + k] = poses[i].position[k];
+            poses32[8 * i + 7] = poses[i].score;
+        }
+        return ok ? 1 : 0;
+    }
+    int ocbh_decompose_homography_mat(const double *H9, double *R36, double *t12, double *n12)
+    {
+        return ocb_host::detail::decompose_homography_mat(H9, R36, t12, n12);
+    }
+
     // assembleInliers -> rows of (pixel_1.x, pixel_1.y, pixel_2.x, pixel_2.y) + (idx1, idx2, match_index)
     size_t ocbh_assemble_inliers(const size_t *m_i1, const size_t *m_i2, const double *m_dist, size_t n_matches,
                                  const uint8_t *inliers, const double *xy1, size_t nf1, const double *xy2, size_t nf2,

@@ -31,6 +31,9 @@ bool epipolar_rows_from_inliers(const std::vector<opencalibration::correspondenc
                                 const std::vector<bool> &inliers, size_t minimum,
                                 std::vector<std::array<double, 9>> &rows);
 void rank2_from(const double *in9, double *out9);
+// cv::decomposeHomographyMat(H, I, ...) restated (homography_decompose.cpp): H column-major; up to 4 solutions,
+// R36 column-major 3x3 each, t12, n12; returns the number of solutions (1 for a pure rotation, else 4)
+int decompose_homography_mat(const double *H9, double *R36, double *t12, double *n12);
 
 // Eigen::Quaterniond(Matrix3d) (Shepperd's method as in Eigen/src/Geometry/Quaternion.h); R column-major
 inline Eigen::Quaterniond quaternion_from_rotation(const double *R)
