@@ -15,7 +15,8 @@
  *   - there is no CPU fallback: without a usable CUDA device every compute entry point fails;
  *   - host-buffer entry points are thread-safe and blocking (the reference calls this path concurrently
  *     from OpenMP workers, src/pipeline/pipeline.cpp:42-49); each calling thread gets its own stream and
- *     staging buffers on the device selected by ocb_set_device (default: device 0);
+ *     staging buffers on the device selected by ocb_set_device (default: the device of the process's first
+ *     ocb_init, else device 0);
  *   - *_device entry points take device pointers (16-byte aligned) and a cudaStream_t passed as void*,
  *     enqueue asynchronously and do not synchronise.
  *
@@ -72,7 +73,10 @@ extern "C"
 
     /* ---- lifecycle ------------------------------------------------------------------------------ */
     int ocb_device_count(void);
-    int ocb_init(int device);       /* idempotent; also selects `device` for the calling thread */
+    /* idempotent; selects `device` for the calling thread. The first successful call of the process also makes
+     * `device` the default of every thread that never selects one itself (the reference's OpenMP workers,
+     * src/pipeline/pipeline.cpp:42-49, in a one-process-per-GPU job). */
+    int ocb_init(int device);
     int ocb_set_device(int device); /* device used by the calling thread's host-buffer calls */
     void ocb_shutdown(void);        /* frees cached staging buffers and registered descriptor sets */
     const char *ocb_last_error(void);

@@ -13,6 +13,10 @@ namespace ocb
 {
 
 std::atomic<uint64_t> g_kernel_launches{0};
+// device of threads that never called ocb_init / ocb_set_device themselves (OpenMP workers of a one-process-per-GPU
+// job must land on the process's GPU, not on device 0): set by the first ocb_init of the process
+static std::atomic<int> g_default_device{0};
+static std::atomic<bool> g_default_device_set{false};
 
 static thread_local std::string t_last_error;
 void set_last_error(const std::string &msg)
@@ -66,7 +70,7 @@ struct Buf
 
 struct ThreadCtx
 {
-    int device = 0;
+    int device = -1; // -1: follow the process default
     bool ready = false;
     cudaStream_t stream = nullptr;
     Buf dev, pinned;
@@ -74,6 +78,8 @@ struct ThreadCtx
 
     int ensure()
     {
+        if (device < 0)
+            device = g_default_device.load();
         if (ready && ready_device == device)
         {
             OCB_CUDA(cudaSetDevice(device));
@@ -238,7 +244,10 @@ extern "C"
     int ocb_init(int device)
     {
         t_ctx.device = device;
-        return t_ctx.ensure();
+        const int rc = t_ctx.ensure();
+        if (rc == 0 && !g_default_device_set.exchange(true))
+            g_default_device.store(device);
+        return rc;
     }
 
     int ocb_set_device(int device)

@@ -69,6 +69,18 @@ def lib():
     L.ocbh_jacobi_svd_tall.argtypes = [_f64p, i32, i32, _f64p, _f64p]
     L.ocbh_jacobi_svd_tall.restype = None
     L.ocbh_run_parallel_match.argtypes = [_u64p, _u64p, sz, sz, sz, i32, _szp, _f64p]
+    L.ocbh_image_to_3d.argtypes = [_f64p, sz, _f64p, _f64p]
+    L.ocbh_image_to_3d.restype = None
+    L.ocbh_link_pairs.argtypes = [C.c_void_p, _szp, _f64p, sz, _szp, sz, i32, sz, i32]
+    L.ocbh_link_pairs.restype = C.c_void_p
+    L.ocbh_link_free.argtypes = [C.c_void_p]
+    L.ocbh_link_free.restype = None
+    L.ocbh_link_stats.argtypes = [C.c_void_p, _f64p]
+    L.ocbh_link_stats.restype = None
+    L.ocbh_link_sizes.argtypes = [C.c_void_p, sz, _szp, _szp]
+    L.ocbh_link_sizes.restype = None
+    L.ocbh_link_get.argtypes = [C.c_void_p, sz, _szp, _szp, _f64p, _f64p, C.c_void_p, _f64p, _f64p, _szp]
+    L.ocbh_link_get.restype = None
     L.ocbh_run_parallel_handles.argtypes = [C.c_void_p, C.c_void_p, sz, i32, i32, i32, _szp, _f64p]
     _lib = L
     return L
@@ -297,3 +309,68 @@ def run_parallel_handles(sets_q, sets_c, threads=0, cross_check=False, reps=1):
     nm, secs = np.zeros(1, np.uintp), np.zeros(1)
     _check(lib().ocbh_run_parallel_handles(hq, hc, n, int(threads), int(cross_check), int(reps), nm, secs))
     return float(secs[0]), int(nm[0])
+
+
+# ---- src/distort (host) ----
+def camera8(f, pp, radial=(0, 0, 0), tangential=(0, 0)):
+    """(f, ppx, ppy, k1, k2, k3, p1, p2): the DifferentiableCameraModel<double> members image_to_3d reads."""
+    return np.array([f, pp[0], pp[1], *radial, *tangential], np.float64)
+
+
+def image_to_3d(xy, cam8):
+    xy = np.ascontiguousarray(xy, np.float64).reshape(-1, 2)
+    rays = np.zeros((len(xy), 3))
+    lib().ocbh_image_to_3d(xy, len(xy), np.ascontiguousarray(cam8, np.float64), rays)
+    return rays
+
+
+# ---- batched LinkStage runner (host/link_batch.hpp) ----
+class LinkResults:
+    """Per-pair camera_relations of one link_pairs call (kept on the C++ side; get(p) flattens one pair)."""
+
+    def __init__(self, handle, n_pairs):
+        self.handle, self.n_pairs = handle, n_pairs
+        st = np.zeros(8)
+        lib().ocbh_link_stats(handle, st)
+        self.stats = dict(seconds_subsample_upload=st[0], seconds_match_gpu=st[1], seconds_tail=st[2],
+                          seconds_total=st[3], comparisons=int(st[4]), matches=int(st[5]), ransac_inliers=int(st[6]))
+
+    def sizes(self, p):
+        a, b = np.zeros(1, np.uintp), np.zeros(1, np.uintp)
+        lib().ocbh_link_sizes(self.handle, p, a, b)
+        return int(a[0]), int(b[0])
+
+    def get(self, p):
+        nm, ni = self.sizes(p)
+        i1, i2, d = np.zeros(max(nm, 1), np.uintp), np.zeros(max(nm, 1), np.uintp), np.zeros(max(nm, 1))
+        H9, poses, rt = np.zeros(9), np.zeros(32), C.c_int(0)
+        px, ix = np.zeros((max(ni, 1), 4)), np.zeros((max(ni, 1), 3), np.uintp)
+        lib().ocbh_link_get(self.handle, p, i1, i2, d, H9, C.byref(rt), poses, px, ix)
+        return dict(matches=(i1[:nm].copy(), i2[:nm].copy(), d[:nm].copy()), H=H9.reshape(3, 3).T.copy(),
+                    relation_type=rt.value, poses=poses.reshape(4, 8).copy(), inlier_pixels=px[:ni].copy(),
+                    inlier_idx=ix[:ni].copy())
+
+    def close(self):
+        if self.handle:
+            lib().ocbh_link_free(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+
+def link_pairs(feature_sets, cameras8, pairs, num_sparse=None, threads=0, pairs_per_submission=0, run_ransac=True):
+    """What LinkStage's closures compute for every (image, neighbour) pair (src/pipeline/link_stage.cpp:75-112), for
+    the whole pair list: feature_sets = FeatureSet per image, cameras8 = camera8() per image, pairs = [(i, j)]."""
+    n = len(feature_sets)
+    h = (C.c_void_p * n)(*[s.handle for s in feature_sets])
+    ns = np.zeros(n, np.uintp) if num_sparse is None else np.ascontiguousarray(num_sparse, np.uintp)
+    cams = np.ascontiguousarray(cameras8, np.float64).reshape(n, 8)
+    pr = np.ascontiguousarray(pairs, np.uintp).reshape(-1, 2)
+    res = lib().ocbh_link_pairs(h, ns, cams, n, pr, len(pr), int(threads), int(pairs_per_submission), int(run_ransac))
+    if not res:
+        raise OcbError("host mirror: " + lib().ocbh_last_error().decode())
+    return LinkResults(res, len(pr))

@@ -1,6 +1,7 @@
 // Flat C entry points over the C++ mirror, for ctypes-driven tests and bench.py (opencalibration_b200/host.py).
 // They build the reference-typed arguments (std::vector<feature_2d>, std::vector<correspondence>, model structs),
 // call the mirror exactly as src/pipeline/link_stage.cpp:80-93 would, and flatten the results.
+#include "link_batch.hpp"
 #include "models_detail.hpp"
 
 #include <chrono>
@@ -449,5 +450,101 @@ extern "C"
         *n_matches = total;
         *seconds = std::chrono::duration<double>(t1 - t0).count();
         return failed ? -1 : 0;
+    }
+    // ---- distort_keypoints / image_to_3d: cam8 = (f, ppx, ppy, k1, k2, k3, p1, p2); rays out [n][3]
+    void ocbh_image_to_3d(const double *xy, size_t n, const double *cam8, double *rays)
+    {
+        DifferentiableCameraModel<double> m;
+        m.focal_length_pixels = cam8[0];
+        m.principle_point = Eigen::Vector2d(cam8[1], cam8[2]);
+        m.radial_distortion = Eigen::Vector3d(cam8[3], cam8[4], cam8[5]);
+        m.tangential_distortion = Eigen::Vector2d(cam8[6], cam8[7]);
+        for (size_t i = 0; i < n; i++)
+        {
+            const Eigen::Vector3d r = image_to_3d(Eigen::Vector2d(xy[2 * i], xy[2 * i + 1]), m);
+            rays[3 * i] = r[0], rays[3 * i + 1] = r[1], rays[3 * i + 2] = r[2];
+        }
+    }
+
+    // ---- batched LinkStage runner (link_batch.hpp). images: handles from ocbh_features_create, num_sparse[i],
+    // cam8[i]; pairs: [n_pairs][2] image indices. Returns an opaque result handle (nullptr on error).
+    struct LinkResultHandle
+    {
+        std::vector<camera_relations> relations;
+        ocb_host::LinkStats stats;
+    };
+    void *ocbh_link_pairs(const void *const *image_handles, const size_t *num_sparse, const double *cam8, size_t n_images,
+                          const size_t *pairs2, size_t n_pairs, int threads, size_t pairs_per_submission, int run_ransac)
+    {
+        auto *res = new LinkResultHandle;
+        const int rc = guarded([&] {
+            std::vector<ocb_host::LinkImage> images(n_images);
+            for (size_t i = 0; i < n_images; i++)
+            {
+                images[i].features = static_cast<const std::vector<feature_2d> *>(image_handles[i]);
+                images[i].num_sparse_features = num_sparse ? num_sparse[i] : 0;
+                const double *c = cam8 + 8 * i;
+                images[i].model.focal_length_pixels = c[0];
+                images[i].model.principle_point = Eigen::Vector2d(c[1], c[2]);
+                images[i].model.radial_distortion = Eigen::Vector3d(c[3], c[4], c[5]);
+                images[i].model.tangential_distortion = Eigen::Vector2d(c[6], c[7]);
+            }
+            std::vector<ocb_host::LinkPair> pairs(n_pairs);
+            for (size_t p = 0; p < n_pairs; p++)
+                pairs[p] = ocb_host::LinkPair{pairs2[2 * p], pairs2[2 * p + 1]};
+            ocb_host::LinkOptions opt;
+            opt.threads = threads;
+            if (pairs_per_submission)
+                opt.pairs_per_submission = pairs_per_submission;
+            opt.run_ransac = run_ransac != 0;
+            res->relations = ocb_host::link_pairs(images, pairs, opt, &res->stats);
+        });
+        if (rc)
+        {
+            delete res;
+            return nullptr;
+        }
+        return res;
+    }
+    void ocbh_link_free(void *h) { delete static_cast<LinkResultHandle *>(h); }
+    // stats8: seconds subsample+upload, gpu match, tail, total, comparisons, matches, ransac inliers, 0
+    void ocbh_link_stats(const void *h, double *stats8)
+    {
+        const auto &s = static_cast<const LinkResultHandle *>(h)->stats;
+        stats8[0] = s.seconds_subsample_upload, stats8[1] = s.seconds_match_gpu, stats8[2] = s.seconds_tail;
+        stats8[3] = s.seconds_total, stats8[4] = (double)s.comparisons, stats8[5] = (double)s.matches;
+        stats8[6] = (double)s.ransac_inliers, stats8[7] = 0;
+    }
+    void ocbh_link_sizes(const void *h, size_t p, size_t *n_matches, size_t *n_inlier_matches)
+    {
+        const auto &r = static_cast<const LinkResultHandle *>(h)->relations[p];
+        *n_matches = r.matches.size();
+        *n_inlier_matches = r.inlier_matches.size();
+    }
+    // one pair: matches (i1, i2, dist), H9 column-major, relation type, poses [4][8], inlier pixels4 + idx3
+    void ocbh_link_get(const void *h, size_t p, size_t *m_i1, size_t *m_i2, double *m_dist, double *H9, int *relation_type,
+                       double *poses32, double *inl_pixels4, size_t *inl_idx3)
+    {
+        const auto &r = static_cast<const LinkResultHandle *>(h)->relations[p];
+        for (size_t i = 0; i < r.matches.size(); i++)
+            m_i1[i] = r.matches[i].feature_index_1, m_i2[i] = r.matches[i].feature_index_2,
+            m_dist[i] = r.matches[i].distance;
+        std::memcpy(H9, r.ransac_relation.data(), 72);
+        *relation_type = (int)r.relationType;
+        for (int i = 0; i < 4; i++)
+        {
+            for (int k = 0; k < 4; k++)
+                poses32[8 * i + k] = r.relative_poses[i].orientation.coeffs()[k];
+            for (int k = 0; k < 3; k++)
+                poses32[8 * i + 4 + k] = r.relative_poses[i].position[k];
+            poses32[8 * i + 7] = r.relative_poses[i].score;
+        }
+        for (size_t i = 0; i < r.inlier_matches.size(); i++)
+        {
+            const auto &m = r.inlier_matches[i];
+            inl_pixels4[4 * i] = m.pixel_1[0], inl_pixels4[4 * i + 1] = m.pixel_1[1];
+            inl_pixels4[4 * i + 2] = m.pixel_2[0], inl_pixels4[4 * i + 3] = m.pixel_2[1];
+            inl_idx3[3 * i] = m.feature_index_1, inl_idx3[3 * i + 1] = m.feature_index_2, inl_idx3[3 * i + 2] = m.match_index;
+        }
     }
 }

@@ -1,0 +1,49 @@
+// Batched LinkStage runner: what the closures of LinkStage::get_runners do for every
+// (image, neighbour) pair (reference src/pipeline/link_stage.cpp:63-65,75-112), for a whole batch of pairs at once.
+//   reference: one closure per pair on an OpenMP worker: subsample -> match_features_subset -> distort_keypoints ->
+//              ransac<homography_model> -> decompose -> assembleInliers, all on that worker's core;
+//   here:      the packed descriptor rows of every image are uploaded ONCE (ocb_register_descriptors), the pairs are
+//              matched in large submissions (ocb_match_pairs: one K1 launch per submission), and the per-pair tail
+//              (ratio test + sort, rays, RANSAC with GPU scoring, decomposition, inlier assembly) runs on OpenMP
+//              workers while the next submission is on the GPU.
+// Results are returned in pair order (the order LinkStage::finalize restores, link_stage.cpp:119-131) and are
+// identical to running the reference-signature functions of opencalibration_api.hpp pair by pair.
+#pragma once
+#include "opencalibration_api.hpp"
+
+#include <cstddef>
+#include <vector>
+
+namespace ocb_host
+{
+// What a LinkStage closure reads from an `image` node (include/opencalibration/types/image.hpp:18-48).
+struct LinkImage
+{
+    const std::vector<opencalibration::feature_2d> *features = nullptr;
+    size_t num_sparse_features = 0; // link_stage.cpp:63-65: subsample only the sparse prefix (0 = all)
+    opencalibration::DifferentiableCameraModel<double> model;
+};
+struct LinkPair
+{
+    size_t image_1; // node_id: the query side
+    size_t image_2; // match_node_id: the candidate side
+};
+struct LinkOptions
+{
+    int threads = 0;                    // OpenMP workers of the per-pair tail (0 = all cores)
+    size_t pairs_per_submission = 256;  // pairs per ocb_match_pairs call
+    double coarse_spacing_pixels = 40.0; // link_stage.cpp:62
+    bool run_ransac = true;             // false: stop after the match lists (relations.matches only)
+};
+struct LinkStats
+{
+    double seconds_subsample_upload = 0, seconds_match_gpu = 0, seconds_tail = 0, seconds_total = 0;
+    size_t comparisons = 0, matches = 0, ransac_inliers = 0;
+};
+// relations[p] is what the closure of pair p would have stored in its edge_payload (link_stage.cpp:95-111).
+// With run_ransac == false only relations[p].matches is filled.
+std::vector<opencalibration::camera_relations> link_pairs(const std::vector<LinkImage> &images,
+                                                          const std::vector<LinkPair> &pairs,
+                                                          const LinkOptions &options = LinkOptions(),
+                                                          LinkStats *stats = nullptr);
+} // namespace ocb_host

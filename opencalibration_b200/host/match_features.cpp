@@ -38,10 +38,22 @@ std::vector<feature_match> run_match(const std::vector<feature_2d> &set_1, const
                                                        sizeof(feature_2d), indices_2.data(), n2, top.data(),
                                                        mutual ? col.data() : nullptr),
                                 "ocb_match_top2_strided");
+    return ocb_host::detail::matches_from_top2(indices_1, indices_2, top.data(), mutual ? col.data() : nullptr, mutual);
+}
+} // namespace
+
+namespace ocb_host
+{
+namespace detail
+{
+std::vector<feature_match> matches_from_top2(const std::vector<size_t> &indices_1, const std::vector<size_t> &indices_2,
+                                             const ocb_top2 *top, const uint32_t *col, std::vector<bool> *mutual)
+{
     // Ratio test in double like the reference (:94), then the reference's std::sort (:100-101). The sort runs on
     // compact (query position, integer distance) records: std::sort's sequence of comparisons and moves depends
     // only on the comparator's answers, and a.d > b.d <=> a.d * (1.0 / 486) > b.d * (1.0 / 486) for these
     // integers, so the permutation is the one the reference's sort produces on its 24-byte records.
+    const size_t n1 = indices_1.size();
     struct Rec
     {
         uint32_t a;
@@ -64,11 +76,12 @@ std::vector<feature_match> run_match(const std::vector<feature_2d> &set_1, const
         const uint32_t a = recs[i].a, k = top[a].best_k;
         results[i] = feature_match{indices_1[a], indices_2[k], as_distance(top[a].best_d)};
         if (mutual)
-            (*mutual)[i] = col[k] == a;
+            (*mutual)[i] = col && col[k] == a;
     }
     return results;
 }
-} // namespace
+} // namespace detail
+} // namespace ocb_host
 
 namespace opencalibration
 {

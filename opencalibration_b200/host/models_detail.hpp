@@ -30,6 +30,11 @@ void epipolar_rows_from_sample(const std::vector<opencalibration::correspondence
 bool epipolar_rows_from_inliers(const std::vector<opencalibration::correspondence> &corrs,
                                 const std::vector<bool> &inliers, size_t minimum,
                                 std::vector<std::array<double, 9>> &rows);
+// tail of match_features_subset (src/match/match_features.cpp:94-101) on the K1 records of one pair: ratio test in
+// double, feature_match records with ORIGINAL indices, the reference's std::sort; optional cross-check flags
+std::vector<opencalibration::feature_match> matches_from_top2(const std::vector<size_t> &indices_1,
+                                                              const std::vector<size_t> &indices_2, const ocb_top2 *top,
+                                                              const uint32_t *col, std::vector<bool> *mutual);
 void rank2_from(const double *in9, double *out9);
 // cv::decomposeHomographyMat(H, I, ...) restated (homography_decompose.cpp): H column-major; up to 4 solutions,
 // R36 column-major 3x3 each, t12, n12; returns the number of solutions (1 for a pure rotation, else 4)

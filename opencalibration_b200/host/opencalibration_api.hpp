@@ -25,6 +25,15 @@ double ransac(const std::vector<correspondence> &matches, Model &model, std::vec
 void assembleInliers(const std::vector<feature_match> &matches, const std::vector<bool> &inliers,
                      const std::vector<feature_2d> &source_features, const std::vector<feature_2d> &dest_features,
                      std::vector<feature_match_denormalized> &inlier_list);
+
+// include/opencalibration/distort/distort_keypoints.hpp:17-24 (src/distort/distort_keypoints.cpp:48-103): the step
+// between match and ransac in LinkStage (link_stage.cpp:87-88). Host code: ~500 matches per pair.
+std::vector<correspondence> distort_keypoints(const std::vector<feature_2d> &features1,
+                                              const std::vector<feature_2d> &features2,
+                                              const std::vector<feature_match> &matches,
+                                              const DifferentiableCameraModel<double> &model1,
+                                              const DifferentiableCameraModel<double> &model2);
+Eigen::Vector3d image_to_3d(const Eigen::Vector2d &keypoint, const DifferentiableCameraModel<double> &model);
 } // namespace opencalibration
 
 // Extensions that the reference does not have (kept out of its namespace).

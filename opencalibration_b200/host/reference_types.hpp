@@ -2,7 +2,8 @@
 //
 // Built inside the reference tree (OCB_WITH_REFERENCE_HEADERS) this header simply pulls in
 // the reference's own headers, so the adapters are compiled against the real types and real Eigen:
-//   include/opencalibration/types/{feature_2d,feature_match,correspondence,decomposed_pose}.hpp
+//   include/opencalibration/types/{feature_2d,feature_match,correspondence,decomposed_pose,camera_model,
+//                                  camera_relations}.hpp
 //   include/opencalibration/model_inliers/{homography,essential_matrix,fundamental_matrix}_model.hpp
 // Stand-alone (this repository, where Eigen is not installed) it declares layout-compatible equivalents: same
 // namespace, member names, member order, sizes and alignment (static_asserts below; the expected numbers were
@@ -14,6 +15,8 @@
 #include <opencalibration/model_inliers/essential_matrix_model.hpp>
 #include <opencalibration/model_inliers/fundamental_matrix_model.hpp>
 #include <opencalibration/model_inliers/homography_model.hpp>
+#include <opencalibration/types/camera_model.hpp>
+#include <opencalibration/types/camera_relations.hpp>
 #include <opencalibration/types/correspondence.hpp>
 #include <opencalibration/types/decomposed_pose.hpp>
 #include <opencalibration/types/feature_2d.hpp>
@@ -163,6 +166,45 @@ struct decomposed_pose
     Eigen::Vector3d position{NAN, NAN, NAN};
     int score{0};
 };
+
+// include/opencalibration/types/camera_relations.hpp:13-35 -- the edge payload LinkStage fills
+struct camera_relations
+{
+    std::vector<feature_match_denormalized> inlier_matches;
+    std::vector<feature_match> matches;
+    Eigen::Matrix3d ransac_relation = Eigen::Matrix3d::Constant(NAN);
+    enum class RelationType
+    {
+        HOMOGRAPHY,
+        FUNDAMENTAL_MATRIX,
+        UNKNOWN
+    } relationType = RelationType::UNKNOWN;
+    std::array<decomposed_pose, 4> relative_poses;
+};
+// include/opencalibration/types/camera_model.hpp:10-60 (the members image_to_3d reads; T = double only here)
+enum class ProjectionType
+{
+    PLANAR,
+    UNKNOWN
+};
+enum class CameraModelTag
+{
+    FORWARD,
+    INVERSE
+};
+template <typename T, CameraModelTag tag> struct DifferentiableCameraModelBase
+{
+    size_t pixels_rows = 0;
+    size_t pixels_cols = 0;
+    T focal_length_pixels = T(0);
+    Eigen::Vector2d principle_point{0, 0};
+    Eigen::Vector3d radial_distortion{0, 0, 0};
+    Eigen::Vector2d tangential_distortion{0, 0};
+    ProjectionType projection_type = ProjectionType::PLANAR;
+};
+template <typename T> using DifferentiableCameraModel = DifferentiableCameraModelBase<T, CameraModelTag::FORWARD>;
+template <typename T>
+using InverseDifferentiableCameraModel = DifferentiableCameraModelBase<T, CameraModelTag::INVERSE>;
 
 // include/opencalibration/model_inliers/homography_model.hpp:14-34
 struct homography_model

@@ -112,3 +112,72 @@ def grid_survey(rows, cols, n_desc, seed=7, k_nn=10, noise=0.08, overlap=0.6):
             if j != i:
                 pairs.append((i, int(j)))
     return images, pos, pairs
+
+
+class PlanarSurvey:
+    """SURVEY 8d c4/c5 with geometry: a rows x cols grid of nadir cameras over a textured plane. World points live
+    in unit cells of the ground plane (`per_cell` points each, position and descriptor derived from (seed, cell), so
+    any image can be generated on its own, on any rank); an image sees the points inside its footprint
+    (`footprint` grid units wide) at pixel = principal point + (world - camera position) * pixels_per_unit + noise,
+    with `noise` descriptor bit flips; it is padded with clutter up to n_desc features. Directed pairs = k_nn nearest
+    cameras minus self (mirrors src/pipeline/link_stage.cpp:26-34). Feature order = strength descending, like the
+    reference's extractor leaves it."""
+
+    def __init__(self, rows, cols, n_desc, seed=7, k_nn=10, noise=0.08, footprint=2.5, image_size=(4000, 3000),
+                 focal=3000.0, pixel_noise=0.3):
+        self.rows, self.cols, self.n_desc, self.seed, self.noise = rows, cols, n_desc, seed, noise
+        self.footprint, self.image_size, self.focal, self.pixel_noise = footprint, image_size, focal, pixel_noise
+        self.n_images = rows * cols
+        self.positions = np.stack(np.meshgrid(np.arange(cols, dtype=np.float64), np.arange(rows, dtype=np.float64)),
+                                  -1).reshape(-1, 2)
+        # ~70 % of an image's features are world points, the rest clutter
+        self.per_cell = max(1, int(0.7 * n_desc / (footprint * footprint * image_size[1] / image_size[0])))
+        self.pairs = []
+        for i in range(self.n_images):
+            d2 = ((self.positions - self.positions[i]) ** 2).sum(1)
+            for j in np.argsort(d2, kind="stable")[:k_nn]:
+                if j != i:
+                    self.pairs.append((i, int(j)))
+        self._cells = {}
+
+    def camera8(self):
+        w, h = self.image_size
+        return np.array([self.focal, w / 2, h / 2, 0, 0, 0, 0, 0], np.float64)
+
+    def _cell(self, cx, cy):
+        key = (cx, cy)
+        if key not in self._cells:
+            r = np.random.default_rng([self.seed, cx + 100000, cy + 100000])
+            xy = r.random((self.per_cell, 2)) + np.array([cx, cy], np.float64)
+            self._cells[key] = (xy, random_descriptors(self.per_cell, r))
+        return self._cells[key]
+
+    def image(self, i):
+        """-> (descriptors [n][8] u64, xy [n][2] pixels, strength [n] f32)"""
+        rng = np.random.default_rng([self.seed, 7919, i])
+        w, h = self.image_size
+        px_per_unit = w / self.footprint
+        half = np.array([self.footprint / 2, self.footprint / 2 * h / w])
+        c = self.positions[i]
+        lo, hi = c - half, c + half
+        xs, ds = [], []
+        for cx in range(int(np.floor(lo[0])), int(np.floor(hi[0])) + 1):
+            for cy in range(int(np.floor(lo[1])), int(np.floor(hi[1])) + 1):
+                xy, d = self._cell(cx, cy)
+                keep = np.all((xy >= lo) & (xy < hi), axis=1)
+                xs.append(xy[keep])
+                ds.append(d[keep])
+        xy = np.concatenate(xs)
+        d = np.concatenate(ds)
+        if len(xy) > self.n_desc:
+            sel = rng.permutation(len(xy))[:self.n_desc]
+            xy, d = xy[sel], d[sel]
+        pix = (xy - c) * px_per_unit + np.array([w / 2, h / 2]) + rng.normal(0, self.pixel_noise, xy.shape)
+        d = flip_bits(d, self.noise, rng)
+        n_clutter = self.n_desc - len(d)
+        if n_clutter > 0:
+            pix = np.concatenate([pix, rng.random((n_clutter, 2)) * np.array([w, h])])
+            d = np.concatenate([d, random_descriptors(n_clutter, rng)])
+        strength = np.sort(rng.random(len(d)).astype(np.float32))[::-1].copy()
+        order = rng.permutation(len(d))
+        return d[order].copy(), pix[order].copy(), strength

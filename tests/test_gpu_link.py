@@ -1,0 +1,93 @@
+"""Batched LinkStage runner (host/link_batch.hpp; reference src/pipeline/link_stage.cpp:75-112): every pair's
+camera_relations must equal what the per-pair reference flow gives -- subsample, match, rays, RANSAC, decomposition,
+inlier assembly -- with the oracle standing in for the reference functions."""
+import numpy as np
+import pytest
+
+import oc_decompose
+import oc_distort
+import oc_oracle as O
+from opencalibration_b200 import synthetic
+
+pytestmark = pytest.mark.gpu
+
+
+def expected_pair(oracle, img_a, img_b, cam, spacing=40.0, num_sparse=(0, 0)):
+    (da, xa, sa), (db, xb, sb) = img_a, img_b
+    ia = oracle.subsample(xa, sa, spacing, num_sparse[0]) if len(da) else np.zeros(0, np.uintp)
+    ib = oracle.subsample(xb, sb, spacing, num_sparse[1]) if len(db) else np.zeros(0, np.uintp)
+    m1, m2, md = oracle.match_features_subset(da, db, ia, ib)
+    corr = np.zeros((len(m1), 7))
+    corr[:, 0:3] = oc_distort.image_to_3d_undistorted(xa[m1], cam[0], cam[1:3]) if len(m1) else 0
+    corr[:, 3:6] = oc_distort.image_to_3d_undistorted(xb[m2], cam[0], cam[1:3]) if len(m1) else 0
+    corr[:, 6] = md
+    score, M, inl, _ = oracle.ransac(O.KIND_H, corr)
+    H = M[:9].reshape(3, 3).T
+    ok, poses = oc_decompose.homography_decompose(H, corr, inl) if not np.isnan(H).any() else (False, None)
+    keep = ok and inl.sum() > 4 * 1.5
+    return dict(matches=(m1, m2, md), H=H, inl=inl, ok=ok, keep=keep, poses=poses, xa=xa, xb=xb)
+
+
+def check_pair(got, exp):
+    assert np.array_equal(got["H"], exp["H"], equal_nan=True)
+    assert got["relation_type"] == 0  # RelationType::HOMOGRAPHY (link_stage.cpp:96)
+    if exp["poses"] is not None:
+        assert np.array_equal(got["poses"][:, 7], exp["poses"][:, 7])
+        assert np.allclose(got["poses"][:, :7], exp["poses"][:, :7], atol=1e-9, rtol=0, equal_nan=True)
+    m1, m2, md = exp["matches"]
+    if exp["keep"]:
+        assert np.array_equal(got["matches"][0], m1) and np.array_equal(got["matches"][1], m2)
+        assert np.array_equal(got["matches"][2], md)
+        idx = np.nonzero(exp["inl"])[0]
+        assert np.array_equal(got["inlier_idx"][:, 2], idx)
+        assert np.array_equal(got["inlier_idx"][:, 0], m1[idx]) and np.array_equal(got["inlier_idx"][:, 1], m2[idx])
+        assert np.array_equal(got["inlier_pixels"][:, 0:2], exp["xa"][m1[idx]])
+        assert np.array_equal(got["inlier_pixels"][:, 2:4], exp["xb"][m2[idx]])
+    else:  # link_stage.cpp:104: matches are only stored for decomposable, well-supported relations
+        assert len(got["matches"][0]) == 0 and len(got["inlier_idx"]) == 0
+
+
+def test_config1_pair_both_directions(gpu, hostlib, oracle, config1):
+    imgs = [(config1["a_desc"], config1["a_xy"], config1["a_strength"]),
+            (config1["b_desc"], config1["b_xy"], config1["b_strength"])]
+    cam = hostlib.camera8(5000, (2672, 2008))  # test/test_ransac_functional.cpp:26-31
+    sets = [hostlib.FeatureSet(d, xy, s) for d, xy, s in imgs]
+    res = hostlib.link_pairs(sets, [cam, cam], [(0, 1), (1, 0)], threads=2)
+    for p, (a, b) in enumerate([(0, 1), (1, 0)]):
+        exp = expected_pair(oracle, imgs[a], imgs[b], cam)
+        got = res.get(p)
+        check_pair(got, exp)
+        assert exp["keep"] and len(got["matches"][0]) > 400 and len(got["inlier_idx"]) > 100
+    assert res.stats["comparisons"] == 2 * 4052 * 4198
+
+
+def test_planar_survey_grid(gpu, hostlib, oracle):
+    survey = synthetic.PlanarSurvey(3, 3, 1500, seed=11)
+    imgs = [survey.image(i) for i in range(survey.n_images)]
+    imgs[4] = tuple(x[:400] for x in imgs[4])  # ragged
+    imgs[8] = tuple(x[:0] for x in imgs[8])    # an image without features
+    cam = survey.camera8()
+    sets = [hostlib.FeatureSet(d, xy, s) for d, xy, s in imgs]
+    pairs = survey.pairs + [(2, 2)]
+    num_sparse = [0] * 9
+    num_sparse[1] = 700  # only the sparse prefix of image 1 is subsampled (link_stage.cpp:63-65)
+    res = hostlib.link_pairs(sets, [cam] * 9, pairs, num_sparse=num_sparse, threads=4, pairs_per_submission=7)
+    kept = 0
+    for p, (a, b) in enumerate(pairs):
+        exp = expected_pair(oracle, imgs[a], imgs[b], cam, num_sparse=(num_sparse[a], num_sparse[b]))
+        check_pair(res.get(p), exp)
+        kept += bool(exp["keep"])
+    assert kept >= 20  # neighbouring images genuinely overlap
+    # matches only
+    res2 = hostlib.link_pairs(sets, [cam] * 9, pairs[:5], num_sparse=num_sparse, run_ransac=False)
+    for p, (a, b) in enumerate(pairs[:5]):
+        exp = expected_pair(oracle, imgs[a], imgs[b], cam, num_sparse=(num_sparse[a], num_sparse[b]))
+        got = res2.get(p)
+        assert np.array_equal(got["matches"][0], exp["matches"][0]) and np.array_equal(got["matches"][2], exp["matches"][2])
+
+
+def test_link_pairs_rejects_bad_input(gpu, hostlib):
+    survey = synthetic.PlanarSurvey(1, 2, 100, seed=3)
+    sets = [hostlib.FeatureSet(*survey.image(i)) for i in range(2)]
+    with pytest.raises(hostlib.OcbError):
+        hostlib.link_pairs(sets, [survey.camera8()] * 2, [(0, 5)])
