@@ -373,6 +373,107 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_survey(args):
+    """--workload c4 / c5 (BASELINE.json configs[3] / configs[4]): a synthetic aerial survey (PlanarSurvey: grid of
+    nadir cameras over a textured plane, 8192 features per image, directed pairs = 10 nearest cameras minus self)
+    through the batched LinkStage runner (host/link_batch.hpp = src/pipeline/link_stage.cpp:75-112 for a pair list):
+    subsample, descriptor upload, K1 matching in large submissions, ratio test + sort, rays, RANSAC (GPU scoring),
+    decomposition, inlier assembly. Pairs are sharded over the ranks by Hilbert-curve partition of the camera
+    positions (opencalibration_b200/sharding.py); no data-path collective; rank 0 gathers per-pair summaries.
+    One step = the whole survey once. value = pairs of all ranks / max-over-ranks wall time of the step (host code is
+    part of this path, so it is wall time, bracketed by device synchronisation + barrier)."""
+    import torch
+    from concurrent.futures import ThreadPoolExecutor
+    from opencalibration_b200 import capi, host, sharding, synthetic
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    capi.init(local_rank)
+    rows, cols = (25, 40) if args.workload == "c4" else (50, 100)
+    if args.survey_scale != 1.0:
+        rows, cols = max(2, int(rows * args.survey_scale)), max(2, int(cols * args.survey_scale))
+    survey = synthetic.PlanarSurvey(rows, cols, 8192, seed=7)
+    pairs = survey.pairs
+    if args.workload == "c5":
+        pairs = pairs[:40000]
+    shard = sharding.partition(survey.positions, pairs, world)[rank]
+    resident = shard.resident_images.tolist()
+    local_index = {g: i for i, g in enumerate(resident)}
+    with ThreadPoolExecutor(8) as ex:
+        images = list(ex.map(survey.image, resident))
+    sets = [host.FeatureSet(d, xy, st) for d, xy, st in images]
+    cams = [survey.camera8()] * len(sets)
+    local_pairs = [(local_index[a], local_index[b]) for a, b in shard.pairs]
+    threads = max(1, (os.cpu_count() or 1) // world)
+    spacing = args.spacing
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+
+    def step():
+        return host.link_pairs(sets, cams, local_pairs, threads=threads, pairs_per_submission=args.pairs_per_submission,
+                               run_ransac=args.with_ransac, spacing=spacing)
+
+    host.link_pairs(sets, cams, local_pairs[:32], threads=threads, run_ransac=args.with_ransac, spacing=spacing).close()
+    steps = max(1, args.steps if args.steps < 50 else 1)
+    launches0 = capi.kernel_launches()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    t0 = time.perf_counter()
+    stats = None
+    for _ in range(steps):
+        res = step()
+        stats = res.stats
+        kept = sum(1 for p in range(res.n_pairs) if res.sizes(p)[0] > 0)
+        res.close()
+    barrier()
+    secs = (time.perf_counter() - t0) / steps
+    clocks = sampler.result()
+    launches = capi.kernel_launches() - launches0
+    t = torch.tensor([secs], dtype=torch.float64, device="cuda")
+    agg = torch.tensor([len(local_pairs), stats["comparisons"], stats["matches"], stats["ransac_inliers"], kept,
+                        len(resident)], dtype=torch.float64, device="cuda")
+    if dist:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(agg, op=dist.ReduceOp.SUM)
+    summaries = sharding.gather_results(shard.pair_ids, [0] * len(shard.pair_ids), len(pairs), dist)
+    if rank == 0:
+        assert summaries is not None and len(summaries) == len(pairs)
+        secs = float(t.item())
+        n_pairs, cmps, matches, inliers, kept_all, resident_all = [float(x) for x in agg.tolist()]
+        line = {
+            "metric": "image_pairs_matched_per_s", "value": n_pairs / secs, "unit": "pairs/s", "n_gpus": world,
+            "steps": steps, "warmup": 1, "ms_per_step": secs * 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "config": {"workload": f"configs[{3 if args.workload == 'c4' else 4}]: {rows}x{cols} image survey, "
+                                   f"{int(n_pairs)} directed pairs x 8192 features, batched LinkStage runner "
+                                   f"(match + ratio test + sort{' + rays + RANSAC + decompose' if args.with_ransac else ''})",
+                       "images": survey.n_images, "pairs": int(n_pairs), "subsample_spacing_px": spacing,
+                       "comparisons_per_step": cmps, "Gcmp_per_s": cmps / secs / 1e9, "matches": int(matches),
+                       "ransac_inliers": int(inliers), "pairs_with_relation": int(kept_all),
+                       "resident_images_all_ranks": int(resident_all), "host_threads_per_rank": threads,
+                       "rank0_breakdown_s": {k: v for k, v in stats.items() if k.startswith("seconds")}},
+            "clocks": clocks, "gpu_launches": int(launches),
+            "e2e": {"value": n_pairs / secs, "unit": "pairs/s",
+                    "h2d_bytes_per_step": int(resident_all) * 8192 * 64, "d2h_bytes_per_step": int(n_pairs) * 8192 * 8,
+                    "note": "the step is end to end by construction: features start in host vectors, relations end there"},
+        }
+        emit(line)
+    if dist:
+        dist.destroy_process_group()
+
+
 _REAL_STDOUT = None
 
 
@@ -402,12 +503,23 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c4", "c5"],
+                    help="c2 = headline (default); c4 / c5 = survey through the batched LinkStage runner")
+    ap.add_argument("--survey-scale", type=float, default=1.0, help="shrink the c4/c5 grid (for quick runs)")
+    ap.add_argument("--spacing", type=float, default=0.5,
+                    help="c4/c5: subsample spacing in px (0.5 keeps all 8192 features; LinkStage uses 40)")
+    ap.add_argument("--pairs-per-submission", type=int, default=256)
+    ap.add_argument("--with-ransac", action="store_true",
+                    help="c4/c5: continue every pair through rays + RANSAC + decomposition + inlier assembly "
+                         "(default: the metric's unit, pairs MATCHED: match lists after ratio test and sort)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true")
     ap.add_argument("--callers", type=int, default=4, help="concurrent host callers of the e2e measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload != "c2":
+        run_survey(args)
     else:
         run_ours(args)
 

@@ -118,6 +118,24 @@ extern "C"
      * (src/pipeline/link_stage.cpp:63-65,80-81). Re-registering an id replaces it. */
     int ocb_register_descriptors(uint64_t set_id, const uint64_t *rows, size_t n);
     int ocb_unregister_descriptors(uint64_t set_id);
+    /* Registers many sets with ONE device allocation and a pipelined gather -> page-locked staging -> device copy
+     * (the per-image cudaMalloc + synchronous copy of ocb_register_descriptors dominates when a LinkStage batch
+     * uploads hundreds of images). Row k of a set is the 64 bytes at rows + idx[k] * stride (idx == NULL: k * stride):
+     * pass &features[0].descriptor, sizeof(feature_2d) and the subsample indices to upload straight from
+     * std::vector<feature_2d>. The allocation is released when the last of its sets is unregistered / replaced. */
+    typedef struct ocb_set_source
+    {
+        uint64_t set_id;
+        const void *rows;
+        size_t stride;
+        const size_t *idx;
+        size_t n;
+    } ocb_set_source;
+    int ocb_register_descriptors_batch(const ocb_set_source *sources, size_t count);
+    /* Page-locked host memory for callers that want results copied straight into their buffers (every host-buffer
+     * entry point detects page-locked arguments and skips its staging copy). NULL on failure. */
+    void *ocb_host_alloc(size_t bytes);
+    void ocb_host_free(void *p);
     /* Matches n_pairs pairs in one submission. out receives the ocb_top2 records of pair p at
      * out[out_offsets[p] .. out_offsets[p] + n_query_rows(p)); out_offsets has n_pairs entries. */
     int ocb_match_pairs(const ocb_pair *pairs, size_t n_pairs, ocb_top2 *out, const uint64_t *out_offsets);

@@ -52,7 +52,7 @@ def build_host(force=False, verbose=False):
     deps = srcs + [os.path.join(HOST, f) for f in os.listdir(HOST) if f.endswith(".hpp")] + \
         [os.path.join(ROOT, "include", "ocb.h")]
     if force or _newer(out, deps):
-        _run(["g++", "-std=c++17", "-O2", "-fPIC", "-Wall", "-Wextra", "-ffp-contract=off", "-fopenmp", "-shared",
+        _run(["g++", "-std=c++17", "-O3", "-fPIC", "-Wall", "-Wextra", "-ffp-contract=off", "-fopenmp", "-shared",
               "-I", os.path.join(ROOT, "include"), "-I", HOST, "-o", out] + srcs +
              ["-L", PKG, "-locb", "-Wl,-rpath,$ORIGIN"], verbose)
     return out

@@ -7,6 +7,7 @@ import numpy as np
 PKG = os.path.dirname(os.path.abspath(__file__))
 
 TOP2_DTYPE = np.dtype([("best_k", np.uint32), ("best_d", np.uint16), ("second_d", np.uint16)])
+SET_SOURCE_DTYPE = np.dtype([("set_id", "<u8"), ("rows", "<u8"), ("stride", "<u8"), ("idx", "<u8"), ("n", "<u8")])
 PAIR_DTYPE = np.dtype([("query_set", np.uint64), ("candidate_set", np.uint64)])
 DIST_INF = 0xFFFF
 NO_INDEX = 0xFFFFFFFF
@@ -50,6 +51,9 @@ def lib():
         "ocb_match_top2_device": (i32, [vp, sz, vp, sz, vp, vp, vp, sz, vp]),
         "ocb_register_descriptors": (i32, [u64, vp, sz]),
         "ocb_unregister_descriptors": (i32, [u64]),
+        "ocb_register_descriptors_batch": (i32, [vp, sz]),
+        "ocb_host_alloc": (vp, [sz]),
+        "ocb_host_free": (None, [vp]),
         "ocb_match_pairs": (i32, [vp, sz, vp, vp]),
         "ocb_score_models": (i32, [i32, vp, sz, vp, sz, dbl, vp, vp, vp, vp]),
         "ocb_residuals": (i32, [i32, vp, vp, sz, vp]),
@@ -148,6 +152,18 @@ def match_top2_device(d_q, n1, d_c, n2, d_out, d_col, d_ws, ws_bytes, stream):
 def register_descriptors(set_id, rows):
     rows = _rows(rows)
     check(lib().ocb_register_descriptors(int(set_id), _ptr(rows), len(rows)))
+
+
+def register_descriptors_batch(sets):
+    """sets: [(set_id, base uint8 array, stride, idx or None, n)] -> one device allocation for all of them."""
+    src = np.zeros(len(sets), SET_SOURCE_DTYPE)
+    keep = []
+    for i, (sid, base, stride, idx, n) in enumerate(sets):
+        base = np.ascontiguousarray(base)
+        idx = None if idx is None else np.ascontiguousarray(idx, dtype=np.uintp)
+        keep += [base, idx]
+        src[i] = (sid, base.ctypes.data if n else 0, stride, 0 if idx is None else idx.ctypes.data, n)
+    check(lib().ocb_register_descriptors_batch(_ptr(src), len(src)))
 
 
 def unregister_descriptors(set_id):

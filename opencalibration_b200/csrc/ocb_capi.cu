@@ -72,7 +72,10 @@ struct ThreadCtx
 {
     int device = -1; // -1: follow the process default
     bool ready = false;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr; // latency-sensitive per-call work: highest priority
+    cudaStream_t bulk = nullptr;   // large batched submissions (ocb_match_pairs): lowest priority, so that the small
+                                   // kernels of other host threads (RANSAC scoring of the previous submission) are
+                                   // dispatched ahead of the thousands of queued matching CTAs
     Buf dev, pinned;
     int ready_device = -1;
 
@@ -97,7 +100,10 @@ struct ThreadCtx
         if (device < 0 || device >= n)
             return fail_invalid("device index out of range");
         OCB_CUDA(cudaSetDevice(device));
-        OCB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        int prio_low = 0, prio_high = 0;
+        OCB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_low, &prio_high));
+        OCB_CUDA(cudaStreamCreateWithPriority(&stream, cudaStreamNonBlocking, prio_high));
+        OCB_CUDA(cudaStreamCreateWithPriority(&bulk, cudaStreamNonBlocking, prio_low));
         ready = true;
         ready_device = device;
         return 0;
@@ -147,16 +153,25 @@ struct ThreadCtx
                 cudaFreeHost(pinned.p);
             if (stream)
                 cudaStreamDestroy(stream);
+            if (bulk)
+            {
+                cudaStreamSynchronize(bulk);
+                cudaStreamDestroy(bulk);
+            }
         }
         dev = Buf();
         pinned = Buf();
         stream = nullptr;
+        bulk = nullptr;
         ready = false;
         ready_device = -1;
     }
     ~ThreadCtx()
     {
-        // the CUDA runtime may already be gone at thread/process exit; leak rather than crash
+        // worker threads come and go (std::async, OpenMP teams): give their streams and buffers back. At process
+        // exit the runtime may already be unloading; the calls then fail harmlessly and the OS reclaims the rest.
+        release();
+        cudaGetLastError();
     }
 };
 thread_local ThreadCtx t_ctx;
@@ -208,12 +223,43 @@ int upload(ThreadCtx &c, void *d_dst, const void *h_src, size_t bytes, size_t st
     return 0;
 }
 
+// One device allocation shared by the sets of a batched registration; freed with its last set.
+struct Arena
+{
+    void *base = nullptr;
+    int device = 0;
+    size_t live = 0;
+};
 struct DescSet
 {
     void *d_rows = nullptr;
     size_t n = 0;
     int device = 0;
+    Arena *arena = nullptr; // nullptr: d_rows is its own allocation
 };
+// caller holds g_sets_mu
+void free_set_storage(DescSet &s)
+{
+    int cur = 0;
+    cudaGetDevice(&cur);
+    if (s.arena)
+    {
+        if (--s.arena->live == 0)
+        {
+            cudaSetDevice(s.arena->device);
+            cudaFree(s.arena->base);
+            delete s.arena;
+        }
+    }
+    else if (s.d_rows)
+    {
+        cudaSetDevice(s.device);
+        cudaFree(s.d_rows);
+    }
+    cudaSetDevice(cur);
+    s.d_rows = nullptr;
+    s.arena = nullptr;
+}
 std::mutex g_sets_mu;
 std::unordered_map<uint64_t, DescSet> g_sets; // key = set id; one device per id
 
@@ -261,10 +307,7 @@ extern "C"
         {
             std::lock_guard<std::mutex> lk(g_sets_mu);
             for (auto &kv : g_sets)
-            {
-                cudaSetDevice(kv.second.device);
-                cudaFree(kv.second.d_rows);
-            }
+                free_set_storage(kv.second);
             g_sets.clear();
         }
         t_ctx.release();
@@ -431,9 +474,9 @@ extern "C"
     }
 
     // Gathers rows base[idx[k] * stride .. +64) (idx == NULL: k * stride) into dst.
-    static void gather_rows(char *dst, const void *base, size_t stride, const size_t *idx, size_t n)
+    static void gather_rows(char *dst, const void *base, size_t stride, const size_t *idx, size_t n, size_t first = 0)
     {
-        const char *b = static_cast<const char *>(base);
+        const char *b = static_cast<const char *>(base) + first * stride;
         if (!idx && stride == OCB_ROW_BYTES)
         {
             memcpy(dst, b, n * OCB_ROW_BYTES);
@@ -534,13 +577,129 @@ extern "C"
         std::lock_guard<std::mutex> lk(g_sets_mu);
         auto it = g_sets.find(set_id);
         if (it != g_sets.end())
-        {
-            cudaSetDevice(it->second.device);
-            cudaFree(it->second.d_rows);
-            cudaSetDevice(cx.device);
-        }
+            free_set_storage(it->second);
         g_sets[set_id] = s;
         return 0;
+    }
+
+    int ocb_register_descriptors_batch(const ocb_set_source *sources, size_t count)
+    {
+        if (count == 0)
+            return 0;
+        if (!sources)
+            return fail_invalid("sources");
+        ThreadCtx &cx = t_ctx;
+        int rc = cx.ensure();
+        if (rc)
+            return rc;
+        size_t total_rows = 0;
+        for (size_t i = 0; i < count; i++)
+        {
+            if (sources[i].n >= 0xFFFFFFFFull)
+                return fail_invalid("n must fit in 32 bits");
+            if (sources[i].n && (!sources[i].rows || sources[i].stride < OCB_ROW_BYTES))
+                return fail_invalid("rows / stride");
+            total_rows += sources[i].n;
+        }
+        Arena *arena = nullptr;
+        char *d_base = nullptr;
+        if (total_rows)
+        {
+            void *p = nullptr;
+            OCB_CUDA(cudaMalloc(&p, total_rows * OCB_ROW_BYTES));
+            arena = new Arena;
+            arena->base = p, arena->device = cx.device, arena->live = 0;
+            d_base = static_cast<char *>(p);
+        }
+        // gather -> page-locked staging -> device, double-buffered so that the copy engine works while the next
+        // block of rows is gathered
+        const size_t block_rows = (size_t)1 << 16; // 4 MiB
+        rc = cx.pinned_reserve(2 * block_rows * OCB_ROW_BYTES);
+        cudaEvent_t ev[2] = {nullptr, nullptr};
+        if (!rc && total_rows)
+        {
+            char *hp = static_cast<char *>(cx.pinned.p);
+            cudaError_t e = cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming);
+            if (e == cudaSuccess)
+                e = cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming);
+            size_t done = 0, blk = 0;
+            for (size_t i = 0; i < count && e == cudaSuccess; i++)
+            {
+                size_t k = 0;
+                while (k < sources[i].n && e == cudaSuccess)
+                {
+                    const size_t take = std::min(block_rows, sources[i].n - k);
+                    const int b = (int)(blk & 1);
+                    if (blk >= 2)
+                        e = cudaEventSynchronize(ev[b]);
+                    if (e != cudaSuccess)
+                        break;
+                    gather_rows(hp + (size_t)b * block_rows * OCB_ROW_BYTES, sources[i].rows, sources[i].stride,
+                                sources[i].idx ? sources[i].idx + k : nullptr, take, sources[i].idx ? 0 : k);
+                    e = cudaMemcpyAsync(d_base + done * OCB_ROW_BYTES, hp + (size_t)b * block_rows * OCB_ROW_BYTES,
+                                        take * OCB_ROW_BYTES, cudaMemcpyHostToDevice, cx.stream);
+                    if (e == cudaSuccess)
+                        e = cudaEventRecord(ev[b], cx.stream);
+                    k += take, done += take, blk++;
+                }
+            }
+            if (e == cudaSuccess)
+                e = cudaStreamSynchronize(cx.stream);
+            for (cudaEvent_t v : ev)
+                if (v)
+                    cudaEventDestroy(v);
+            if (e != cudaSuccess)
+                rc = fail_cuda(e, "upload descriptor sets", __FILE__, __LINE__);
+        }
+        if (rc)
+        {
+            if (arena)
+            {
+                cudaFree(arena->base);
+                delete arena;
+            }
+            return rc;
+        }
+        std::lock_guard<std::mutex> lk(g_sets_mu);
+        size_t off = 0;
+        for (size_t i = 0; i < count; i++)
+        {
+            auto it = g_sets.find(sources[i].set_id);
+            if (it != g_sets.end())
+                free_set_storage(it->second);
+            DescSet s;
+            s.n = sources[i].n;
+            s.device = cx.device;
+            if (sources[i].n)
+            {
+                s.d_rows = d_base + off * OCB_ROW_BYTES;
+                s.arena = arena;
+                arena->live++;
+            }
+            off += sources[i].n;
+            g_sets[sources[i].set_id] = s;
+        }
+        return 0;
+    }
+
+    void *ocb_host_alloc(size_t bytes)
+    {
+        void *p = nullptr;
+        if (t_ctx.ensure() != 0)
+            return nullptr;
+        if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess)
+        {
+            cudaGetLastError();
+            set_last_error("cudaHostAlloc failed");
+            return nullptr;
+        }
+        return p;
+    }
+
+    void ocb_host_free(void *p)
+    {
+        if (p)
+            cudaFreeHost(p);
     }
 
     int ocb_unregister_descriptors(uint64_t set_id)
@@ -552,11 +711,7 @@ extern "C"
             set_last_error("unknown descriptor set");
             return OCB_E_NOT_FOUND;
         }
-        int cur = 0;
-        cudaGetDevice(&cur);
-        cudaSetDevice(it->second.device);
-        cudaFree(it->second.d_rows);
-        cudaSetDevice(cur);
+        free_set_storage(it->second);
         g_sets.erase(it);
         return 0;
     }
@@ -573,6 +728,7 @@ extern "C"
         int rc = cx.ensure();
         if (rc)
             return rc;
+        cudaStream_t bulk = cx.bulk;
         std::vector<K1Problem> pr(n_pairs);
         memset(pr.data(), 0, sizeof(K1Problem) * n_pairs);
         uint64_t out_end = 0;
@@ -621,22 +777,22 @@ extern "C"
             state_off += align_up(k1_state_bytes(pr[p]), 16);
         }
         if (state_total)
-            OCB_CUDA(cudaMemsetAsync(d + o_state, 0, state_total, cx.stream));
+            OCB_CUDA(cudaMemsetAsync(d + o_state, 0, state_total, bulk));
         const K1Problem *d_tab = nullptr;
         if (n_pairs > (size_t)K1_INLINE)
         {
             memcpy(hp + s_tab, pr.data(), table_bytes);
-            OCB_CUDA(cudaMemcpyAsync(d + o_tab, hp + s_tab, table_bytes, cudaMemcpyHostToDevice, cx.stream));
+            OCB_CUDA(cudaMemcpyAsync(d + o_tab, hp + s_tab, table_bytes, cudaMemcpyHostToDevice, bulk));
             d_tab = reinterpret_cast<const K1Problem *>(d + o_tab);
         }
-        rc = k1_launch(d_tab, pr.data(), n_pairs, plan, cx.stream);
+        rc = k1_launch(d_tab, pr.data(), n_pairs, plan, bulk);
         if (rc)
             return rc;
         const bool out_pinned = is_pinned_host(out);
         if (out_end)
             OCB_CUDA(cudaMemcpyAsync(out_pinned ? (void *)out : (void *)(hp + s_out), d + o_out,
-                                     out_end * sizeof(ocb_top2), cudaMemcpyDeviceToHost, cx.stream));
-        OCB_CUDA(cudaStreamSynchronize(cx.stream));
+                                     out_end * sizeof(ocb_top2), cudaMemcpyDeviceToHost, bulk));
+        OCB_CUDA(cudaStreamSynchronize(bulk));
         if (out_end && !out_pinned)
             memcpy(out, hp + s_out, out_end * sizeof(ocb_top2));
         return 0;

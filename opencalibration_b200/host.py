@@ -71,7 +71,7 @@ def lib():
     L.ocbh_run_parallel_match.argtypes = [_u64p, _u64p, sz, sz, sz, i32, _szp, _f64p]
     L.ocbh_image_to_3d.argtypes = [_f64p, sz, _f64p, _f64p]
     L.ocbh_image_to_3d.restype = None
-    L.ocbh_link_pairs.argtypes = [C.c_void_p, _szp, _f64p, sz, _szp, sz, i32, sz, i32]
+    L.ocbh_link_pairs.argtypes = [C.c_void_p, _szp, _f64p, sz, _szp, sz, i32, sz, i32, dbl]
     L.ocbh_link_pairs.restype = C.c_void_p
     L.ocbh_link_free.argtypes = [C.c_void_p]
     L.ocbh_link_free.restype = None
@@ -362,7 +362,8 @@ class LinkResults:
             pass
 
 
-def link_pairs(feature_sets, cameras8, pairs, num_sparse=None, threads=0, pairs_per_submission=0, run_ransac=True):
+def link_pairs(feature_sets, cameras8, pairs, num_sparse=None, threads=0, pairs_per_submission=0, run_ransac=True,
+               spacing=0.0):
     """What LinkStage's closures compute for every (image, neighbour) pair (src/pipeline/link_stage.cpp:75-112), for
     the whole pair list: feature_sets = FeatureSet per image, cameras8 = camera8() per image, pairs = [(i, j)]."""
     n = len(feature_sets)
@@ -370,7 +371,8 @@ def link_pairs(feature_sets, cameras8, pairs, num_sparse=None, threads=0, pairs_
     ns = np.zeros(n, np.uintp) if num_sparse is None else np.ascontiguousarray(num_sparse, np.uintp)
     cams = np.ascontiguousarray(cameras8, np.float64).reshape(n, 8)
     pr = np.ascontiguousarray(pairs, np.uintp).reshape(-1, 2)
-    res = lib().ocbh_link_pairs(h, ns, cams, n, pr, len(pr), int(threads), int(pairs_per_submission), int(run_ransac))
+    res = lib().ocbh_link_pairs(h, ns, cams, n, pr, len(pr), int(threads), int(pairs_per_submission), int(run_ransac),
+                               float(spacing))
     if not res:
         raise OcbError("host mirror: " + lib().ocbh_last_error().decode())
     return LinkResults(res, len(pr))

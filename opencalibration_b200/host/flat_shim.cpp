@@ -474,7 +474,8 @@ extern "C"
         ocb_host::LinkStats stats;
     };
     void *ocbh_link_pairs(const void *const *image_handles, const size_t *num_sparse, const double *cam8, size_t n_images,
-                          const size_t *pairs2, size_t n_pairs, int threads, size_t pairs_per_submission, int run_ransac)
+                          const size_t *pairs2, size_t n_pairs, int threads, size_t pairs_per_submission, int run_ransac,
+                          double spacing)
     {
         auto *res = new LinkResultHandle;
         const int rc = guarded([&] {
@@ -497,6 +498,8 @@ extern "C"
             if (pairs_per_submission)
                 opt.pairs_per_submission = pairs_per_submission;
             opt.run_ransac = run_ransac != 0;
+            if (spacing > 0)
+                opt.coarse_spacing_pixels = spacing;
             res->relations = ocb_host::link_pairs(images, pairs, opt, &res->stats);
         });
         if (rc)

@@ -23,13 +23,28 @@ std::vector<double> full_piv_lu_solve(const ColMat &A, const std::vector<double>
 
     for (int k = 0; k < K; ++k)
     {
-        // complete pivoting: largest magnitude of the trailing block, scanned column by column, first hit wins
+        // complete pivoting: largest magnitude of the trailing block, scanned column by column, first hit wins.
+        // Two passes per column (a branch-free max reduction the compiler vectorises, then the first row holding
+        // it) select the same element as a single scan with a strict comparison.
         int pr = k, pc = k;
         double best = std::fabs(lu(k, k));
         for (int c = k; c < Cn; ++c)
+        {
+            const double *col = &lu.a[(size_t)c * R];
+            double cmax = 0.0;
             for (int r = k; r < R; ++r)
-                if (std::fabs(lu(r, c)) > best)
-                    best = std::fabs(lu(r, c)), pr = r, pc = c;
+                cmax = std::max(cmax, std::fabs(col[r]));
+            if (cmax > best)
+            {
+                best = cmax, pc = c;
+                for (int r = k; r < R; ++r)
+                    if (std::fabs(col[r]) == cmax)
+                    {
+                        pr = r;
+                        break;
+                    }
+            }
+        }
         if (best == 0.0)
         {
             pivots = k;
@@ -49,11 +64,13 @@ std::vector<double> full_piv_lu_solve(const ColMat &A, const std::vector<double>
         const double d = lu(k, k);
         for (int r = k + 1; r < R; ++r)
             lu(r, k) /= d;
+        const double *lk = &lu.a[(size_t)k * R];
         for (int c = k + 1; c < Cn; ++c)
         {
             const double top = lu(k, c);
+            double *lc = &lu.a[(size_t)c * R];
             for (int r = k + 1; r < R; ++r)
-                lu(r, c) -= lu(r, k) * top;
+                lc[r] -= lk[r] * top;
         }
     }
 

@@ -6,7 +6,10 @@
 #include <atomic>
 #include <chrono>
 #include <cstring>
-#include <future>
+#include <condition_variable>
+#include <mutex>
+#include <string>
+#include <thread>
 #include <omp.h>
 #include <stdexcept>
 
@@ -76,15 +79,8 @@ std::vector<camera_relations> link_pairs(const std::vector<LinkImage> &images, c
             continue;
         try
         {
-            const std::vector<feature_2d> &f = *images[i].features;
-            indices[i] = spatially_subsample_feature_indices(f, options.coarse_spacing_pixels,
+            indices[i] = spatially_subsample_feature_indices(*images[i].features, options.coarse_spacing_pixels,
                                                              images[i].num_sparse_features);
-            std::vector<uint64_t> rows(indices[i].size() * OCB_ROW_WORDS);
-            for (size_t k = 0; k < indices[i].size(); k++)
-                std::memcpy(&rows[k * OCB_ROW_WORDS], static_cast<const void *>(&f[indices[i][k]].descriptor),
-                            OCB_ROW_BYTES);
-            detail::gpu_check(ocb_register_descriptors(id_base + i, rows.data(), indices[i].size()),
-                              "ocb_register_descriptors");
         }
         catch (const std::exception &e)
         {
@@ -92,9 +88,41 @@ std::vector<camera_relations> link_pairs(const std::vector<LinkImage> &images, c
             error = e.what();
         }
     }
+    // upload: one batched registration (one device allocation, pipelined gather + copy) per worker, rows taken
+    // straight from the feature vectors through the subsample indices
+    std::vector<size_t> used_ids;
+    for (size_t i = 0; i < n_img; i++)
+        if (used[i])
+            used_ids.push_back(i);
+    std::vector<char> registered(n_img, 0);
+    const int groups = (int)std::min<size_t>((size_t)std::min(threads, 8), std::max<size_t>(used_ids.size(), 1));
+    if (error.empty())
+    {
+#pragma omp parallel for schedule(static, 1) num_threads(groups)
+        for (int g = 0; g < groups; g++)
+        {
+            std::vector<ocb_set_source> src;
+            for (size_t u = (size_t)g; u < used_ids.size(); u += (size_t)groups)
+            {
+                const size_t i = used_ids[u];
+                const std::vector<feature_2d> &f = *images[i].features;
+                src.push_back(ocb_set_source{id_base + i, f.empty() ? nullptr : static_cast<const void *>(&f[0].descriptor),
+                                             sizeof(feature_2d), indices[i].data(), indices[i].size()});
+            }
+            const int rc = ocb_register_descriptors_batch(src.data(), src.size());
+#pragma omp critical(ocb_link_error)
+            {
+                if (rc)
+                    error = std::string("ocb_register_descriptors_batch: ") + ocb_last_error();
+                else
+                    for (const ocb_set_source &sset : src)
+                        registered[sset.set_id - id_base] = 1;
+            }
+        }
+    }
     auto release_sets = [&]() {
         for (size_t i = 0; i < n_img; i++)
-            if (used[i])
+            if (registered[i])
                 ocb_unregister_descriptors(id_base + i);
     };
     if (!error.empty())
@@ -105,88 +133,134 @@ std::vector<camera_relations> link_pairs(const std::vector<LinkImage> &images, c
     LinkStats st;
     st.seconds_subsample_upload = since(t_begin);
 
-    // ---- submissions: GPU matches chunk k+1 while the workers finish chunk k
-    struct Chunk
+    // ---- submissions: one long-lived thread keeps the GPU matching chunk k+1 (into the other of two page-locked
+    // result buffers) while the OpenMP workers finish chunk k
+    const size_t per = std::max<size_t>(1, options.pairs_per_submission);
+    const size_t n_chunks = (n_pairs + per - 1) / per;
+    size_t max_rows = 1;
+    for (size_t c = 0; c < n_chunks; c++)
     {
-        size_t begin = 0, end = 0;
-        std::vector<ocb_top2> top;
+        size_t rows = 0;
+        for (size_t p = c * per; p < std::min(n_pairs, (c + 1) * per); p++)
+            rows += indices[pairs[p].image_1].size();
+        max_rows = std::max(max_rows, rows);
+    }
+    struct Slot
+    {
+        ocb_top2 *top = nullptr;
         std::vector<uint64_t> offsets;
         double gpu_seconds = 0;
-    };
-    const size_t per = std::max<size_t>(1, options.pairs_per_submission);
-    auto match_chunk = [&](size_t begin) {
-        Chunk c;
-        c.begin = begin, c.end = std::min(n_pairs, begin + per);
-        std::vector<ocb_pair> sub(c.end - c.begin);
-        c.offsets.resize(sub.size());
-        uint64_t total = 0;
-        for (size_t p = c.begin; p < c.end; p++)
+        bool full = false;
+    } slot[2];
+    for (Slot &sl : slot)
+    {
+        sl.top = static_cast<ocb_top2 *>(ocb_host_alloc(max_rows * sizeof(ocb_top2)));
+        if (!sl.top)
         {
-            sub[p - c.begin] = ocb_pair{id_base + pairs[p].image_1, id_base + pairs[p].image_2};
-            c.offsets[p - c.begin] = total;
-            total += indices[pairs[p].image_1].size();
+            for (Slot &o : slot)
+                ocb_host_free(o.top);
+            release_sets();
+            throw std::runtime_error(std::string("ocb_host_alloc: ") + ocb_last_error());
         }
-        c.top.resize(total);
-        const auto t0 = clock_type::now();
-        detail::gpu_check(ocb_match_pairs(sub.data(), sub.size(), c.top.data(), c.offsets.data()), "ocb_match_pairs");
-        c.gpu_seconds = since(t0);
-        return c;
-    };
+    }
+    std::mutex mu;
+    std::condition_variable cv;
+    std::string producer_error;
+    bool stop = false;
+    std::thread producer([&]() {
+        for (size_t c = 0; c < n_chunks; c++)
+        {
+            Slot &sl = slot[c & 1];
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return !sl.full || stop; });
+                if (stop)
+                    return;
+            }
+            const size_t begin = c * per, end = std::min(n_pairs, begin + per);
+            std::vector<ocb_pair> sub(end - begin);
+            sl.offsets.resize(sub.size());
+            uint64_t total = 0;
+            for (size_t p = begin; p < end; p++)
+            {
+                sub[p - begin] = ocb_pair{id_base + pairs[p].image_1, id_base + pairs[p].image_2};
+                sl.offsets[p - begin] = total;
+                total += indices[pairs[p].image_1].size();
+            }
+            const auto t0 = clock_type::now();
+            const int rc = ocb_match_pairs(sub.data(), sub.size(), sl.top, sl.offsets.data());
+            sl.gpu_seconds = since(t0);
+            std::lock_guard<std::mutex> lk(mu);
+            if (rc)
+            {
+                producer_error = std::string("ocb_match_pairs: ") + ocb_last_error();
+                stop = true;
+            }
+            sl.full = true;
+            cv.notify_all();
+            if (rc)
+                return;
+        }
+    });
 
     std::vector<camera_relations> relations(n_pairs);
     size_t total_matches = 0, total_inliers = 0;
-    try
+    for (size_t c = 0; c < n_chunks && error.empty(); c++)
     {
-        std::future<Chunk> next;
-        if (n_pairs)
-            next = std::async(std::launch::async, match_chunk, (size_t)0);
-        for (size_t begin = 0; begin < n_pairs; begin += per)
+        Slot &sl = slot[c & 1];
         {
-            Chunk c = next.get();
-            st.seconds_match_gpu += c.gpu_seconds;
-            if (c.end < n_pairs)
-                next = std::async(std::launch::async, match_chunk, c.end);
-            const auto t0 = clock_type::now();
-#pragma omp parallel for schedule(dynamic, 1) num_threads(threads) reduction(+ : total_matches, total_inliers)
-            for (size_t p = c.begin; p < c.end; p++)
+            std::unique_lock<std::mutex> lk(mu);
+            cv.wait(lk, [&] { return sl.full; });
+            if (!producer_error.empty())
             {
-                try
-                {
-                    const LinkImage &img = images[pairs[p].image_1], &near_image = images[pairs[p].image_2];
-                    std::vector<feature_match> coarse_matches =
-                        detail::matches_from_top2(indices[pairs[p].image_1], indices[pairs[p].image_2],
-                                                  c.top.data() + c.offsets[p - c.begin], nullptr, nullptr);
-                    total_matches += coarse_matches.size();
-                    if (options.run_ransac)
-                    {
-                        size_t inl = 0;
-                        finish_pair(img, near_image, relations[p], std::move(coarse_matches), &inl);
-                        total_inliers += inl;
-                    }
-                    else
-                        relations[p].matches = std::move(coarse_matches);
-                }
-                catch (const std::exception &e)
-                {
-#pragma omp critical(ocb_link_error)
-                    error = e.what();
-                }
-            }
-            st.seconds_tail += since(t0);
-            if (!error.empty())
-            {
-                if (next.valid())
-                    next.wait();
-                throw std::runtime_error(error);
+                error = producer_error;
+                break;
             }
         }
+        st.seconds_match_gpu += sl.gpu_seconds;
+        const size_t begin = c * per, end = std::min(n_pairs, begin + per);
+        const auto t0 = clock_type::now();
+#pragma omp parallel for schedule(dynamic, 1) num_threads(threads) reduction(+ : total_matches, total_inliers)
+        for (size_t p = begin; p < end; p++)
+        {
+            try
+            {
+                const LinkImage &img = images[pairs[p].image_1], &near_image = images[pairs[p].image_2];
+                std::vector<feature_match> coarse_matches =
+                    detail::matches_from_top2(indices[pairs[p].image_1], indices[pairs[p].image_2],
+                                              sl.top + sl.offsets[p - begin], nullptr, nullptr);
+                total_matches += coarse_matches.size();
+                if (options.run_ransac)
+                {
+                    size_t inl = 0;
+                    finish_pair(img, near_image, relations[p], std::move(coarse_matches), &inl);
+                    total_inliers += inl;
+                }
+                else
+                    relations[p].matches = std::move(coarse_matches);
+            }
+            catch (const std::exception &e)
+            {
+#pragma omp critical(ocb_link_error)
+                error = e.what();
+            }
+        }
+        st.seconds_tail += since(t0);
+        std::lock_guard<std::mutex> lk(mu);
+        sl.full = false;
+        cv.notify_all();
     }
-    catch (...)
     {
-        release_sets();
-        throw;
+        std::lock_guard<std::mutex> lk(mu);
+        stop = true;
+        cv.notify_all();
     }
+    producer.join();
+    for (Slot &sl : slot)
+        ocb_host_free(sl.top);
     release_sets();
+    if (!error.empty())
+        throw std::runtime_error(error);
     for (const LinkPair &p : pairs)
         st.comparisons += indices[p.image_1].size() * indices[p.image_2].size();
     st.matches = total_matches;

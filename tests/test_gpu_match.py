@@ -151,6 +151,28 @@ def test_batched_pairs_match_single_calls(gpu, oracle):
         gpu.unregister_descriptors(1000)
 
 
+def test_batched_registration_shares_one_allocation(gpu, oracle):
+    a, b = synthetic.config2_pair(3000, 2500, seed=31)
+    rec = np.zeros((3000, 96), np.uint8)
+    rec[:, 24:88] = a.view(np.uint8).reshape(3000, 64)
+    idx = np.random.default_rng(2).permutation(3000)[:1700].astype(np.uintp)
+    gpu.register_descriptors_batch([(7001, rec.reshape(-1)[24:], 96, idx, len(idx)),
+                                    (7002, b.view(np.uint8).reshape(-1), 64, None, len(b)),
+                                    (7003, b.view(np.uint8).reshape(-1), 64, None, 0)])
+    out, offs = gpu.match_pairs([(7001, 7002), (7002, 7001), (7003, 7001), (7001, 7003)], [1700, 2500, 0, 1700])
+    assert_top2_equal(out[:1700], oracle.match_top2(a[idx], b))
+    assert_top2_equal(out[1700:4200], oracle.match_top2(b, a[idx]))
+    assert np.all(out[4200:]["best_d"] == 0xFFFF)  # no candidates
+    gpu.unregister_descriptors(7002)  # the shared allocation must survive for the remaining sets
+    out, _ = gpu.match_pairs([(7001, 7001)], [1700])
+    assert_top2_equal(out, oracle.match_top2(a[idx], a[idx]))
+    gpu.register_descriptors(7001, b[:10])  # replacing a batched set by a plain one
+    out, _ = gpu.match_pairs([(7001, 7001)], [10])
+    assert np.all(out["best_d"] == 0)
+    for sid in (7001, 7003):
+        gpu.unregister_descriptors(sid)
+
+
 def test_config1_pair_through_the_mirror(gpu, hostlib, config1, golden):
     # BASELINE configs[0]: test_match's flow on the repo pair; golden = the reference's own match_features.cpp
     ia = hostlib.spatially_subsample_feature_indices(config1["a_xy"], config1["a_strength"], 40.0)
