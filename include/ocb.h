@@ -162,6 +162,18 @@ extern "C"
      * prefix test (ransac.cpp:197-202) exactly for the rare hypotheses that beat the best score. */
     int ocb_residuals(int kind, const double *model18, const double *corr, size_t n, double *e);
 
+    /* One RANSAC run scores many batches of models (and single models: evaluate, residuals) against the SAME
+     * correspondences (src/model_inliers/ransac.cpp:162-252). ocb_corr_bind uploads and prepares them once for the
+     * calling thread (index order, and evaluation order when `order` is given); ocb_score_bound /
+     * ocb_residuals_bound then behave exactly like ocb_score_models (order = in_order ? the bound order : NULL) and
+     * ocb_residuals, without re-sending the correspondences. The binding is per thread and lasts until the next
+     * ocb_corr_bind / ocb_corr_unbind on that thread. */
+    int ocb_corr_bind(const double *corr, size_t n, const uint32_t *order);
+    int ocb_corr_unbind(void);
+    int ocb_score_bound(int kind, const double *models, size_t h, double thr, int in_order, double *score,
+                        uint32_t *count, uint32_t *inlier_bits);
+    int ocb_residuals_bound(int kind, const double *model18, double *e);
+
     /* Device-resident variant of ocb_score_models. d_corr4: [n][4] doubles (x1,y1,x2,y2) = measurement / z,
      * already in evaluation order; d_pos: nullable [n] uint32 correspondence index of each evaluation
      * position (for the bit mask); everything else as above but device pointers. */

@@ -77,6 +77,11 @@ struct ThreadCtx
                                    // kernels of other host threads (RANSAC scoring of the previous submission) are
                                    // dispatched ahead of the thousands of queued matching CTAs
     Buf dev, pinned;
+    // correspondences bound to this thread by ocb_corr_bind (one RANSAC run scores many model batches against the
+    // same set): [n][7] as given, [n] double4 in index order, [n] double4 + positions in evaluation order
+    Buf bound;
+    size_t bound_n = 0;
+    bool bound_valid = false, bound_has_order = false;
     int ready_device = -1;
 
     int ensure()
@@ -151,6 +156,8 @@ struct ThreadCtx
                 cudaFree(dev.p);
             if (pinned.p)
                 cudaFreeHost(pinned.p);
+            if (bound.p)
+                cudaFree(bound.p);
             if (stream)
                 cudaStreamDestroy(stream);
             if (bulk)
@@ -161,6 +168,8 @@ struct ThreadCtx
         }
         dev = Buf();
         pinned = Buf();
+        bound = Buf();
+        bound_valid = false;
         stream = nullptr;
         bulk = nullptr;
         ready = false;
@@ -891,6 +900,179 @@ extern "C"
         memcpy(count, hp + s_cnt, h * sizeof(uint32_t));
         if (bb)
             memcpy(inlier_bits, hp + s_bits, bb);
+        return 0;
+    }
+
+    // ---- correspondences resident for the calling thread ------------------------------------------------
+    namespace
+    {
+    struct BoundLayout
+    {
+        size_t o_c7, o_nat, o_ord, o_pos, total;
+    };
+    BoundLayout bound_layout(size_t n)
+    {
+        Carver cv;
+        BoundLayout L;
+        L.o_c7 = cv.take(n * 7 * sizeof(double));
+        L.o_nat = cv.take(n * 32);
+        L.o_ord = cv.take(n * 32);
+        L.o_pos = cv.take(n * sizeof(uint32_t));
+        L.total = cv.off;
+        return L;
+    }
+    } // namespace
+
+    int ocb_corr_bind(const double *corr, size_t n, const uint32_t *order)
+    {
+        if (n >= 0xFFFFFFFFull)
+            return fail_invalid("n must fit in 32 bits");
+        if (n && !corr)
+            return fail_invalid("corr");
+        ThreadCtx &cx = t_ctx;
+        int rc = cx.ensure();
+        if (rc)
+            return rc;
+        cx.bound_valid = false;
+        const BoundLayout L = bound_layout(n);
+        if (L.total > cx.bound.cap)
+        {
+            OCB_CUDA(cudaStreamSynchronize(cx.stream));
+            if (cx.bound.p)
+                OCB_CUDA(cudaFree(cx.bound.p));
+            cx.bound = Buf();
+            const size_t cap = std::max(L.total * 2, (size_t)1 << 20);
+            OCB_CUDA(cudaMalloc(&cx.bound.p, cap));
+            cx.bound.cap = cap;
+        }
+        const size_t cb = n * 7 * sizeof(double), ob = order ? n * sizeof(uint32_t) : 0;
+        Carver sv;
+        const size_t s_c7 = sv.take(cb), s_ord = sv.take(ob);
+        Carver dv;
+        const size_t o_ord32 = dv.take(ob);
+        if ((rc = cx.pinned_reserve(sv.off)) || (rc = cx.dev_reserve(dv.off)))
+            return rc;
+        char *b = static_cast<char *>(cx.bound.p);
+        char *d = static_cast<char *>(cx.dev.p);
+        if (n)
+        {
+            if ((rc = upload(cx, b + L.o_c7, corr, cb, s_c7)))
+                return rc;
+            if (order && (rc = upload(cx, d + o_ord32, order, ob, s_ord)))
+                return rc;
+            rc = k2_prepare(reinterpret_cast<double *>(b + L.o_c7), nullptr, n, reinterpret_cast<double *>(b + L.o_nat),
+                            nullptr, cx.stream);
+            if (!rc && order)
+                rc = k2_prepare(reinterpret_cast<double *>(b + L.o_c7), reinterpret_cast<uint32_t *>(d + o_ord32), n,
+                                reinterpret_cast<double *>(b + L.o_ord), reinterpret_cast<uint32_t *>(b + L.o_pos),
+                                cx.stream);
+            if (rc)
+                return rc;
+            // the order indices live in the per-call buffer: they must be consumed before the next call reuses it
+            OCB_CUDA(cudaStreamSynchronize(cx.stream));
+        }
+        cx.bound_n = n;
+        cx.bound_has_order = order != nullptr;
+        cx.bound_valid = true;
+        return 0;
+    }
+
+    int ocb_corr_unbind(void)
+    {
+        t_ctx.bound_valid = false;
+        return 0;
+    }
+
+    int ocb_score_bound(int kind, const double *models, size_t h, double thr, int in_order, double *score,
+                        uint32_t *count, uint32_t *inlier_bits)
+    {
+        if (kind < 0 || kind > 2)
+            return fail_invalid("kind");
+        if (h >= 0xFFFFFFFFull)
+            return fail_invalid("sizes must fit in 32 bits");
+        ThreadCtx &cx = t_ctx;
+        int rc = cx.ensure();
+        if (rc)
+            return rc;
+        if (!cx.bound_valid)
+            return fail_invalid("no correspondences bound on this thread (ocb_corr_bind)");
+        if (in_order && !cx.bound_has_order)
+            return fail_invalid("correspondences were bound without an evaluation order");
+        if (h == 0)
+            return 0;
+        if (!models || !score || !count)
+            return fail_invalid("null pointer");
+        const size_t n = cx.bound_n, words = (n + 31) / 32;
+        const BoundLayout L = bound_layout(n);
+        const size_t mb = h * 18 * sizeof(double), bb = inlier_bits ? h * words * sizeof(uint32_t) : 0;
+        Carver cv;
+        const size_t o_m = cv.take(mb), o_sc = cv.take(h * sizeof(double)), o_cnt = cv.take(h * sizeof(uint32_t)),
+                     o_bits = cv.take(bb), o_scr = cv.take(in_order ? bb : 0);
+        Carver sv;
+        const size_t s_m = sv.take(mb), s_sc = sv.take(h * sizeof(double)), s_cnt = sv.take(h * sizeof(uint32_t)),
+                     s_bits = sv.take(bb);
+        if ((rc = cx.dev_reserve(cv.off)) || (rc = cx.pinned_reserve(sv.off)))
+            return rc;
+        char *b = static_cast<char *>(cx.bound.p);
+        char *d = static_cast<char *>(cx.dev.p);
+        char *hp = static_cast<char *>(cx.pinned.p);
+        if ((rc = upload(cx, d + o_m, models, mb, s_m)))
+            return rc;
+        rc = k2_score(kind, reinterpret_cast<double *>(d + o_m), h,
+                      reinterpret_cast<double *>(b + (in_order ? L.o_ord : L.o_nat)),
+                      in_order ? reinterpret_cast<uint32_t *>(b + L.o_pos) : nullptr, n, thr,
+                      reinterpret_cast<double *>(d + o_sc), reinterpret_cast<uint32_t *>(d + o_cnt),
+                      inlier_bits ? reinterpret_cast<uint32_t *>(d + o_bits) : nullptr,
+                      reinterpret_cast<uint32_t *>(d + o_scr), cx.stream);
+        if (rc)
+            return rc;
+        OCB_CUDA(cudaMemcpyAsync(hp + s_sc, d + o_sc, h * sizeof(double), cudaMemcpyDeviceToHost, cx.stream));
+        OCB_CUDA(cudaMemcpyAsync(hp + s_cnt, d + o_cnt, h * sizeof(uint32_t), cudaMemcpyDeviceToHost, cx.stream));
+        if (bb)
+            OCB_CUDA(cudaMemcpyAsync(hp + s_bits, d + o_bits, bb, cudaMemcpyDeviceToHost, cx.stream));
+        OCB_CUDA(cudaStreamSynchronize(cx.stream));
+        memcpy(score, hp + s_sc, h * sizeof(double));
+        memcpy(count, hp + s_cnt, h * sizeof(uint32_t));
+        if (bb)
+            memcpy(inlier_bits, hp + s_bits, bb);
+        return 0;
+    }
+
+    int ocb_residuals_bound(int kind, const double *model18, double *e)
+    {
+        if (kind < 0 || kind > 2)
+            return fail_invalid("kind");
+        ThreadCtx &cx = t_ctx;
+        int rc = cx.ensure();
+        if (rc)
+            return rc;
+        if (!cx.bound_valid)
+            return fail_invalid("no correspondences bound on this thread (ocb_corr_bind)");
+        const size_t n = cx.bound_n;
+        if (n == 0)
+            return 0;
+        if (!model18 || !e)
+            return fail_invalid("null pointer");
+        const BoundLayout L = bound_layout(n);
+        const size_t eb = n * sizeof(double);
+        Carver cv;
+        const size_t o_m = cv.take(18 * sizeof(double)), o_e = cv.take(eb);
+        Carver sv;
+        const size_t s_m = sv.take(18 * sizeof(double)), s_e = sv.take(eb);
+        if ((rc = cx.dev_reserve(cv.off)) || (rc = cx.pinned_reserve(sv.off)))
+            return rc;
+        char *b = static_cast<char *>(cx.bound.p);
+        char *d = static_cast<char *>(cx.dev.p);
+        char *hp = static_cast<char *>(cx.pinned.p);
+        if ((rc = upload(cx, d + o_m, model18, 18 * sizeof(double), s_m)))
+            return rc;
+        rc = k2_residuals(kind, reinterpret_cast<double *>(d + o_m), reinterpret_cast<double *>(b + L.o_c7), n,
+                          reinterpret_cast<double *>(d + o_e), cx.stream);
+        if (rc)
+            return rc;
+        OCB_CUDA(cudaMemcpyAsync(hp + s_e, d + o_e, eb, cudaMemcpyDeviceToHost, cx.stream));
+        OCB_CUDA(cudaStreamSynchronize(cx.stream));
+        memcpy(e, hp + s_e, eb);
         return 0;
     }
 

@@ -13,6 +13,12 @@ namespace ocb_host
 namespace linalg
 {
 
+// The tall systems of fitInliers ((2n+1) x 9, n up to thousands) make this the hottest host routine of the RANSAC
+// tail: the pivot search and the rank-1 update are plain column sweeps, cloned for wider vector units (the build is
+// generic x86-64; -ffp-contract=off keeps every multiply and subtract individually rounded in all clones).
+#if defined(__x86_64__) && defined(__GNUC__) && !defined(__clang__)
+__attribute__((target_clones("avx512f", "avx2", "default")))
+#endif
 std::vector<double> full_piv_lu_solve(const ColMat &A, const std::vector<double> &b)
 {
     const int R = A.rows, Cn = A.cols, K = std::min(R, Cn);
@@ -31,9 +37,18 @@ std::vector<double> full_piv_lu_solve(const ColMat &A, const std::vector<double>
         for (int c = k; c < Cn; ++c)
         {
             const double *col = &lu.a[(size_t)c * R];
+            // eight independent running maxima: a single one is a serial dependency chain the compiler may not
+            // reorder; the maximum itself does not depend on the order (NaNs lose every comparison either way)
+            double m[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            int r = k;
+            for (; r + 8 <= R; r += 8)
+                for (int j = 0; j < 8; ++j)
+                    m[j] = std::max(m[j], std::fabs(col[r + j]));
+            for (; r < R; ++r)
+                m[0] = std::max(m[0], std::fabs(col[r]));
             double cmax = 0.0;
-            for (int r = k; r < R; ++r)
-                cmax = std::max(cmax, std::fabs(col[r]));
+            for (int j = 0; j < 8; ++j)
+                cmax = std::max(cmax, m[j]);
             if (cmax > best)
             {
                 best = cmax, pc = c;

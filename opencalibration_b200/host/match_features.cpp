@@ -8,7 +8,6 @@
 #include <cmath>
 #include <cstring>
 #include <limits>
-#include <unordered_map>
 
 namespace
 {
@@ -115,19 +114,40 @@ std::vector<size_t> spatially_subsample_feature_indices(const std::vector<featur
     kept.reserve(features.size() / 4);
     const double limit = spacing_pixels * spacing_pixels;
     const bool gridded = spacing_pixels > 0 && std::isfinite(spacing_pixels);
-    std::unordered_map<uint64_t, std::vector<size_t>> cells;
+    // kept points bucketed by grid cell (cell = spacing) in a flat chained hash table: a point closer than `spacing`
+    // lies at most one cell away; two cells are searched so that a quotient rounded across a cell border cannot hide it
+    size_t table_size = 64;
+    while (table_size < 4 * count)
+        table_size <<= 1;
+    std::vector<int32_t> head(table_size, -1);
+    struct Entry
+    {
+        uint64_t key;
+        int32_t next;
+        size_t idx;
+    };
+    std::vector<Entry> entries;
+    entries.reserve(count);
     auto cell_key = [](int64_t cx, int64_t cy) {
         return (static_cast<uint64_t>(static_cast<uint32_t>(cx)) << 32) | static_cast<uint32_t>(cy);
+    };
+    auto slot_of = [table_size](uint64_t key) {
+        key ^= key >> 33;
+        key *= 0xff51afd7ed558ccdull;
+        key ^= key >> 33;
+        return static_cast<size_t>(key) & (table_size - 1);
     };
     auto too_close = [&](size_t idx, size_t other) {
         const double dx = features[idx].location.x() - features[other].location.x();
         const double dy = features[idx].location.y() - features[other].location.y();
         return !(dx * dx + dy * dy > limit);
     };
+    std::vector<size_t> unbucketed; // kept points with non-finite coordinates (compared against everything)
     for (size_t idx : by_strength)
     {
         const double x = features[idx].location.x(), y = features[idx].location.y();
-        const bool finite = gridded && std::isfinite(x) && std::isfinite(y);
+        const bool finite = gridded && std::isfinite(x) && std::isfinite(y) && std::abs(x / spacing_pixels) < 1e9 &&
+                            std::abs(y / spacing_pixels) < 1e9;
         bool keep = true;
         if (!kept.empty())
         {
@@ -137,16 +157,17 @@ std::vector<size_t> spatially_subsample_feature_indices(const std::vector<featur
                 for (int64_t gx = cx - 2; gx <= cx + 2 && keep; gx++)
                     for (int64_t gy = cy - 2; gy <= cy + 2 && keep; gy++)
                     {
-                        auto it = cells.find(cell_key(gx, gy));
-                        if (it == cells.end())
-                            continue;
-                        for (size_t other : it->second)
-                            if (too_close(idx, other))
+                        const uint64_t key = cell_key(gx, gy);
+                        for (int32_t e = head[slot_of(key)]; e >= 0; e = entries[e].next)
+                            if (entries[e].key == key && too_close(idx, entries[e].idx))
                             {
                                 keep = false;
                                 break;
                             }
                     }
+                for (size_t other : unbucketed)
+                    if (keep && too_close(idx, other))
+                        keep = false;
             }
             else
             {
@@ -161,7 +182,14 @@ std::vector<size_t> spatially_subsample_feature_indices(const std::vector<featur
         if (!keep)
             continue;
         if (finite)
-            cells[cell_key((int64_t)std::floor(x / spacing_pixels), (int64_t)std::floor(y / spacing_pixels))].push_back(idx);
+        {
+            const uint64_t key = cell_key((int64_t)std::floor(x / spacing_pixels), (int64_t)std::floor(y / spacing_pixels));
+            const size_t sl = slot_of(key);
+            entries.push_back(Entry{key, head[sl], idx});
+            head[sl] = (int32_t)(entries.size() - 1);
+        }
+        else
+            unbucketed.push_back(idx);
         kept.push_back(idx);
     }
     return kept;

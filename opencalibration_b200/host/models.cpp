@@ -84,6 +84,60 @@ double epipolar_error(const double *E, const opencalibration::correspondence &c)
     return std::sqrt((num * num) / denom);
 }
 
+namespace
+{
+struct BoundState
+{
+    const void *data = nullptr;
+    size_t n = 0;
+    const uint32_t *order = nullptr;
+};
+thread_local BoundState t_bound;
+bool is_bound(const std::vector<opencalibration::correspondence> &corrs)
+{
+    return t_bound.data != nullptr && t_bound.data == static_cast<const void *>(corrs.data()) &&
+           t_bound.n == corrs.size();
+}
+} // namespace
+
+BoundCorrespondences::BoundCorrespondences(const std::vector<opencalibration::correspondence> &corrs,
+                                           const uint32_t *order)
+    : prev_data_(t_bound.data), prev_n_(t_bound.n), prev_order_(t_bound.order)
+{
+    t_bound = BoundState();
+    if (corrs.empty())
+        return;
+    gpu_check(ocb_corr_bind(corr_data(corrs), corrs.size(), order), "ocb_corr_bind");
+    t_bound.data = corrs.data(), t_bound.n = corrs.size(), t_bound.order = order;
+}
+
+BoundCorrespondences::~BoundCorrespondences()
+{
+    t_bound = BoundState();
+    ocb_corr_unbind();
+    if (prev_data_ && ocb_corr_bind(static_cast<const double *>(prev_data_), prev_n_, prev_order_) == 0)
+        t_bound.data = prev_data_, t_bound.n = prev_n_, t_bound.order = prev_order_;
+}
+
+void gpu_residuals(int kind, const double *m18, const std::vector<opencalibration::correspondence> &corrs, double *e)
+{
+    if (is_bound(corrs))
+        gpu_check(ocb_residuals_bound(kind, m18, e), "ocb_residuals_bound");
+    else
+        gpu_check(ocb_residuals(kind, m18, corr_data(corrs), corrs.size(), e), "ocb_residuals");
+}
+
+void gpu_score_in_order(int kind, const double *models18, size_t h,
+                        const std::vector<opencalibration::correspondence> &corrs, double thr, const uint32_t *order,
+                        double *score, uint32_t *count)
+{
+    if (is_bound(corrs) && t_bound.order == order && order != nullptr)
+        gpu_check(ocb_score_bound(kind, models18, h, thr, 1, score, count, nullptr), "ocb_score_bound");
+    else
+        gpu_check(ocb_score_models(kind, models18, h, corr_data(corrs), corrs.size(), thr, order, score, count, nullptr),
+                  "ocb_score_models");
+}
+
 double gpu_evaluate(int kind, const double *matrix9, const double *inverse9, double thr,
                     const std::vector<opencalibration::correspondence> &corrs, std::vector<bool> &inliers)
 {
@@ -101,8 +155,11 @@ double gpu_evaluate(int kind, const double *matrix9, const double *inverse9, dou
     std::vector<uint32_t> bits((n + 31) / 32);
     double score = 0.0;
     uint32_t count = 0;
-    gpu_check(ocb_score_models(kind, m18, 1, corr_data(corrs), n, thr, nullptr, &score, &count, bits.data()),
-              "ocb_score_models");
+    if (is_bound(corrs))
+        gpu_check(ocb_score_bound(kind, m18, 1, thr, 0, &score, &count, bits.data()), "ocb_score_bound");
+    else
+        gpu_check(ocb_score_models(kind, m18, 1, corr_data(corrs), n, thr, nullptr, &score, &count, bits.data()),
+                  "ocb_score_models");
     for (size_t i = 0; i < n; i++)
         inliers[i] = (bits[i >> 5] >> (i & 31)) & 1u;
     return score;
@@ -434,7 +491,7 @@ void fundamental_matrix_model::checkDegeneracy(const std::vector<correspondence>
         double m18[18];
         std::memcpy(m18, plane.homography.data(), 72);
         std::memcpy(m18 + 9, plane.homography_inverse.data(), 72);
-        gpu_check(ocb_residuals(OCB_MODEL_HOMOGRAPHY, m18, corr_data(corrs), corrs.size(), e.data()), "ocb_residuals");
+        gpu_residuals(OCB_MODEL_HOMOGRAPHY, m18, corrs, e.data());
     };
     plane_residuals();
     std::vector<bool> on_plane(corrs.size(), false);

@@ -19,6 +19,28 @@ const double *corr_data(const std::vector<opencalibration::correspondence> &c);
 
 double homography_error(const double *H, const double *Hinv, const opencalibration::correspondence &c);
 double epipolar_error(const double *E, const opencalibration::correspondence &c);
+// While alive, the correspondences are resident on the GPU for the calling thread (ocb_corr_bind): every
+// gpu_evaluate / gpu_residuals / gpu_score_in_order on the SAME vector skips the upload. ransac() holds one for
+// the duration of a run. Nesting restores the outer binding on destruction.
+class BoundCorrespondences
+{
+  public:
+    BoundCorrespondences(const std::vector<opencalibration::correspondence> &corrs, const uint32_t *order);
+    ~BoundCorrespondences();
+    BoundCorrespondences(const BoundCorrespondences &) = delete;
+    BoundCorrespondences &operator=(const BoundCorrespondences &) = delete;
+
+  private:
+    const void *prev_data_;
+    size_t prev_n_;
+    const uint32_t *prev_order_;
+};
+// Model::error for every correspondence (index order) of one model
+void gpu_residuals(int kind, const double *m18, const std::vector<opencalibration::correspondence> &corrs, double *e);
+// the score loop of ransac.cpp:183-196 for a batch of models, summed in `order`
+void gpu_score_in_order(int kind, const double *models18, size_t h,
+                        const std::vector<opencalibration::correspondence> &corrs, double thr, const uint32_t *order,
+                        double *score, uint32_t *count);
 double gpu_evaluate(int kind, const double *matrix9, const double *inverse9, double thr,
                     const std::vector<opencalibration::correspondence> &corrs, std::vector<bool> &inliers);
 

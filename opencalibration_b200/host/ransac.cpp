@@ -182,6 +182,10 @@ double ransac(const std::vector<correspondence> &matches, Model &model, std::vec
     for (size_t p = 0; p < N; p++)
         order32[p] = static_cast<uint32_t>(stream.eval_order[p]);
 
+    // the correspondences stay on the GPU for the whole run: every batch, residual fetch and evaluate() below
+    // sends only its models
+    const BoundCorrespondences resident(matches, order32.data());
+
     Model best_model{};
     double best_score = 0;
     size_t probability_iterations = MAX_ITERATIONS;
@@ -218,9 +222,8 @@ double ransac(const std::vector<correspondence> &matches, Model &model, std::vec
         }
         batch_score.assign(want, 0.0);
         batch_count.assign(want, 0);
-        gpu_check(ocb_score_models(kind, batch_m18.data(), want, corr_data(matches), N, thr, order32.data(),
-                                   batch_score.data(), batch_count.data(), nullptr),
-                  "ocb_score_models");
+        gpu_score_in_order(kind, batch_m18.data(), want, matches, thr, order32.data(), batch_score.data(),
+                           batch_count.data());
         stats.gpu_calls++;
         stats.scored += want;
 
@@ -236,7 +239,7 @@ double ransac(const std::vector<correspondence> &matches, Model &model, std::vec
 
             // would-be improver: replay ransac.cpp:183-203 on its residuals
             model = batch_models[b];
-            gpu_check(ocb_residuals(kind, &batch_m18[b * 18], corr_data(matches), N, residual.data()), "ocb_residuals");
+            gpu_residuals(kind, &batch_m18[b * 18], matches, residual.data());
             stats.gpu_calls++;
             double score = 0;
             size_t checked = 0;
