@@ -174,6 +174,44 @@ extern "C"
                         uint32_t *count, uint32_t *inlier_bits);
     int ocb_residuals_bound(int kind, const double *model18, double *e);
 
+    /* Batched form for a whole submission of image pairs (the batched LinkStage runner advances the RANSAC runs of
+     * all its pairs in lock step): ocb_corr_bind_batch makes `count` correspondence sets resident for the calling
+     * thread with one copy; ocb_score_requests then serves any mix of requests against them with ONE kernel launch
+     * and one copy each way:
+     *   mode OCB_REQ_SCORE_ORDERED  h models scored in the set's evaluation order -> score[h], count[h]
+     *                               (the score loop of src/model_inliers/ransac.cpp:183-196, no early exit)
+     *   mode OCB_REQ_EVALUATE       h models in index order -> score[h], count[h], inlier_bits[h][ceil(n/32)]
+     *                               (Model::evaluate, homography_model.cpp:99-118 and twins)
+     *   mode OCB_REQ_RESIDUALS      one model -> residuals[n] (Model::error per correspondence)
+     * Results are bit-identical to ocb_score_models / ocb_residuals on the same inputs. */
+    typedef struct ocb_corr_set
+    {
+        const double *corr;    /* [n][7] */
+        size_t n;
+        const uint32_t *order; /* nullable [n] */
+    } ocb_corr_set;
+    enum ocb_request_mode
+    {
+        OCB_REQ_SCORE_ORDERED = 0,
+        OCB_REQ_EVALUATE = 1,
+        OCB_REQ_RESIDUALS = 2
+    };
+    typedef struct ocb_score_request
+    {
+        uint32_t set; /* index into the batch bound by ocb_corr_bind_batch */
+        int32_t kind; /* enum ocb_model_kind */
+        int32_t mode; /* enum ocb_request_mode */
+        uint32_t h;   /* number of models (1 for OCB_REQ_RESIDUALS) */
+        const double *models; /* [h][18] */
+        double thr;
+        double *score;
+        uint32_t *count;
+        uint32_t *inlier_bits;
+        double *residuals;
+    } ocb_score_request;
+    int ocb_corr_bind_batch(const ocb_corr_set *sets, size_t count);
+    int ocb_score_requests(const ocb_score_request *requests, size_t count);
+
     /* Device-resident variant of ocb_score_models. d_corr4: [n][4] doubles (x1,y1,x2,y2) = measurement / z,
      * already in evaluation order; d_pos: nullable [n] uint32 correspondence index of each evaluation
      * position (for the bit mask); everything else as above but device pointers. */

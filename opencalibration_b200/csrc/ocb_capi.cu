@@ -80,6 +80,15 @@ struct ThreadCtx
     // correspondences bound to this thread by ocb_corr_bind (one RANSAC run scores many model batches against the
     // same set): [n][7] as given, [n] double4 in index order, [n] double4 + positions in evaluation order
     Buf bound;
+    // batch binding (ocb_corr_bind_batch): concatenated [n][7] rows and evaluation orders of many sets
+    struct BatchSet
+    {
+        size_t o_c7 = 0, o_ord = 0, n = 0;
+        bool has_order = false;
+    };
+    Buf batch;
+    std::vector<BatchSet> batch_sets;
+    bool batch_valid = false;
     size_t bound_n = 0;
     bool bound_valid = false, bound_has_order = false;
     int ready_device = -1;
@@ -158,6 +167,8 @@ struct ThreadCtx
                 cudaFreeHost(pinned.p);
             if (bound.p)
                 cudaFree(bound.p);
+            if (batch.p)
+                cudaFree(batch.p);
             if (stream)
                 cudaStreamDestroy(stream);
             if (bulk)
@@ -170,6 +181,9 @@ struct ThreadCtx
         pinned = Buf();
         bound = Buf();
         bound_valid = false;
+        batch = Buf();
+        batch_valid = false;
+        batch_sets.clear();
         stream = nullptr;
         bulk = nullptr;
         ready = false;
@@ -232,6 +246,38 @@ int upload(ThreadCtx &c, void *d_dst, const void *h_src, size_t bytes, size_t st
     return 0;
 }
 
+// Descriptor sets come and go with every LinkStage batch; cudaMalloc / cudaFree of hundreds of MB cost tens to hundreds
+// of milliseconds (and cudaFree synchronises the device), so set storage comes from the device's stream-ordered
+// memory pool with a release threshold that keeps freed blocks cached for the next batch.
+cudaError_t set_storage_alloc(void **p, size_t bytes, int device)
+{
+    static std::mutex mu;
+    static std::unordered_map<int, bool> configured;
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        if (!configured[device])
+        {
+            cudaMemPool_t pool;
+            if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess)
+            {
+                uint64_t keep = ~0ull;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            }
+            cudaGetLastError();
+            configured[device] = true;
+        }
+    }
+    cudaError_t e = cudaMallocAsync(p, bytes, cudaStreamPerThread);
+    if (e == cudaSuccess)
+        e = cudaStreamSynchronize(cudaStreamPerThread);
+    return e;
+}
+void set_storage_free(void *p)
+{
+    if (p)
+        cudaFreeAsync(p, cudaStreamPerThread);
+}
+
 // One device allocation shared by the sets of a batched registration; freed with its last set.
 struct Arena
 {
@@ -256,14 +302,14 @@ void free_set_storage(DescSet &s)
         if (--s.arena->live == 0)
         {
             cudaSetDevice(s.arena->device);
-            cudaFree(s.arena->base);
+            set_storage_free(s.arena->base);
             delete s.arena;
         }
     }
     else if (s.d_rows)
     {
         cudaSetDevice(s.device);
-        cudaFree(s.d_rows);
+        set_storage_free(s.d_rows);
     }
     cudaSetDevice(cur);
     s.d_rows = nullptr;
@@ -573,13 +619,13 @@ extern "C"
         s.device = cx.device;
         if (n)
         {
-            OCB_CUDA(cudaMalloc(&s.d_rows, n * OCB_ROW_BYTES));
+            OCB_CUDA(set_storage_alloc(&s.d_rows, n * OCB_ROW_BYTES, cx.device));
             cudaError_t e = cudaMemcpyAsync(s.d_rows, rows, n * OCB_ROW_BYTES, cudaMemcpyHostToDevice, cx.stream);
             if (e == cudaSuccess)
                 e = cudaStreamSynchronize(cx.stream);
             if (e != cudaSuccess)
             {
-                cudaFree(s.d_rows);
+                set_storage_free(s.d_rows);
                 return fail_cuda(e, "upload descriptor set", __FILE__, __LINE__);
             }
         }
@@ -615,7 +661,7 @@ extern "C"
         if (total_rows)
         {
             void *p = nullptr;
-            OCB_CUDA(cudaMalloc(&p, total_rows * OCB_ROW_BYTES));
+            OCB_CUDA(set_storage_alloc(&p, total_rows * OCB_ROW_BYTES, cx.device));
             arena = new Arena;
             arena->base = p, arena->device = cx.device, arena->live = 0;
             d_base = static_cast<char *>(p);
@@ -664,7 +710,7 @@ extern "C"
         {
             if (arena)
             {
-                cudaFree(arena->base);
+                set_storage_free(arena->base);
                 delete arena;
             }
             return rc;
@@ -1073,6 +1119,158 @@ extern "C"
         OCB_CUDA(cudaMemcpyAsync(hp + s_e, d + o_e, eb, cudaMemcpyDeviceToHost, cx.stream));
         OCB_CUDA(cudaStreamSynchronize(cx.stream));
         memcpy(e, hp + s_e, eb);
+        return 0;
+    }
+
+    // ---- many correspondence sets resident at once + request-table scoring --------------------------------
+    int ocb_corr_bind_batch(const ocb_corr_set *sets, size_t count)
+    {
+        ThreadCtx &cx = t_ctx;
+        int rc = cx.ensure();
+        if (rc)
+            return rc;
+        cx.batch_valid = false;
+        cx.batch_sets.clear();
+        if (count && !sets)
+            return fail_invalid("sets");
+        Carver cv;
+        cx.batch_sets.resize(count);
+        for (size_t i = 0; i < count; i++)
+        {
+            if (sets[i].n >= 0xFFFFFFFFull || (sets[i].n && !sets[i].corr))
+                return fail_invalid("correspondence set");
+            cx.batch_sets[i].n = sets[i].n;
+            cx.batch_sets[i].has_order = sets[i].order != nullptr && sets[i].n > 0;
+            cx.batch_sets[i].o_c7 = cv.take(sets[i].n * 7 * sizeof(double));
+            cx.batch_sets[i].o_ord = cv.take(cx.batch_sets[i].has_order ? sets[i].n * sizeof(uint32_t) : 0);
+        }
+        const size_t total = cv.off;
+        if (total > cx.batch.cap)
+        {
+            OCB_CUDA(cudaStreamSynchronize(cx.stream));
+            if (cx.batch.p)
+                OCB_CUDA(cudaFree(cx.batch.p));
+            cx.batch = Buf();
+            const size_t cap = std::max(total + total / 2, (size_t)1 << 20);
+            OCB_CUDA(cudaMalloc(&cx.batch.p, cap));
+            cx.batch.cap = cap;
+        }
+        if (total)
+        {
+            // the staging image mirrors the device layout: one copy moves every set
+            if ((rc = cx.pinned_reserve(total)))
+                return rc;
+            char *hp = static_cast<char *>(cx.pinned.p);
+            for (size_t i = 0; i < count; i++)
+            {
+                if (sets[i].n == 0)
+                    continue;
+                memcpy(hp + cx.batch_sets[i].o_c7, sets[i].corr, sets[i].n * 7 * sizeof(double));
+                if (cx.batch_sets[i].has_order)
+                    memcpy(hp + cx.batch_sets[i].o_ord, sets[i].order, sets[i].n * sizeof(uint32_t));
+            }
+            OCB_CUDA(cudaMemcpyAsync(cx.batch.p, hp, total, cudaMemcpyHostToDevice, cx.stream));
+            OCB_CUDA(cudaStreamSynchronize(cx.stream)); // the staging area is reused by the next call
+        }
+        cx.batch_valid = true;
+        return 0;
+    }
+
+    int ocb_score_requests(const ocb_score_request *req, size_t count)
+    {
+        if (count == 0)
+            return 0;
+        if (!req)
+            return fail_invalid("requests");
+        ThreadCtx &cx = t_ctx;
+        int rc = cx.ensure();
+        if (rc)
+            return rc;
+        if (!cx.batch_valid)
+            return fail_invalid("no correspondence batch bound on this thread (ocb_corr_bind_batch)");
+        // layout of the per-call device block: [request table][models][outputs]; outputs are read back in one copy
+        Carver in_cv, out_cv;
+        const size_t o_tab = in_cv.take(count * sizeof(K2Request));
+        std::vector<size_t> o_models(count), o_score(count), o_count(count), o_aux(count);
+        for (size_t i = 0; i < count; i++)
+        {
+            const ocb_score_request &r = req[i];
+            if (r.kind < 0 || r.kind > 2 || r.mode < 0 || r.mode > 2)
+                return fail_invalid("request kind / mode");
+            if (r.set >= cx.batch_sets.size())
+                return fail_invalid("request references an unbound set");
+            const ThreadCtx::BatchSet &bs = cx.batch_sets[r.set];
+            if (!r.models || r.h == 0 || (r.mode == 2 && (r.h != 1 || !r.residuals)) ||
+                (r.mode != 2 && (!r.score || !r.count)) || (r.mode == 1 && !r.inlier_bits))
+                return fail_invalid("request pointers");
+            if (r.mode == 0 && !bs.has_order && bs.n)
+                return fail_invalid("set was bound without an evaluation order");
+            o_models[i] = in_cv.take((size_t)r.h * 18 * sizeof(double));
+            const size_t words = (bs.n + 31) / 32;
+            if (r.mode == 2)
+                o_aux[i] = out_cv.take(bs.n * sizeof(double));
+            else
+            {
+                o_score[i] = out_cv.take((size_t)r.h * sizeof(double));
+                o_count[i] = out_cv.take((size_t)r.h * sizeof(uint32_t));
+                o_aux[i] = out_cv.take(r.mode == 1 ? (size_t)r.h * words * sizeof(uint32_t) : 0);
+            }
+        }
+        const size_t in_bytes = in_cv.off, out_bytes = out_cv.off;
+        if ((rc = cx.dev_reserve(in_bytes + out_bytes)) || (rc = cx.pinned_reserve(in_bytes + out_bytes)))
+            return rc;
+        char *d = static_cast<char *>(cx.dev.p);
+        char *d_out = d + in_bytes;
+        char *hp = static_cast<char *>(cx.pinned.p);
+        char *b = static_cast<char *>(cx.batch.p);
+        K2Request *tab = reinterpret_cast<K2Request *>(hp + o_tab);
+        uint32_t ctas = 0;
+        for (size_t i = 0; i < count; i++)
+        {
+            const ocb_score_request &r = req[i];
+            const ThreadCtx::BatchSet &bs = cx.batch_sets[r.set];
+            memcpy(hp + o_models[i], r.models, (size_t)r.h * 18 * sizeof(double));
+            K2Request q;
+            memset(&q, 0, sizeof q);
+            q.models = reinterpret_cast<const double *>(d + o_models[i]);
+            q.c7 = reinterpret_cast<const double *>(b + bs.o_c7);
+            q.order = (r.mode == 0 && bs.has_order) ? reinterpret_cast<const uint32_t *>(b + bs.o_ord) : nullptr;
+            q.thr = r.thr;
+            q.h = r.h, q.n = (uint32_t)bs.n, q.words = (uint32_t)((bs.n + 31) / 32);
+            q.kind = r.kind, q.mode = r.mode;
+            if (r.mode == 2)
+                q.e = reinterpret_cast<double *>(d_out + o_aux[i]);
+            else
+            {
+                q.score = reinterpret_cast<double *>(d_out + o_score[i]);
+                q.count = reinterpret_cast<uint32_t *>(d_out + o_count[i]);
+                q.bits = r.mode == 1 ? reinterpret_cast<uint32_t *>(d_out + o_aux[i]) : nullptr;
+            }
+            q.cta_begin = ctas;
+            ctas += k2_request_ctas(q);
+            tab[i] = q;
+        }
+        OCB_CUDA(cudaMemcpyAsync(d, hp, in_bytes, cudaMemcpyHostToDevice, cx.stream));
+        if ((rc = k2_run_requests(reinterpret_cast<const K2Request *>(d + o_tab), count, ctas, cx.stream)))
+            return rc;
+        char *hout = hp + in_bytes;
+        if (out_bytes)
+            OCB_CUDA(cudaMemcpyAsync(hout, d_out, out_bytes, cudaMemcpyDeviceToHost, cx.stream));
+        OCB_CUDA(cudaStreamSynchronize(cx.stream));
+        for (size_t i = 0; i < count; i++)
+        {
+            const ocb_score_request &r = req[i];
+            const size_t n = cx.batch_sets[r.set].n, words = (n + 31) / 32;
+            if (r.mode == 2)
+                memcpy(r.residuals, hout + o_aux[i], n * sizeof(double));
+            else
+            {
+                memcpy(r.score, hout + o_score[i], (size_t)r.h * sizeof(double));
+                memcpy(r.count, hout + o_count[i], (size_t)r.h * sizeof(uint32_t));
+                if (r.mode == 1)
+                    memcpy(r.inlier_bits, hout + o_aux[i], (size_t)r.h * words * sizeof(uint32_t));
+            }
+        }
         return 0;
     }
 

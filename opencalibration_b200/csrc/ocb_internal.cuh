@@ -94,6 +94,23 @@ int k2_score(int kind, const double *d_models, size_t h, const double *d_corr4, 
 int k2_residuals(int kind, const double *d_model18, const double *d_corr7, size_t n, double *d_e,
                  cudaStream_t stream);
 
+// One entry of the request table of k2_requests_kernel (all pointers are device pointers).
+struct K2Request
+{
+    const double *models;  // [h][18] (mode 2: one model)
+    const double *c7;      // [n][7] correspondences as given
+    const uint32_t *order; // mode 0: evaluation order; nullptr = index order
+    double *score;         // [h]
+    uint32_t *count;       // [h]
+    uint32_t *bits;        // mode 1: [h][words] inlier masks in index order; else nullptr
+    double *e;             // mode 2: [n] residuals
+    double thr;
+    uint32_t h, n, words, cta_begin;
+    int32_t kind, mode; // mode 0 = score in evaluation order, 1 = evaluate (index order + bits), 2 = residuals
+};
+uint32_t k2_request_ctas(const K2Request &rq);
+int k2_run_requests(const K2Request *d_requests, size_t n_requests, uint32_t total_ctas, cudaStream_t stream);
+
 // ---- PTX helpers: mbarrier + 1-D bulk (TMA) copies -----------------------------------------------------------
 #if defined(__CUDACC__)
 __device__ __forceinline__ uint32_t smem_u32(const void *p)

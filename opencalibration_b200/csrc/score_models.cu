@@ -216,6 +216,141 @@ __global__ void __launch_bounds__(256)
     e[i] = residual<KIND>(M, c.x, c.y, c.z, c.w);
 }
 
+// ----------------------------------------------------------------------------------------------------------
+// Request-table form: ONE launch serves many small scoring problems (one RANSAC round of a whole batch of image
+// pairs: every pair contributes a batch of hypotheses, a single model to evaluate, or a residual fetch). A CTA finds
+// its request by binary search over cta_begin and then does exactly what the single-problem kernels do; the
+// correspondences are normalised on the fly from the [n][7] rows (through the evaluation order for mode 0), which
+// costs 4 divisions per position per CTA and saves the per-problem prepare launches.
+// ----------------------------------------------------------------------------------------------------------
+template <int KIND>
+__device__ __forceinline__ void score_request(const K2Request &rq, uint32_t local_cta, double (*M)[18],
+                                              double (*contrib)[K2_HG][K2_TP], uint32_t (*mask)[K2_HG][K2_CW + 1])
+{
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t h0 = local_cta * K2_HG;
+    const uint32_t nh = min((uint32_t)K2_HG, rq.h - h0);
+    const uint32_t n = rq.n;
+    const double thr = rq.thr;
+    for (uint32_t i = tid; i < nh * 18; i += K2_THREADS)
+        M[i / 18][i % 18] = rq.models[(size_t)h0 * 18 + i];
+    __syncthreads();
+    const uint32_t rounds = (n + K2_TP - 1) / K2_TP;
+    double s = 0.0;
+    uint32_t cnt = 0;
+    for (uint32_t r = 0; r <= rounds; r++)
+    {
+        if (warp < K2_CW)
+        {
+            if (r < rounds)
+            {
+                const uint32_t p = r * K2_TP + warp * 32 + lane;
+                const bool valid = p < n;
+                double4 c = make_double4(0, 0, 0, 0);
+                if (valid)
+                {
+                    const uint32_t idx = rq.order ? rq.order[p] : p;
+                    c = normalise_corr(rq.c7 + (size_t)idx * 7);
+                }
+#pragma unroll
+                for (int g = 0; g < K2_HG; g++)
+                {
+                    if ((uint32_t)g < nh)
+                    {
+                        const double e = residual<KIND>(M[g], c.x, c.y, c.z, c.w);
+                        const bool inl = valid && (e < thr);
+                        const double ratio = __ddiv_rn(e, thr);
+                        contrib[r & 1][g][warp * 32 + lane] = __dsub_rn(1.0, __dmul_rn(ratio, ratio));
+                        const uint32_t m = __ballot_sync(0xFFFFFFFFu, inl);
+                        if (lane == 0)
+                        {
+                            mask[r & 1][g][warp] = m;
+                            if (rq.bits && (p >> 5) < rq.words)
+                                rq.bits[(size_t)(h0 + g) * rq.words + (p >> 5)] = m;
+                        }
+                    }
+                }
+            }
+        }
+        else if (r > 0 && lane < nh)
+        {
+            const uint32_t b = (r - 1) & 1;
+#pragma unroll
+            for (int w = 0; w < K2_CW; w++)
+            {
+                uint32_t m = mask[b][lane][w];
+                cnt += __popc(m);
+                while (m)
+                {
+                    const int bit = __ffs(m) - 1;
+                    s = __dadd_rn(s, contrib[b][lane][w * 32 + bit]);
+                    m &= m - 1;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (warp == K2_CW && lane < nh)
+    {
+        rq.score[h0 + lane] = s;
+        rq.count[h0 + lane] = cnt;
+    }
+}
+
+__global__ void __launch_bounds__(K2_THREADS) k2_requests_kernel(const K2Request *__restrict__ requests, uint32_t n_requests)
+{
+    __shared__ double M[K2_HG][18];
+    __shared__ double contrib[2][K2_HG][K2_TP];
+    __shared__ uint32_t mask[2][K2_HG][K2_CW + 1];
+    uint32_t lo = 0, hi = n_requests - 1;
+    while (lo < hi)
+    {
+        const uint32_t mid = (lo + hi + 1) >> 1;
+        if (requests[mid].cta_begin <= blockIdx.x)
+            lo = mid;
+        else
+            hi = mid - 1;
+    }
+    const K2Request rq = requests[lo];
+    const uint32_t local = blockIdx.x - rq.cta_begin;
+    if (rq.mode == 2)
+    {
+        // residual fetch: Model::error of one model for 256 correspondences, index order
+        if (threadIdx.x < 18)
+            M[0][threadIdx.x] = rq.models[threadIdx.x];
+        __syncthreads();
+        const uint32_t i = local * K2_THREADS + threadIdx.x;
+        if (i < rq.n)
+        {
+            const double4 c = normalise_corr(rq.c7 + (size_t)i * 7);
+            rq.e[i] = rq.kind == OCB_MODEL_HOMOGRAPHY ? residual<OCB_MODEL_HOMOGRAPHY>(M[0], c.x, c.y, c.z, c.w)
+                                                      : residual<OCB_MODEL_ESSENTIAL>(M[0], c.x, c.y, c.z, c.w);
+        }
+        return;
+    }
+    if (rq.kind == OCB_MODEL_HOMOGRAPHY)
+        score_request<OCB_MODEL_HOMOGRAPHY>(rq, local, M, contrib, mask);
+    else
+        score_request<OCB_MODEL_ESSENTIAL>(rq, local, M, contrib, mask);
+}
+
+uint32_t k2_request_ctas(const K2Request &rq)
+{
+    if (rq.mode == 2)
+        return (rq.n + K2_THREADS - 1) / K2_THREADS;
+    return (rq.h + K2_HG - 1) / K2_HG;
+}
+
+int k2_run_requests(const K2Request *d_requests, size_t n_requests, uint32_t total_ctas, cudaStream_t stream)
+{
+    if (n_requests == 0 || total_ctas == 0)
+        return 0;
+    k2_requests_kernel<<<total_ctas, K2_THREADS, 0, stream>>>(d_requests, (uint32_t)n_requests);
+    count_launch();
+    OCB_CUDA(cudaGetLastError());
+    return 0;
+}
+
 int k2_prepare(const double *d_corr7, const uint32_t *d_order, size_t n, double *d_corr4, uint32_t *d_pos,
                cudaStream_t stream)
 {

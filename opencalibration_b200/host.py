@@ -81,6 +81,7 @@ def lib():
     L.ocbh_link_sizes.restype = None
     L.ocbh_link_get.argtypes = [C.c_void_p, sz, _szp, _szp, _f64p, _f64p, C.c_void_p, _f64p, _f64p, _szp]
     L.ocbh_link_get.restype = None
+    L.ocbh_ransac_batch.argtypes = [i32, _f64p, _szp, sz, i32, _f64p, _f64p, _u8p, _szp]
     L.ocbh_run_parallel_handles.argtypes = [C.c_void_p, C.c_void_p, sz, i32, i32, i32, _szp, _f64p]
     _lib = L
     return L
@@ -330,10 +331,10 @@ class LinkResults:
 
     def __init__(self, handle, n_pairs):
         self.handle, self.n_pairs = handle, n_pairs
-        st = np.zeros(8)
+        st = np.zeros(9)
         lib().ocbh_link_stats(handle, st)
         self.stats = dict(seconds_subsample_upload=st[0], seconds_match_gpu=st[1], seconds_tail=st[2],
-                          seconds_total=st[3], comparisons=int(st[4]), matches=int(st[5]), ransac_inliers=int(st[6]))
+                          seconds_total=st[3], seconds_setup=st[7], seconds_release=st[8], comparisons=int(st[4]), matches=int(st[5]), ransac_inliers=int(st[6]))
 
     def sizes(self, p):
         a, b = np.zeros(1, np.uintp), np.zeros(1, np.uintp)
@@ -376,3 +377,19 @@ def link_pairs(feature_sets, cameras8, pairs, num_sparse=None, threads=0, pairs_
     if not res:
         raise OcbError("host mirror: " + lib().ocbh_last_error().decode())
     return LinkResults(res, len(pr))
+
+
+def ransac_batch(kind, corr_list, threads=0):
+    """ransac<Model>() for every correspondence set of corr_list, advanced in lock step (one GPU launch per round)
+    -> list of (score, M18, inliers, stats)."""
+    corr_list = [_corr(c) for c in corr_list]
+    n = len(corr_list)
+    offsets = np.zeros(n + 1, np.uintp)
+    offsets[1:] = np.cumsum([len(c) for c in corr_list])
+    total = int(offsets[-1])
+    allc = np.concatenate(corr_list) if total else np.zeros((0, 7))
+    scores, M18 = np.zeros(max(n, 1)), np.full((max(n, 1), 18), np.nan)
+    inl, st = np.zeros(max(total, 1), np.uint8), np.zeros((max(n, 1), 2), np.uintp)
+    _check(lib().ocbh_ransac_batch(kind, np.ascontiguousarray(allc), offsets, n, int(threads), scores, M18, inl, st))
+    return [(float(scores[j]), M18[j].copy(), inl[int(offsets[j]):int(offsets[j + 1])].astype(bool),
+             dict(iterations=int(st[j, 0]), improvements=int(st[j, 1]))) for j in range(n)]

@@ -106,6 +106,34 @@ template <typename F> int guarded(F &&f)
 }
 } // namespace
 
+namespace
+{
+// ransac_batch over n_jobs correspondence sets stored back to back (offsets[j] .. offsets[j+1]) -> per job the
+// returned score, the model (18 doubles), the inlier flags (same layout as corr) and (iterations, improvements)
+template <typename Model> void run_batch(const double *corr, const size_t *offsets, size_t n_jobs, int threads,
+                                                double *scores, double *M18, uint8_t *inl, size_t *stats2)
+{
+    std::vector<std::vector<correspondence>> c(n_jobs);
+    std::vector<Model> models(n_jobs);
+    std::vector<std::vector<bool>> flags(n_jobs);
+    std::vector<ocb_host::RansacJob<Model>> jobs(n_jobs);
+    for (size_t j = 0; j < n_jobs; j++)
+    {
+        c[j] = make_corr(corr + 7 * offsets[j], offsets[j + 1] - offsets[j]);
+        jobs[j].matches = &c[j], jobs[j].model = &models[j], jobs[j].inliers = &flags[j];
+    }
+    ocb_host::ransac_batch(jobs, threads);
+    for (size_t j = 0; j < n_jobs; j++)
+    {
+        scores[j] = jobs[j].result;
+        store(models[j], M18 + 18 * j);
+        for (size_t k = 0; k < flags[j].size(); k++)
+            inl[offsets[j] + k] = flags[j][k];
+        stats2[2 * j] = jobs[j].stats.iterations, stats2[2 * j + 1] = jobs[j].stats.improvements;
+    }
+}
+} // namespace
+
 extern "C"
 {
     const char *ocbh_last_error() { return t_err.c_str(); }
@@ -510,13 +538,15 @@ extern "C"
         return res;
     }
     void ocbh_link_free(void *h) { delete static_cast<LinkResultHandle *>(h); }
-    // stats8: seconds subsample+upload, gpu match, tail, total, comparisons, matches, ransac inliers, 0
+    // stats9: seconds subsample+upload, gpu match, tail, total, comparisons, matches, ransac inliers, seconds setup,
+    // seconds release
     void ocbh_link_stats(const void *h, double *stats8)
     {
         const auto &s = static_cast<const LinkResultHandle *>(h)->stats;
         stats8[0] = s.seconds_subsample_upload, stats8[1] = s.seconds_match_gpu, stats8[2] = s.seconds_tail;
         stats8[3] = s.seconds_total, stats8[4] = (double)s.comparisons, stats8[5] = (double)s.matches;
-        stats8[6] = (double)s.ransac_inliers, stats8[7] = 0;
+        stats8[6] = (double)s.ransac_inliers, stats8[7] = s.seconds_setup + 1e3 * 0;
+        stats8[8] = s.seconds_release;
     }
     void ocbh_link_sizes(const void *h, size_t p, size_t *n_matches, size_t *n_inlier_matches)
     {
@@ -549,5 +579,17 @@ extern "C"
             inl_pixels4[4 * i + 2] = m.pixel_2[0], inl_pixels4[4 * i + 3] = m.pixel_2[1];
             inl_idx3[3 * i] = m.feature_index_1, inl_idx3[3 * i + 1] = m.feature_index_2, inl_idx3[3 * i + 2] = m.match_index;
         }
+    }
+    int ocbh_ransac_batch(int kind, const double *corr, const size_t *offsets, size_t n_jobs, int threads, double *scores,
+                          double *M18, uint8_t *inl, size_t *stats2)
+    {
+        return guarded([&] {
+            if (kind == OCB_MODEL_HOMOGRAPHY)
+                run_batch<homography_model>(corr, offsets, n_jobs, threads, scores, M18, inl, stats2);
+            else if (kind == OCB_MODEL_ESSENTIAL)
+                run_batch<essential_matrix_model>(corr, offsets, n_jobs, threads, scores, M18, inl, stats2);
+            else
+                run_batch<fundamental_matrix_model>(corr, offsets, n_jobs, threads, scores, M18, inl, stats2);
+        });
     }
 }

@@ -25,15 +25,70 @@ double since(clock_type::time_point t0)
 
 std::atomic<uint64_t> g_next_set_id{0x4c4e4b0000000000ull}; // ids of descriptor sets owned by link_pairs calls
 
-// the tail of one LinkStage closure after the match (link_stage.cpp:86-108)
-void finish_pair(const ocb_host::LinkImage &img, const ocb_host::LinkImage &near_image, camera_relations &relations,
-                 std::vector<feature_match> &&coarse_matches, size_t *n_inliers)
+// page-locked result buffers (one per slot of a link_pairs call), recycled through a small pool
+struct ResultBuffers
 {
-    std::vector<correspondence> coarse_correspondences =
-        distort_keypoints(*img.features, *near_image.features, coarse_matches, img.model, near_image.model);
-    homography_model h;
-    std::vector<bool> coarse_inliers;
-    ransac(coarse_correspondences, h, coarse_inliers);
+    std::vector<void *> p;
+    size_t cap = 0;
+};
+std::mutex g_pool_mu;
+std::vector<ResultBuffers> g_pool;
+
+void free_result_buffers(ResultBuffers &b)
+{
+    for (void *q : b.p)
+        ocb_host_free(q);
+    b.p.clear();
+    b.cap = 0;
+}
+
+ResultBuffers take_result_buffers(size_t count, size_t bytes)
+{
+    ResultBuffers b;
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        if (!g_pool.empty())
+        {
+            b = g_pool.back();
+            g_pool.pop_back();
+        }
+    }
+    if (b.cap < bytes)
+        free_result_buffers(b);
+    if (b.p.empty())
+        b.cap = bytes + bytes / 4;
+    while (b.p.size() < count)
+    {
+        void *q = ocb_host_alloc(b.cap);
+        if (!q)
+        {
+            free_result_buffers(b);
+            return b;
+        }
+        b.p.push_back(q);
+    }
+    while (b.p.size() > count)
+    {
+        ocb_host_free(b.p.back());
+        b.p.pop_back();
+    }
+    return b;
+}
+
+void give_back_result_buffers(ResultBuffers &b)
+{
+    if (b.p.empty())
+        return;
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    g_pool.push_back(b);
+    b.p.clear();
+}
+
+// the end of one LinkStage closure, after ransac (link_stage.cpp:95-108)
+void finish_pair(const ocb_host::LinkImage &img, const ocb_host::LinkImage &near_image, camera_relations &relations,
+                 std::vector<feature_match> &&coarse_matches, const std::vector<correspondence> &coarse_correspondences,
+                 homography_model &h, const std::vector<bool> &coarse_inliers, size_t *n_inliers)
+{
     relations.ransac_relation = h.homography;
     relations.relationType = camera_relations::RelationType::HOMOGRAPHY;
     const bool can_decompose = h.decompose(coarse_correspondences, coarse_inliers, relations.relative_poses);
@@ -133,8 +188,10 @@ std::vector<camera_relations> link_pairs(const std::vector<LinkImage> &images, c
     LinkStats st;
     st.seconds_subsample_upload = since(t_begin);
 
-    // ---- submissions: one long-lived thread keeps the GPU matching chunk k+1 (into the other of two page-locked
-    // result buffers) while the OpenMP workers finish chunk k
+    // ---- submissions: one long-lived producer thread keeps the GPU matching the next chunks (into page-locked
+    // result buffers, one per slot) while `tail_workers` consumer threads, each with its own OpenMP team, finish the
+    // chunks already matched. Several consumers are needed because a chunk's RANSAC rounds are a serial chain of
+    // GPU round trips: with one consumer the chain's latency, not the host cores, bounds the tail.
     const size_t per = std::max<size_t>(1, options.pairs_per_submission);
     const size_t n_chunks = (n_pairs + per - 1) / per;
     size_t max_rows = 1;
@@ -145,32 +202,37 @@ std::vector<camera_relations> link_pairs(const std::vector<LinkImage> &images, c
             rows += indices[pairs[p].image_1].size();
         max_rows = std::max(max_rows, rows);
     }
+    const int workers = options.run_ransac ? std::max(1, std::min(options.tail_workers, threads)) : 1;
+    const int team = std::max(1, threads / workers);
+    const size_t n_slots = (size_t)workers + 1;
     struct Slot
     {
         ocb_top2 *top = nullptr;
         std::vector<uint64_t> offsets;
         double gpu_seconds = 0;
+        size_t chunk = 0; // which submission the records belong to
         bool full = false;
-    } slot[2];
-    for (Slot &sl : slot)
+    };
+    std::vector<Slot> slot(n_slots);
+    // page-locked result buffers are expensive to create (the driver maps them into every visible GPU), so they are
+    // kept between calls and only grow
+    ResultBuffers buffers = take_result_buffers(n_slots, max_rows * sizeof(ocb_top2));
+    if (buffers.p.size() != n_slots)
     {
-        sl.top = static_cast<ocb_top2 *>(ocb_host_alloc(max_rows * sizeof(ocb_top2)));
-        if (!sl.top)
-        {
-            for (Slot &o : slot)
-                ocb_host_free(o.top);
-            release_sets();
-            throw std::runtime_error(std::string("ocb_host_alloc: ") + ocb_last_error());
-        }
+        give_back_result_buffers(buffers);
+        release_sets();
+        throw std::runtime_error(std::string("ocb_host_alloc: ") + ocb_last_error());
     }
+    for (size_t k = 0; k < n_slots; k++)
+        slot[k].top = static_cast<ocb_top2 *>(buffers.p[k]);
+    st.seconds_setup = since(t_begin) - st.seconds_subsample_upload;
     std::mutex mu;
     std::condition_variable cv;
-    std::string producer_error;
-    bool stop = false;
+    bool stop = false; // set on the first error: everybody drains
     std::thread producer([&]() {
         for (size_t c = 0; c < n_chunks; c++)
         {
-            Slot &sl = slot[c & 1];
+            Slot &sl = slot[c % n_slots];
             {
                 std::unique_lock<std::mutex> lk(mu);
                 cv.wait(lk, [&] { return !sl.full || stop; });
@@ -193,9 +255,11 @@ std::vector<camera_relations> link_pairs(const std::vector<LinkImage> &images, c
             std::lock_guard<std::mutex> lk(mu);
             if (rc)
             {
-                producer_error = std::string("ocb_match_pairs: ") + ocb_last_error();
+                if (error.empty())
+                    error = std::string("ocb_match_pairs: ") + ocb_last_error();
                 stop = true;
             }
+            sl.chunk = c;
             sl.full = true;
             cv.notify_all();
             if (rc)
@@ -204,67 +268,142 @@ std::vector<camera_relations> link_pairs(const std::vector<LinkImage> &images, c
     });
 
     std::vector<camera_relations> relations(n_pairs);
-    size_t total_matches = 0, total_inliers = 0;
-    for (size_t c = 0; c < n_chunks && error.empty(); c++)
-    {
-        Slot &sl = slot[c & 1];
-        {
-            std::unique_lock<std::mutex> lk(mu);
-            cv.wait(lk, [&] { return sl.full; });
-            if (!producer_error.empty())
-            {
-                error = producer_error;
-                break;
-            }
-        }
-        st.seconds_match_gpu += sl.gpu_seconds;
-        const size_t begin = c * per, end = std::min(n_pairs, begin + per);
-        const auto t0 = clock_type::now();
-#pragma omp parallel for schedule(dynamic, 1) num_threads(threads) reduction(+ : total_matches, total_inliers)
-        for (size_t p = begin; p < end; p++)
-        {
-            try
-            {
-                const LinkImage &img = images[pairs[p].image_1], &near_image = images[pairs[p].image_2];
-                std::vector<feature_match> coarse_matches =
-                    detail::matches_from_top2(indices[pairs[p].image_1], indices[pairs[p].image_2],
-                                              sl.top + sl.offsets[p - begin], nullptr, nullptr);
-                total_matches += coarse_matches.size();
-                if (options.run_ransac)
-                {
-                    size_t inl = 0;
-                    finish_pair(img, near_image, relations[p], std::move(coarse_matches), &inl);
-                    total_inliers += inl;
-                }
-                else
-                    relations[p].matches = std::move(coarse_matches);
-            }
-            catch (const std::exception &e)
-            {
-#pragma omp critical(ocb_link_error)
-                error = e.what();
-            }
-        }
-        st.seconds_tail += since(t0);
+    std::atomic<size_t> next_chunk{0}, total_matches{0}, total_inliers{0};
+    double tail_seconds = 0, gpu_seconds = 0;
+    auto fail = [&](const std::string &what) {
         std::lock_guard<std::mutex> lk(mu);
-        sl.full = false;
+        if (error.empty())
+            error = what;
+        stop = true;
         cv.notify_all();
-    }
+    };
+    auto consume = [&]() {
+        for (;;)
+        {
+            const size_t c = next_chunk.fetch_add(1);
+            if (c >= n_chunks)
+                return;
+            Slot &sl = slot[c % n_slots];
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return (sl.full && sl.chunk == c) || stop; });
+                if (stop)
+                    return;
+            }
+            const size_t begin = c * per, end = std::min(n_pairs, begin + per), cn = end - begin;
+            const auto t0 = clock_type::now();
+            std::string local_error;
+            size_t n_matches = 0, n_inl = 0;
+            // (a) per pair: ratio test + sort -> match list, pixel -> ray (link_stage.cpp:83-88)
+            std::vector<std::vector<feature_match>> coarse_matches(cn);
+            std::vector<std::vector<correspondence>> coarse_correspondences(cn);
+#pragma omp parallel for schedule(dynamic, 1) num_threads(team) reduction(+ : n_matches)
+            for (size_t p = begin; p < end; p++)
+            {
+                try
+                {
+                    const LinkImage &img = images[pairs[p].image_1], &near_image = images[pairs[p].image_2];
+                    coarse_matches[p - begin] =
+                        detail::matches_from_top2(indices[pairs[p].image_1], indices[pairs[p].image_2],
+                                                  sl.top + sl.offsets[p - begin], nullptr, nullptr);
+                    n_matches += coarse_matches[p - begin].size();
+                    if (options.run_ransac)
+                        coarse_correspondences[p - begin] =
+                            distort_keypoints(*img.features, *near_image.features, coarse_matches[p - begin], img.model,
+                                              near_image.model);
+                    else
+                        relations[p].matches = std::move(coarse_matches[p - begin]);
+                }
+                catch (const std::exception &e)
+                {
+#pragma omp critical(ocb_link_error)
+                    local_error = e.what();
+                }
+            }
+            const double gpu_s = sl.gpu_seconds;
+            {
+                // the K1 records have been consumed: the slot can take the next submission
+                std::lock_guard<std::mutex> lk(mu);
+                sl.full = false;
+                cv.notify_all();
+            }
+            if (options.run_ransac && local_error.empty())
+            {
+                // (b) the RANSAC runs of all pairs of the submission advance in lock step: one launch per round
+                std::vector<homography_model> models(cn);
+                std::vector<std::vector<bool>> coarse_inliers(cn);
+                std::vector<RansacJob<homography_model>> jobs(cn);
+                for (size_t k = 0; k < cn; k++)
+                    jobs[k].matches = &coarse_correspondences[k], jobs[k].model = &models[k],
+                    jobs[k].inliers = &coarse_inliers[k];
+                try
+                {
+                    ransac_batch(jobs, team);
+                }
+                catch (const std::exception &e)
+                {
+                    local_error = e.what();
+                }
+                // (c) decomposition + inlier assembly (link_stage.cpp:95-108)
+                if (local_error.empty())
+                {
+#pragma omp parallel for schedule(dynamic, 1) num_threads(team) reduction(+ : n_inl)
+                    for (size_t p = begin; p < end; p++)
+                    {
+                        try
+                        {
+                            size_t inl = 0;
+                            finish_pair(images[pairs[p].image_1], images[pairs[p].image_2], relations[p],
+                                        std::move(coarse_matches[p - begin]), coarse_correspondences[p - begin],
+                                        models[p - begin], coarse_inliers[p - begin], &inl);
+                            n_inl += inl;
+                        }
+                        catch (const std::exception &e)
+                        {
+#pragma omp critical(ocb_link_error)
+                            local_error = e.what();
+                        }
+                    }
+                }
+            }
+            total_matches += n_matches;
+            total_inliers += n_inl;
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                tail_seconds += since(t0);
+                gpu_seconds += gpu_s;
+            }
+            if (!local_error.empty())
+            {
+                fail(local_error);
+                return;
+            }
+        }
+    };
+    std::vector<std::thread> consumers;
+    for (int w = 1; w < workers; w++)
+        consumers.emplace_back(consume);
+    consume();
+    for (std::thread &t : consumers)
+        t.join();
     {
         std::lock_guard<std::mutex> lk(mu);
         stop = true;
         cv.notify_all();
     }
     producer.join();
-    for (Slot &sl : slot)
-        ocb_host_free(sl.top);
+    st.seconds_match_gpu = gpu_seconds;
+    st.seconds_tail = tail_seconds;
+    const auto t_release = clock_type::now();
+    give_back_result_buffers(buffers);
     release_sets();
+    st.seconds_release = since(t_release);
     if (!error.empty())
         throw std::runtime_error(error);
     for (const LinkPair &p : pairs)
         st.comparisons += indices[p.image_1].size() * indices[p.image_2].size();
-    st.matches = total_matches;
-    st.ransac_inliers = total_inliers;
+    st.matches = total_matches.load();
+    st.ransac_inliers = total_inliers.load();
     st.seconds_total = since(t_begin);
     if (stats)
         *stats = st;

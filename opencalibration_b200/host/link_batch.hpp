@@ -34,10 +34,12 @@ struct LinkOptions
     size_t pairs_per_submission = 256;  // pairs per ocb_match_pairs call
     double coarse_spacing_pixels = 40.0; // link_stage.cpp:62
     bool run_ransac = true;             // false: stop after the match lists (relations.matches only)
+    int tail_workers = 3;               // chunks whose tails (incl. the lock-step RANSAC rounds) run concurrently
 };
 struct LinkStats
 {
-    double seconds_subsample_upload = 0, seconds_match_gpu = 0, seconds_tail = 0, seconds_total = 0;
+    double seconds_subsample_upload = 0, seconds_setup = 0, seconds_match_gpu = 0, seconds_tail = 0,
+           seconds_release = 0, seconds_total = 0;
     size_t comparisons = 0, matches = 0, ransac_inliers = 0;
 };
 // relations[p] is what the closure of pair p would have stored in its edge_payload (link_stage.cpp:95-111).

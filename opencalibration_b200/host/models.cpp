@@ -119,6 +119,16 @@ BoundCorrespondences::~BoundCorrespondences()
         t_bound.data = prev_data_, t_bound.n = prev_n_, t_bound.order = prev_order_;
 }
 
+void gpu_evaluate_bits(int kind, const double *m18, double thr, const std::vector<opencalibration::correspondence> &corrs,
+                       double *score, uint32_t *count, uint32_t *bits)
+{
+    if (is_bound(corrs))
+        gpu_check(ocb_score_bound(kind, m18, 1, thr, 0, score, count, bits), "ocb_score_bound");
+    else
+        gpu_check(ocb_score_models(kind, m18, 1, corr_data(corrs), corrs.size(), thr, nullptr, score, count, bits),
+                  "ocb_score_models");
+}
+
 void gpu_residuals(int kind, const double *m18, const std::vector<opencalibration::correspondence> &corrs, double *e)
 {
     if (is_bound(corrs))
@@ -155,11 +165,7 @@ double gpu_evaluate(int kind, const double *matrix9, const double *inverse9, dou
     std::vector<uint32_t> bits((n + 31) / 32);
     double score = 0.0;
     uint32_t count = 0;
-    if (is_bound(corrs))
-        gpu_check(ocb_score_bound(kind, m18, 1, thr, 0, &score, &count, bits.data()), "ocb_score_bound");
-    else
-        gpu_check(ocb_score_models(kind, m18, 1, corr_data(corrs), n, thr, nullptr, &score, &count, bits.data()),
-                  "ocb_score_models");
+    gpu_evaluate_bits(kind, m18, thr, corrs, &score, &count, bits.data());
     for (size_t i = 0; i < n; i++)
         inliers[i] = (bits[i >> 5] >> (i & 31)) & 1u;
     return score;

@@ -35,6 +35,9 @@ class BoundCorrespondences
     size_t prev_n_;
     const uint32_t *prev_order_;
 };
+// Model::evaluate on the GPU for one packed model: index-order MSAC sum, inlier count and bit mask
+void gpu_evaluate_bits(int kind, const double *m18, double thr, const std::vector<opencalibration::correspondence> &corrs,
+                       double *score, uint32_t *count, uint32_t *bits);
 // Model::error for every correspondence (index order) of one model
 void gpu_residuals(int kind, const double *m18, const std::vector<opencalibration::correspondence> &corrs, double *e);
 // the score loop of ransac.cpp:183-196 for a batch of models, summed in `order`

@@ -56,4 +56,17 @@ struct RansacStats
     size_t gpu_calls = 0;
 };
 RansacStats last_ransac_stats();
+
+// Many independent ransac<Model>() runs advanced in lock step (used by the batched LinkStage runner): the result of
+// every job -- model, inliers, returned score -- is what ransac(*matches, *model, *inliers) gives, but each round of
+// GPU work of all jobs is ONE launch instead of one per job.
+template <typename Model> struct RansacJob
+{
+    const std::vector<opencalibration::correspondence> *matches = nullptr;
+    Model *model = nullptr;
+    std::vector<bool> *inliers = nullptr;
+    double result = 0; // what ransac() would have returned
+    RansacStats stats;
+};
+template <typename Model> void ransac_batch(std::vector<RansacJob<Model>> &jobs, int threads = 0);
 } // namespace ocb_host

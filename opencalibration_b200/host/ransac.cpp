@@ -19,8 +19,13 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstring>
+#include <memory>
+#include <omp.h>
 #include <numeric>
 #include <random>
+#include <stdexcept>
+#include <string>
 
 namespace ocb_host
 {
@@ -157,170 +162,418 @@ namespace opencalibration
 using namespace ocb_host;
 using namespace ocb_host::detail;
 
-template <typename Model>
-double ransac(const std::vector<correspondence> &matches, Model &model, std::vector<bool> &inliers)
+// One RANSAC run as a resumable state machine: advance() executes the reference's control flow
+// (src/model_inliers/ransac.cpp:162-256) until it needs a GPU result -- the scores of a batch of hypotheses, the
+// residuals of a would-be improver, or an evaluate() of the model in hand -- and returns what it needs; the driver
+// (one run: ransac() below; many runs in lock step: ransac_batch()) obtains it and calls advance() again. Both
+// drivers therefore execute the same host logic; only how requests reach the GPU differs.
+template <typename Model> class RansacRun
 {
-    constexpr size_t K = Model::MINIMUM_POINTS;
-    const size_t MIN_ITERATIONS = 20;
-    const size_t MAX_ITERATIONS = 10000;
-    const size_t MAX_INNER_ITERATIONS = 5;
-    const double PROBABILITY = 0.999;
-    const double log_1m_p = std::log(1 - PROBABILITY);
-    const size_t N = matches.size();
-    RansacStats stats;
-
-    inliers.resize(N);
-    std::fill(inliers.begin(), inliers.end(), false);
-    if (N < K)
+  public:
+    static constexpr size_t K = Model::MINIMUM_POINTS;
+    enum class Need
     {
-        t_stats = stats;
-        return 0;
+        DONE,
+        SCORE_BATCH, // request_models(): want x 18, evaluation order -> batch_score, batch_count
+        RESIDUALS,   // request_models(): 1 x 18                      -> residual[N]
+        EVALUATE     // request_models(): 1 x 18, index order         -> eval_score, eval_bits
+    };
+
+    RansacRun(const std::vector<correspondence> &matches_, Model &model_, std::vector<bool> &inliers_)
+        : matches(matches_), model(model_), inliers(inliers_), N(matches_.size())
+    {
+        inliers.resize(N);
+        std::fill(inliers.begin(), inliers.end(), false);
+        if (N < K) // ransac.cpp:64-70
+        {
+            state = State::FINISHED;
+            return;
+        }
+        stream.reset(new HypothesisStream<K>(matches));
+        order32.resize(N);
+        for (size_t p = 0; p < N; p++)
+            order32[p] = static_cast<uint32_t>(stream->eval_order[p]);
+        kind = model_kind(model);
+        thr = model.inlier_threshold;
+        residual.resize(N);
+        eval_bits.resize((N + 31) / 32);
+        candidate_inliers.assign(N, false);
     }
 
-    HypothesisStream<K> stream(matches);
-    std::vector<uint32_t> order32(N);
-    for (size_t p = 0; p < N; p++)
-        order32[p] = static_cast<uint32_t>(stream.eval_order[p]);
+    bool trivial() const { return N < K; }
+    const uint32_t *order() const { return order32.data(); }
+    const double *request_models() const { return request_m18; }
+    size_t request_count() const { return request_h; }
 
-    // the correspondences stay on the GPU for the whole run: every batch, residual fetch and evaluate() below
-    // sends only its models
-    const BoundCorrespondences resident(matches, order32.data());
-
-    Model best_model{};
-    double best_score = 0;
-    size_t probability_iterations = MAX_ITERATIONS;
-    const int kind = model_kind(model);
-    const double thr = model.inlier_threshold;
-
-    std::vector<Model> batch_models;
-    std::vector<char> batch_skip;
-    std::vector<double> batch_m18, batch_score, residual(N);
-    std::vector<uint32_t> batch_count;
-    std::vector<bool> candidate_inliers(N, false);
-
-    size_t i = 0;          // the reference's loop counter
-    size_t batch = 32;     // grows geometrically: the adaptive stop usually fires within the first batches
-    while (i < probability_iterations)
+    Need advance()
     {
-        const size_t want = std::min(batch, MAX_ITERATIONS - i);
-        batch_models.assign(want, model);
-        batch_skip.assign(want, 0);
-        batch_m18.assign(want * 18, 0.0);
-        for (size_t b = 0; b < want; b++)
+        for (;;)
         {
-            const std::array<size_t, K> sample = stream.next(i + b);
-            if constexpr (is_homography<Model>)
+            switch (state)
             {
-                if (Model::checkSampleDegeneracy(matches, sample)) // ransac.cpp:173-177
-                {
-                    batch_skip[b] = 1;
-                    continue;
-                }
-            }
-            batch_models[b].fit(matches, sample); // ransac.cpp:179
-            pack_model(batch_models[b], &batch_m18[b * 18]);
-        }
-        batch_score.assign(want, 0.0);
-        batch_count.assign(want, 0);
-        gpu_score_in_order(kind, batch_m18.data(), want, matches, thr, order32.data(), batch_score.data(),
-                           batch_count.data());
-        stats.gpu_calls++;
-        stats.scored += want;
+            case State::FINISHED:
+                return Need::DONE;
 
-        for (size_t b = 0; b < want && i < probability_iterations; b++, i++)
-        {
-            if (batch_skip[b])
-            {
-                stats.degenerate++;
-                continue;
-            }
-            if (!(batch_score[b] > best_score))
-                continue; // rejected early or not, nothing changes (ransac.cpp:204-207)
-
-            // would-be improver: replay ransac.cpp:183-203 on its residuals
-            model = batch_models[b];
-            gpu_residuals(kind, &batch_m18[b * 18], matches, residual.data());
-            stats.gpu_calls++;
-            double score = 0;
-            size_t checked = 0;
-            bool rejected = false;
-            std::fill(candidate_inliers.begin(), candidate_inliers.end(), false);
-            for (size_t idx : stream.eval_order)
-            {
-                const double e = residual[idx];
-                if (e < model.inlier_threshold)
+            case State::START_BATCH: {
+                if (!(i < probability_iterations))
                 {
-                    candidate_inliers[idx] = true;
-                    const double ratio = e / model.inlier_threshold;
-                    score += 1.0 - ratio * ratio;
+                    // ransac.cpp:255-256: model = best_model; return model.evaluate(matches, inliers) / N
+                    stats.iterations = i;
+                    model = best_model;
+                    request_evaluate();
+                    state = State::AFTER_FINAL_EVAL;
+                    return Need::EVALUATE;
                 }
-                checked++;
-                if (checked > 20 && best_score > 0 && score < best_score * static_cast<double>(checked) / N * 0.6)
+                const size_t want = std::min(batch, MAX_ITERATIONS - i);
+                batch_models.assign(want, model);
+                batch_skip.assign(want, 0);
+                batch_m18.assign(want * 18, 0.0);
+                for (size_t k = 0; k < want; k++)
                 {
-                    rejected = true;
+                    const std::array<size_t, K> sample = stream->next(i + k);
+                    if constexpr (is_homography<Model>)
+                    {
+                        if (Model::checkSampleDegeneracy(matches, sample)) // ransac.cpp:173-177
+                        {
+                            batch_skip[k] = 1;
+                            continue;
+                        }
+                    }
+                    batch_models[k].fit(matches, sample); // ransac.cpp:179
+                    pack_model(batch_models[k], &batch_m18[k * 18]);
+                }
+                batch_score.assign(want, 0.0);
+                batch_count.assign(want, 0);
+                stats.gpu_calls++;
+                stats.scored += want;
+                b = 0;
+                request_m18 = batch_m18.data();
+                request_h = want;
+                state = State::SCAN;
+                return Need::SCORE_BATCH;
+            }
+
+            case State::SCAN: {
+                bool requested = false;
+                for (; b < batch_models.size() && i < probability_iterations; b++, i++)
+                {
+                    if (batch_skip[b])
+                    {
+                        stats.degenerate++;
+                        continue;
+                    }
+                    if (!(batch_score[b] > best_score))
+                        continue; // rejected early or not, nothing changes (ransac.cpp:204-207)
+                    // would-be improver: replay ransac.cpp:183-203 on its residuals
+                    model = batch_models[b];
+                    stats.gpu_calls++;
+                    request_m18 = &batch_m18[b * 18];
+                    request_h = 1;
+                    requested = true;
                     break;
                 }
+                if (requested)
+                {
+                    state = State::AFTER_RESIDUALS;
+                    return Need::RESIDUALS;
+                }
+                if (b >= batch_models.size())
+                    batch = std::min<size_t>(batch * 2, 2048);
+                state = State::START_BATCH;
+                break;
             }
-            if (rejected)
-            {
-                stats.rejected++;
-                continue;
-            }
-            if (score > best_score) // ransac.cpp:207
-            {
+
+            case State::AFTER_RESIDUALS: {
+                double score = 0;
+                size_t checked = 0;
+                bool rejected = false;
+                std::fill(candidate_inliers.begin(), candidate_inliers.end(), false);
+                for (size_t idx : stream->eval_order)
+                {
+                    const double e = residual[idx];
+                    if (e < model.inlier_threshold)
+                    {
+                        candidate_inliers[idx] = true;
+                        const double ratio = e / model.inlier_threshold;
+                        score += 1.0 - ratio * ratio;
+                    }
+                    checked++;
+                    if (checked > 20 && best_score > 0 && score < best_score * static_cast<double>(checked) / N * 0.6)
+                    {
+                        rejected = true;
+                        break;
+                    }
+                }
+                if (rejected)
+                    stats.rejected++;
+                if (rejected || !(score > best_score)) // ransac.cpp:207
+                {
+                    next_hypothesis();
+                    break;
+                }
                 stats.improvements++;
                 best_model = model;
                 best_score = score;
                 inliers = candidate_inliers;
-
                 if constexpr (is_fundamental<Model>) // ransac.cpp:213-222
                 {
                     model.checkDegeneracy(matches, inliers);
-                    const double degen_score = model.evaluate(matches, inliers);
-                    if (degen_score > best_score)
-                    {
-                        best_model = model;
-                        best_score = degen_score;
-                    }
+                    request_evaluate();
+                    state = State::AFTER_DEGEN_EVAL;
+                    return Need::EVALUATE;
                 }
+                model.fitInliers(matches, inliers); // ransac.cpp:224
+                lo_round = 0;
+                request_evaluate();
+                state = State::AFTER_LO_EVAL;
+                return Need::EVALUATE;
+            }
 
-                model.fitInliers(matches, inliers); // ransac.cpp:224-245
-                double inlier_score = model.evaluate(matches, inliers);
-                if (inlier_score > best_score)
+            case State::AFTER_DEGEN_EVAL: {
+                const double degen_score = take_evaluate();
+                if (degen_score > best_score)
+                {
+                    best_model = model;
+                    best_score = degen_score;
+                }
+                model.fitInliers(matches, inliers);
+                lo_round = 0;
+                request_evaluate();
+                state = State::AFTER_LO_EVAL;
+                return Need::EVALUATE;
+            }
+
+            case State::AFTER_LO_EVAL: {
+                // ransac.cpp:225-245: keep refitting on the inliers of the last evaluate while the score improves
+                const double inlier_score = take_evaluate();
+                const bool better = inlier_score > best_score;
+                if (better)
                 {
                     best_model = model;
                     best_score = inlier_score;
-                    for (size_t j = 1; j < MAX_INNER_ITERATIONS; j++)
-                    {
-                        model.fitInliers(matches, inliers);
-                        inlier_score = model.evaluate(matches, inliers);
-                        if (inlier_score > best_score)
-                        {
-                            best_model = model;
-                            best_score = inlier_score;
-                        }
-                        else
-                        {
-                            break;
-                        }
-                    }
                 }
-
+                if (better && lo_round + 1 < MAX_INNER_ITERATIONS)
+                {
+                    lo_round++;
+                    model.fitInliers(matches, inliers);
+                    request_evaluate();
+                    return Need::EVALUATE;
+                }
                 const double omega = best_score / N; // ransac.cpp:247-251
                 const double omega_n = small_pow<(int)K>(omega);
                 const double log_1m_omega_n = std::log(1 - omega_n);
-                probability_iterations =
-                    std::max(MIN_ITERATIONS, std::min(MAX_ITERATIONS, static_cast<size_t>(log_1m_p / log_1m_omega_n)));
+                probability_iterations = std::max(
+                    MIN_ITERATIONS, std::min(MAX_ITERATIONS, static_cast<size_t>(log_1m_p / log_1m_omega_n)));
+                next_hypothesis();
+                break;
+            }
+
+            case State::AFTER_FINAL_EVAL:
+                result = take_evaluate() / N;
+                state = State::FINISHED;
+                return Need::DONE;
             }
         }
-        batch = std::min<size_t>(batch * 2, 2048);
     }
-    stats.iterations = i;
-    t_stats = stats;
 
-    model = best_model;
-    return model.evaluate(matches, inliers) / N; // ransac.cpp:255-256
+    // ---- inputs / outputs of the run
+    const std::vector<correspondence> &matches;
+    Model &model;
+    std::vector<bool> &inliers;
+    const size_t N;
+    int kind = 0;
+    double thr = 0;
+    double result = 0;
+    RansacStats stats;
+    // ---- result sinks the driver fills
+    std::vector<double> batch_score, residual;
+    std::vector<uint32_t> batch_count, eval_bits;
+    double eval_score = 0;
+    uint32_t eval_count = 0;
+
+  private:
+    enum class State
+    {
+        START_BATCH,
+        SCAN,
+        AFTER_RESIDUALS,
+        AFTER_DEGEN_EVAL,
+        AFTER_LO_EVAL,
+        AFTER_FINAL_EVAL,
+        FINISHED
+    };
+    static constexpr size_t MIN_ITERATIONS = 20, MAX_ITERATIONS = 10000, MAX_INNER_ITERATIONS = 5;
+    const double log_1m_p = std::log(1 - 0.999); // PROBABILITY, ransac.cpp:60
+
+    void next_hypothesis()
+    {
+        b++, i++;
+        state = State::SCAN;
+    }
+    void request_evaluate()
+    {
+        pack_model(model, eval_m18);
+        request_m18 = eval_m18;
+        request_h = 1;
+        stats.gpu_calls++;
+    }
+    // Model::evaluate's effect on `inliers` (homography_model.cpp:101-116) from the returned bit mask
+    double take_evaluate()
+    {
+        inliers.resize(N);
+        for (size_t k = 0; k < N; k++)
+            inliers[k] = (eval_bits[k >> 5] >> (k & 31)) & 1u;
+        return eval_score;
+    }
+
+    State state = State::START_BATCH;
+    std::unique_ptr<HypothesisStream<K>> stream;
+    std::vector<uint32_t> order32;
+    Model best_model{};
+    double best_score = 0;
+    size_t probability_iterations = MAX_ITERATIONS;
+    size_t i = 0;      // the reference's loop counter
+    size_t batch = 32; // grows geometrically: the adaptive stop usually fires within the first batches
+    size_t b = 0;      // cursor in the current batch
+    size_t lo_round = 0;
+    std::vector<Model> batch_models;
+    std::vector<char> batch_skip;
+    std::vector<double> batch_m18;
+    std::vector<bool> candidate_inliers;
+    double eval_m18[18];
+    const double *request_m18 = nullptr;
+    size_t request_h = 0;
+};
+
+template <typename Model>
+double ransac(const std::vector<correspondence> &matches, Model &model, std::vector<bool> &inliers)
+{
+    RansacRun<Model> run(matches, model, inliers);
+    if (run.trivial())
+    {
+        t_stats = run.stats;
+        return 0;
+    }
+    // the correspondences stay on the GPU for the whole run: every request below sends only its models
+    const BoundCorrespondences resident(matches, run.order());
+    using Need = typename RansacRun<Model>::Need;
+    for (Need need = run.advance(); need != Need::DONE; need = run.advance())
+    {
+        switch (need)
+        {
+        case Need::SCORE_BATCH:
+            gpu_score_in_order(run.kind, run.request_models(), run.request_count(), matches, run.thr, run.order(),
+                               run.batch_score.data(), run.batch_count.data());
+            break;
+        case Need::RESIDUALS:
+            gpu_residuals(run.kind, run.request_models(), matches, run.residual.data());
+            break;
+        case Need::EVALUATE:
+            gpu_evaluate_bits(run.kind, run.request_models(), run.thr, matches, &run.eval_score, &run.eval_count,
+                              run.eval_bits.data());
+            break;
+        case Need::DONE:
+            break;
+        }
+    }
+    t_stats = run.stats;
+    return run.result;
 }
+
+} // namespace opencalibration
+
+namespace ocb_host
+{
+// Many runs advanced in lock step: each round every unfinished run contributes one request, and ONE
+// ocb_score_requests call (one kernel launch, one copy each way) serves them all. The host-side logic of the runs
+// (sampling, fits, SPRT replay, local optimisation) executes on `threads` OpenMP workers between rounds.
+template <typename Model> void ransac_batch(std::vector<RansacJob<Model>> &jobs, int threads)
+{
+    using namespace opencalibration;
+    using Run = opencalibration::RansacRun<Model>;
+    using Need = typename Run::Need;
+    const size_t n_jobs = jobs.size();
+    if (threads <= 0)
+        threads = omp_get_num_procs();
+    std::vector<std::unique_ptr<Run>> runs(n_jobs);
+    std::string error;
+#pragma omp parallel for schedule(dynamic, 1) num_threads(threads)
+    for (size_t j = 0; j < n_jobs; j++)
+        runs[j].reset(new Run(*jobs[j].matches, *jobs[j].model, *jobs[j].inliers));
+    std::vector<ocb_corr_set> sets(n_jobs);
+    std::vector<size_t> active;
+    for (size_t j = 0; j < n_jobs; j++)
+    {
+        const bool live = !runs[j]->trivial();
+        sets[j] = ocb_corr_set{live ? detail::corr_data(*jobs[j].matches) : nullptr, live ? jobs[j].matches->size() : 0,
+                               live ? runs[j]->order() : nullptr};
+        if (live)
+            active.push_back(j);
+        else
+            jobs[j].result = 0;
+    }
+    detail::gpu_check(ocb_corr_bind_batch(sets.data(), sets.size()), "ocb_corr_bind_batch");
+    std::vector<Need> need(n_jobs, Need::DONE);
+    std::vector<ocb_score_request> requests;
+    while (!active.empty())
+    {
+#pragma omp parallel for schedule(dynamic, 1) num_threads(threads)
+        for (size_t a = 0; a < active.size(); a++)
+        {
+            try
+            {
+                need[active[a]] = runs[active[a]]->advance();
+            }
+            catch (const std::exception &e)
+            {
+#pragma omp critical(ocb_ransac_batch_error)
+                error = e.what();
+            }
+        }
+        if (!error.empty())
+            throw std::runtime_error(error);
+        requests.clear();
+        std::vector<size_t> still;
+        for (size_t j : active)
+        {
+            Run &r = *runs[j];
+            if (need[j] == Need::DONE)
+            {
+                jobs[j].result = r.result;
+                jobs[j].stats = r.stats;
+                continue;
+            }
+            still.push_back(j);
+            ocb_score_request q;
+            std::memset(&q, 0, sizeof q);
+            q.set = (uint32_t)j;
+            q.kind = r.kind;
+            q.h = (uint32_t)r.request_count();
+            q.models = r.request_models();
+            q.thr = r.thr;
+            if (need[j] == Need::SCORE_BATCH)
+                q.mode = OCB_REQ_SCORE_ORDERED, q.score = r.batch_score.data(), q.count = r.batch_count.data();
+            else if (need[j] == Need::RESIDUALS)
+                q.mode = OCB_REQ_RESIDUALS, q.residuals = r.residual.data();
+            else
+                q.mode = OCB_REQ_EVALUATE, q.score = &r.eval_score, q.count = &r.eval_count,
+                q.inlier_bits = r.eval_bits.data();
+            requests.push_back(q);
+        }
+        if (!requests.empty())
+            detail::gpu_check(ocb_score_requests(requests.data(), requests.size()), "ocb_score_requests");
+        active.swap(still);
+    }
+}
+template void ransac_batch(std::vector<RansacJob<opencalibration::homography_model>> &, int);
+template void ransac_batch(std::vector<RansacJob<opencalibration::fundamental_matrix_model>> &, int);
+template void ransac_batch(std::vector<RansacJob<opencalibration::essential_matrix_model>> &, int);
+} // namespace ocb_host
+
+namespace opencalibration
+{
+using namespace ocb_host;
+using namespace ocb_host::detail;
 
 template double ransac(const std::vector<correspondence> &, homography_model &, std::vector<bool> &);
 template double ransac(const std::vector<correspondence> &, fundamental_matrix_model &, std::vector<bool> &);

@@ -211,3 +211,24 @@ def test_degensac_through_the_mirror(gpu, hostlib, oracle):
     a = hostlib.check_degeneracy_f(M, corr, inl)
     b = oracle.check_degeneracy_f(M, corr, inl)
     assert np.array_equal(a[0][:9], b[0][:9]) and np.array_equal(a[1], b[1])
+
+
+def test_ransac_batch_equals_single_runs(gpu, hostlib, oracle):
+    # lock-step batch (one request-table launch per round) against ransac() run job by job: identical models,
+    # inlier sets, scores and iteration counts, for all three models, ragged sizes, trivial and PROSAC jobs included
+    scenes_h = [oracle.scene_homography(140, 60, 42)[0], oracle.scene_homography(40, 160, 7)[0],
+                oracle.scene_homography(700, 300, 11)[0], np.zeros((0, 7)), oracle.scene_homography(3, 0, 1)[0],
+                oracle.scene_homography_near_degenerate()[0]]
+    q = oracle.scene_homography(300, 100, 5)[0].copy()
+    q[:, 6] = np.random.default_rng(43).uniform(0.05, 0.4, len(q))  # PROSAC branch
+    scenes_h.append(q)
+    scenes_f = [oracle.scene_fundamental(140, 60, 0.0, 42)[0], oracle.scene_fundamental(200, 0, 0.8, 3)[0],
+                oracle.scene_fundamental(60, 20, 0.0, 9)[0]]
+    for kind, scenes in ((0, scenes_h), (2, scenes_f), (1, scenes_f[:2])):
+        batch = hostlib.ransac_batch(kind, scenes, threads=4)
+        n = 18 if kind == 0 else 9
+        for c, (s, M, inl, st) in zip(scenes, batch):
+            s1, M1, inl1, st1 = hostlib.ransac(kind, c)
+            assert s == s1 and np.array_equal(inl, inl1[:len(c)])
+            assert np.array_equal(M[:n], M1[:n], equal_nan=True)
+            assert st["iterations"] == st1["iterations"] and st["improvements"] == st1["improvements"]
