@@ -162,16 +162,45 @@ def secondary_measurements(torch, capi, synthetic, stream):
     plist = [(1000 + a, 1000 + b) for a, b in pairs]
     nq = [n_desc] * len(plist)
     res = np.zeros(len(plist) * n_desc, capi.TOP2_DTYPE)
-    capi.match_pairs(plist[:8], nq[:8], out=res)
+    capi.match_pairs(plist, nq, out=res)  # untimed: sizes the thread's device / page-locked staging areas
+    reps = 3
     t0 = time.perf_counter()
-    capi.match_pairs(plist, nq, out=res)
-    secs = time.perf_counter() - t0
+    for _ in range(reps):
+        capi.match_pairs(plist, nq, out=res)
+    secs = (time.perf_counter() - t0) / reps
     for i in range(len(images)):
         capi.unregister_descriptors(1000 + i)
     out["grid_pairs_batched"] = {"workload": f"configs[3] slice: {rows}x{cols} image grid, {len(plist)} directed pairs "
                                              f"x {n_desc}x{n_desc} rows, one ocb_match_pairs submission, results to host",
                                  "pairs_per_s": len(plist) / secs, "Gcmp_per_s": len(plist) * n_desc * n_desc / secs / 1e9,
                                  "ms": secs * 1e3}
+    # ---- dense-stage guided matcher: K4 on candidate lists, device resident
+    n_q, n_c = 60000, 20000
+    w = synthetic.guided_visits(n_q, n_c, seed=3)
+    total = int(w["begin"][-1])
+    d_q4, d_c4 = torch.from_numpy(w["q"].view(np.int64)).cuda(), torch.from_numpy(w["c"].view(np.int64)).cuda()
+    d_lq = torch.arange(n_q, dtype=torch.int32, device="cuda")
+    d_lb = torch.from_numpy(w["begin"].view(np.int64)).cuda()
+    d_lc = torch.from_numpy(w["nearby"].view(np.int32)).cuda()
+    d_o = torch.zeros(n_q, dtype=torch.int64, device="cuda")
+    ms = _timed(torch, lambda: capi.match_lists_device(d_q4.data_ptr(), d_c4.data_ptr(), d_lq.data_ptr(), d_lb.data_ptr(),
+                                                       d_lc.data_ptr(), n_q, d_o.data_ptr(), stream), 20)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oc_oracle as O
+    orc = O.Oracle()
+    lq = np.arange(n_q, dtype=np.uint32)
+    bp, bd, sd, _good = orc.match_lists(w["q"], w["c"], lq, w["begin"], w["nearby"])
+    got = d_o.cpu().numpy().view(capi.TOP2_DTYPE)
+    to_int = lambda x: np.where(np.isinf(x), 0xFFFF, np.rint(x * 486)).astype(np.uint16)
+    parity = bool(np.array_equal(got["best_k"], bp) and np.array_equal(got["best_d"], to_int(bd)) and
+                  np.array_equal(got["second_d"], to_int(sd)))
+    cpu_s = min(orc.bench_match_lists(w["q"], w["c"], lq, w["begin"], w["nearby"]) for _ in range(3))
+    algo_bytes = total * 68 + n_q * (64 + 4 + 8 + 8)
+    out["dense_guided_lists"] = {"workload": f"dense stage (src/dense/dense_stereo.cpp:244-281): {n_q} source features x "
+                                             f"candidate lists within 150 px among {n_c} features of one image, "
+                                             f"{total} comparisons", "ms": ms, "Gcmp_per_s": total / (ms * 1e-3) / 1e9,
+                                 "gathered_GB_per_s": algo_bytes / (ms * 1e-3) / 1e9, "parity_vs_oracle": parity,
+                                 "cpu_port_Gcmp_per_s": total / cpu_s / 1e9, "cpu_cores": orc.num_procs()}
     return out
 
 

@@ -140,6 +140,24 @@ extern "C"
      * out[out_offsets[p] .. out_offsets[p] + n_query_rows(p)); out_offsets has n_pairs entries. */
     int ocb_match_pairs(const ocb_pair *pairs, size_t n_pairs, ocb_top2 *out, const uint64_t *out_offsets);
 
+    /* ---- K4: Hamming top-2 over per-query candidate lists (guided matcher of the dense stage) ---------------
+     * Replaces the inner loop of densifyMesh, src/dense/dense_stereo.cpp:251-273: list l compares query row
+     * q[list_query[l]] with the candidate rows c[list_candidates[list_begin[l] .. list_begin[l+1])] in list order
+     * (the order of the KD-tree radius search result `nearby`, :244-246) under the update rule of
+     * match_features.cpp:80-92. out[l].best_k is the POSITION within list l of the first minimum (the adapter maps it
+     * to nearby[best_k].payload), best_d / second_d as in ocb_top2; an empty list gives {0, INF, INF}. list_begin has
+     * n_lists + 1 non-decreasing entries; a list may hold at most OCB_MAX_LIST_LENGTH candidates. Indices out of
+     * range give OCB_E_INVALID (checked on the host before anything is launched). The acceptance rule (:275-276)
+     * stays in the adapter. */
+#define OCB_MAX_LIST_LENGTH 0x3FFFFEu
+    int ocb_match_lists(const uint64_t *q, size_t n_q_rows, const uint64_t *c, size_t n_c_rows,
+                        const uint32_t *list_query, const uint64_t *list_begin, const uint32_t *list_candidates,
+                        size_t n_lists, ocb_top2 *out);
+    /* Device-resident variant: every pointer is a device pointer (rows 16-byte aligned), nothing is validated,
+     * enqueues on `stream` and does not synchronise. */
+    int ocb_match_lists_device(const void *d_q, const void *d_c, const void *d_list_query, const void *d_list_begin,
+                               const void *d_list_candidates, size_t n_lists, void *d_out, void *stream);
+
     /* ---- K2/K3: hypotheses x correspondences MSAC scoring -------------------------------------------------
      * Replaces the score loop of ransac<Model>, src/model_inliers/ransac.cpp:183-196 (without the SPRT
      * early exit, which the host driver replays), and Model::evaluate

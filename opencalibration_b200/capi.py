@@ -55,6 +55,8 @@ def lib():
         "ocb_host_alloc": (vp, [sz]),
         "ocb_host_free": (None, [vp]),
         "ocb_match_pairs": (i32, [vp, sz, vp, vp]),
+        "ocb_match_lists": (i32, [vp, sz, vp, sz, vp, vp, vp, sz, vp]),
+        "ocb_match_lists_device": (i32, [vp, vp, vp, vp, vp, sz, vp, vp]),
         "ocb_score_models": (i32, [i32, vp, sz, vp, sz, dbl, vp, vp, vp, vp]),
         "ocb_residuals": (i32, [i32, vp, vp, sz, vp]),
         "ocb_score_models_device": (i32, [i32, vp, sz, vp, vp, sz, dbl, vp, vp, vp, vp]),
@@ -183,6 +185,25 @@ def match_pairs(pairs, n_query_rows, out=None):
         out = np.zeros(total, TOP2_DTYPE)
     check(lib().ocb_match_pairs(_ptr(pa), len(pa), _ptr(out), _ptr(offs)))
     return out, offs
+
+
+# ---- K4: candidate lists ----
+def match_lists(q, c, list_query, list_begin, list_candidates):
+    """Top-2 over per-query candidate lists (CSR). -> TOP2 records, best_k = position within the list."""
+    q, c = _rows(q), _rows(c)
+    list_query = np.ascontiguousarray(list_query, np.uint32)
+    list_begin = np.ascontiguousarray(list_begin, np.uint64)
+    list_candidates = np.ascontiguousarray(list_candidates, np.uint32)
+    nl = len(list_query)
+    assert len(list_begin) == nl + 1
+    out = np.zeros(nl, TOP2_DTYPE)
+    check(lib().ocb_match_lists(_ptr(q), len(q), _ptr(c), len(c), _ptr(list_query), _ptr(list_begin),
+                                _ptr(list_candidates), nl, _ptr(out)))
+    return out
+
+
+def match_lists_device(d_q, d_c, d_list_query, d_list_begin, d_list_candidates, n_lists, d_out, stream):
+    check(lib().ocb_match_lists_device(d_q, d_c, d_list_query, d_list_begin, d_list_candidates, n_lists, d_out, stream))
 
 
 # ---- K2 / K3 ----

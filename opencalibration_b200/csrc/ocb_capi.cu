@@ -854,6 +854,91 @@ extern "C"
     }
 
     // ---------------------------------------------------------------------------------------------------
+    // K4: candidate lists
+    // ---------------------------------------------------------------------------------------------------
+    int ocb_match_lists_device(const void *d_q, const void *d_c, const void *d_list_query, const void *d_list_begin,
+                               const void *d_list_candidates, size_t n_lists, void *d_out, void *stream)
+    {
+        if (n_lists >= 0xFFFFFFFFull)
+            return fail_invalid("n_lists must fit in 32 bits");
+        if (n_lists && (!d_q || !d_list_query || !d_list_begin || !d_out))
+            return fail_invalid("null device pointer");
+        if (!aligned16(d_q) || !aligned16(d_c) || (reinterpret_cast<uintptr_t>(d_out) & 7u) ||
+            (reinterpret_cast<uintptr_t>(d_list_begin) & 7u))
+            return fail_invalid("device rows must be 16-byte aligned (out / list_begin 8)");
+        return k4_launch(d_q, d_c, static_cast<const uint32_t *>(d_list_query),
+                         static_cast<const uint64_t *>(d_list_begin), static_cast<const uint32_t *>(d_list_candidates),
+                         n_lists, static_cast<ocb_top2 *>(d_out), static_cast<cudaStream_t>(stream));
+    }
+
+    int ocb_match_lists(const uint64_t *q, size_t n_q_rows, const uint64_t *c, size_t n_c_rows,
+                        const uint32_t *list_query, const uint64_t *list_begin, const uint32_t *list_candidates,
+                        size_t n_lists, ocb_top2 *out)
+    {
+        if (n_q_rows >= 0xFFFFFFFFull || n_c_rows >= 0xFFFFFFFFull || n_lists >= 0xFFFFFFFFull)
+            return fail_invalid("row / list counts must fit in 32 bits");
+        if (n_lists == 0)
+            return 0;
+        if (!q || !list_query || !list_begin || !out)
+            return fail_invalid("null pointer");
+        // validate before anything reaches the device: a bad index would be a wild 64-byte read there
+        const uint64_t total = list_begin[n_lists];
+        if (list_begin[0] != 0)
+            return fail_invalid("list_begin[0] must be 0");
+        for (size_t l = 0; l < n_lists; l++)
+        {
+            if (list_begin[l + 1] < list_begin[l] || list_begin[l + 1] - list_begin[l] > OCB_MAX_LIST_LENGTH)
+                return fail_invalid("list_begin must be non-decreasing, lists at most OCB_MAX_LIST_LENGTH long");
+            if (list_query[l] >= n_q_rows)
+                return fail_invalid("list_query index out of range");
+        }
+        if (total && (!c || !list_candidates))
+            return fail_invalid("null pointer");
+        {
+            uint32_t worst = 0;
+            for (uint64_t k = 0; k < total; k++)
+                worst = std::max(worst, list_candidates[k]);
+            if (total && worst >= n_c_rows)
+                return fail_invalid("list_candidates index out of range");
+        }
+        ThreadCtx &cx = t_ctx;
+        int rc = cx.ensure();
+        if (rc)
+            return rc;
+        const size_t qb = n_q_rows * OCB_ROW_BYTES, cb = n_c_rows * OCB_ROW_BYTES;
+        const size_t lqb = n_lists * sizeof(uint32_t), lbb = (n_lists + 1) * sizeof(uint64_t);
+        const size_t lcb = (size_t)total * sizeof(uint32_t), ob = n_lists * sizeof(ocb_top2);
+        Carver cv;
+        const size_t o_q = cv.take(qb), o_c = cv.take(cb), o_lq = cv.take(lqb), o_lb = cv.take(lbb);
+        const size_t o_lc = cv.take(lcb), o_out = cv.take(ob);
+        rc = cx.dev_reserve(cv.off);
+        if (rc)
+            return rc;
+        Carver sv;
+        const size_t s_q = sv.take(qb), s_c = sv.take(cb), s_lq = sv.take(lqb), s_lb = sv.take(lbb);
+        const size_t s_lc = sv.take(lcb), s_out = sv.take(ob);
+        rc = cx.pinned_reserve(sv.off);
+        if (rc)
+            return rc;
+        char *d = static_cast<char *>(cx.dev.p);
+        if ((rc = upload(cx, d + o_q, q, qb, s_q)) || (rc = upload(cx, d + o_c, c, cb, s_c)) ||
+            (rc = upload(cx, d + o_lq, list_query, lqb, s_lq)) || (rc = upload(cx, d + o_lb, list_begin, lbb, s_lb)) ||
+            (rc = upload(cx, d + o_lc, list_candidates, lcb, s_lc)))
+            return rc;
+        rc = ocb_match_lists_device(d + o_q, d + o_c, d + o_lq, d + o_lb, d + o_lc, n_lists, d + o_out, cx.stream);
+        if (rc)
+            return rc;
+        char *hp = static_cast<char *>(cx.pinned.p);
+        const bool out_pinned = is_pinned_host(out);
+        OCB_CUDA(cudaMemcpyAsync(out_pinned ? (void *)out : (void *)(hp + s_out), d + o_out, ob, cudaMemcpyDeviceToHost,
+                                 cx.stream));
+        OCB_CUDA(cudaStreamSynchronize(cx.stream));
+        if (!out_pinned)
+            memcpy(out, hp + s_out, ob);
+        return 0;
+    }
+
+    // ---------------------------------------------------------------------------------------------------
     // K2 / K3
     // ---------------------------------------------------------------------------------------------------
     int ocb_prepare_correspondences_device(const void *d_corr7, const void *d_order, size_t n, void *d_corr4,

@@ -85,6 +85,10 @@ int k1_launch(const K1Problem *d_problems, const K1Problem *h_problems, size_t n
               cudaStream_t stream);
 int k1_queries_per_cta();
 
+// ---- K4 launch interface (hamming_lists.cu) ----------------------------------------------------------------
+int k4_launch(const void *d_q_rows, const void *d_c_rows, const uint32_t *d_list_query, const uint64_t *d_list_begin,
+              const uint32_t *d_list_candidates, size_t n_lists, ocb_top2 *d_out, cudaStream_t stream);
+
 // ---- K2/K3 launch interface (score_models.cu) ---------------------------------------------------------------
 int k2_prepare(const double *d_corr7, const uint32_t *d_order, size_t n, double *d_corr4, uint32_t *d_pos,
                cudaStream_t stream);

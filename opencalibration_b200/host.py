@@ -40,6 +40,7 @@ def lib():
     L.ocbh_features_destroy.argtypes = [vp]
     L.ocbh_features_destroy.restype = None
     L.ocbh_match_handles.argtypes = [vp, vp, _szp, sz, _szp, sz, _szp, _szp, _f64p, vp, _szp]
+    L.ocbh_match_guided.argtypes = [_u64p, sz, _u64p, sz, _szp, _szp, _szp, sz, _szp, _szp, _szp, _f64p, _f64p, _szp]
     L.ocbh_subsample.argtypes = [_f64p, _f32p, sz, dbl, sz, _szp]
     L.ocbh_subsample.restype = sz
     L.ocbh_ransac.argtypes = [i32, _f64p, sz, _f64p, _u8p, _f64p, _szp]
@@ -127,6 +128,27 @@ def match_features_subset(desc1, desc2, idx1, idx2, cross_check=False):
     if cross_check:
         return o1[:m].copy(), o2[:m].copy(), od[:m].copy(), mut[:m].astype(bool)
     return o1[:m].copy(), o2[:m].copy(), od[:m].copy()
+
+
+def match_features_guided(desc1, desc2, query_feature, begin, nearby):
+    """Guided matcher of the dense stage (src/dense/dense_stereo.cpp:244-281) for lists in CSR form.
+    -> (list, query_feature, candidate_feature, best_distance, second_distance) of the accepted visits, list order."""
+    desc1, desc2 = _rows(desc1), _rows(desc2)
+    query_feature = np.ascontiguousarray(query_feature, np.uintp)
+    begin = np.ascontiguousarray(begin, np.uintp)
+    nearby = np.ascontiguousarray(nearby, np.uintp)
+    nl = len(query_feature)
+    assert len(begin) == nl + 1
+    m = max(nl, 1)
+    ol, oq, oc = np.zeros(m, np.uintp), np.zeros(m, np.uintp), np.zeros(m, np.uintp)
+    ob, os_ = np.zeros(m, np.float64), np.zeros(m, np.float64)
+    n = np.zeros(1, np.uintp)
+    if len(nearby) == 0:
+        nearby = np.zeros(1, np.uintp)
+    _check(lib().ocbh_match_guided(desc1, len(desc1), desc2, len(desc2), query_feature if nl else np.zeros(1, np.uintp),
+                                   begin, nearby, nl, ol, oq, oc, ob, os_, n))
+    k = int(n[0])
+    return ol[:k].copy(), oq[:k].copy(), oc[:k].copy(), ob[:k].copy(), os_[:k].copy()
 
 
 class FeatureSet:

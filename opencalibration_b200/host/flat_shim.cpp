@@ -1,6 +1,7 @@
 // Flat C entry points over the C++ mirror, for ctypes-driven tests and bench.py (opencalibration_b200/host.py).
 // They build the reference-typed arguments (std::vector<feature_2d>, std::vector<correspondence>, model structs),
 // call the mirror exactly as src/pipeline/link_stage.cpp:80-93 would, and flatten the results.
+#include "guided_match.hpp"
 #include "link_batch.hpp"
 #include "models_detail.hpp"
 
@@ -192,6 +193,32 @@ extern "C"
                 out_dist[i] = r[i].distance;
                 if (mutual)
                     mutual[i] = mut[i];
+            }
+            *n_out = r.size();
+        });
+    }
+
+    // ---- src/dense guided matcher (guided_match.hpp). Lists in CSR form; outputs hold up to n_lists entries.
+    int ocbh_match_guided(const uint64_t *desc1, size_t nf1, const uint64_t *desc2, size_t nf2,
+                          const size_t *query_feature, const size_t *begin, const size_t *nearby, size_t n_lists,
+                          size_t *out_list, size_t *out_query, size_t *out_candidate, double *out_best,
+                          double *out_second, size_t *n_out)
+    {
+        return guarded([&] {
+            const std::vector<feature_2d> f1 = make_features(nullptr, nullptr, desc1, nf1);
+            const std::vector<feature_2d> f2 = make_features(nullptr, nullptr, desc2, nf2);
+            ocb_host::GuidedLists lists;
+            lists.query_feature.assign(query_feature, query_feature + n_lists);
+            lists.begin.assign(begin, begin + n_lists + 1);
+            lists.nearby.assign(nearby, nearby + begin[n_lists]);
+            const std::vector<ocb_host::GuidedMatch> r = ocb_host::match_features_guided(f1, f2, lists);
+            for (size_t i = 0; i < r.size(); i++)
+            {
+                out_list[i] = r[i].list;
+                out_query[i] = r[i].query_feature;
+                out_candidate[i] = r[i].candidate_feature;
+                out_best[i] = r[i].best_distance;
+                out_second[i] = r[i].second_distance;
             }
             *n_out = r.size();
         });

@@ -181,3 +181,56 @@ class PlanarSurvey:
         strength = np.sort(rng.random(len(d)).astype(np.float32))[::-1].copy()
         order = rng.permutation(len(d))
         return d[order].copy(), pix[order].copy(), strength
+
+
+def guided_visits(n_q, n_c, width=4000.0, height=3000.0, radius=150.0, match_fraction=0.6, noise=0.08, jitter=20.0,
+                  seed=11):
+    """Dense-stage guided matching workload (src/dense/dense_stereo.cpp:217-281) for ONE candidate image:
+    n_c candidate features at uniform positions in a width x height image, n_q source features whose predicted
+    position in that image is known; `match_fraction` of them are noisy copies of a candidate within `jitter`
+    pixels of the prediction (so the 0.85 ratio rule passes for a controlled subset), the rest are unrelated.
+    Queries are ordered along a Hilbert curve of the predicted position like the reference orders its source
+    features (:23-48,191-193). Candidate lists = features within `radius` of the prediction by ascending distance
+    (jk-tree's result order). -> dict(q, c, pred_xy, cand_xy, begin uint64 [n_q+1], nearby uint32)."""
+    from scipy.spatial import cKDTree
+    rng = np.random.default_rng(seed)
+    cand_xy = np.stack([rng.uniform(0, width, n_c), rng.uniform(0, height, n_c)], axis=1)
+    c = random_descriptors(n_c, rng)
+    q = random_descriptors(n_q, rng)
+    m = int(n_q * match_fraction)
+    src = rng.integers(0, max(n_c, 1), m) if n_c else np.zeros(0, np.int64)
+    pred_xy = np.stack([rng.uniform(0, width, n_q), rng.uniform(0, height, n_q)], axis=1)
+    if m and n_c:
+        q[:m] = flip_bits(c[src], noise, rng)
+        pred_xy[:m] = cand_xy[src] + rng.normal(0, jitter, (m, 2))
+    # Hilbert order of the predictions (d2xy-style index on a 4096 grid)
+    def hilbert(x, y, order=4096):
+        x, y = x.astype(np.int64).copy(), y.astype(np.int64).copy()
+        d = np.zeros(len(x), np.int64)
+        s = order // 2
+        while s > 0:
+            rx, ry = ((x & s) > 0).astype(np.int64), ((y & s) > 0).astype(np.int64)
+            d += s * s * ((3 * rx) ^ ry)
+            flip = (ry == 0) & (rx == 1)
+            x, y = np.where(flip, s - 1 - x, x), np.where(flip, s - 1 - y, y)
+            swap = ry == 0
+            x, y = np.where(swap, y, x), np.where(swap, x, y)
+            s //= 2
+        return d
+    perm = np.argsort(hilbert(np.clip(pred_xy[:, 0], 0, width - 1), np.clip(pred_xy[:, 1], 0, height - 1)), kind="stable")
+    q, pred_xy = q[perm], pred_xy[perm]
+    begin = np.zeros(n_q + 1, np.uint64)
+    nearby = np.zeros(0, np.uint32)
+    if n_c and n_q:
+        pairs = cKDTree(pred_xy).sparse_distance_matrix(cKDTree(cand_xy), radius * (1 + 1e-9), output_type="ndarray")
+        owner, flat = pairs["i"].astype(np.int64), pairs["j"].astype(np.int64)
+        d2 = ((cand_xy[flat] - pred_xy[owner]) ** 2).sum(axis=1)
+        keep = d2 < radius * radius  # jk-tree keeps maxRadius > distance (squared), strictly
+        flat, owner, d2 = flat[keep], owner[keep], d2[keep]
+        # per list: ascending distance, the KD-tree's result order (two single-key sorts: by distance, then a stable
+        # one by list -- much faster than a three-key lexsort; exact distance ties do not occur for random positions)
+        order = np.argsort(d2)
+        order = order[np.argsort(owner[order], kind="stable")]
+        nearby = flat[order].astype(np.uint32)
+        begin[1:] = np.cumsum(np.bincount(owner, minlength=n_q)).astype(np.uint64)
+    return dict(q=q, c=c, pred_xy=pred_xy, cand_xy=cand_xy, begin=begin, nearby=nearby.astype(np.uint32))

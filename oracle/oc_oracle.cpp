@@ -81,6 +81,50 @@ void match_top2(const uint64_t *q, size_t n1, const uint64_t *c, size_t n2, uint
     }
 }
 
+void match_lists_top2(const uint64_t *q, const uint64_t *c, const uint32_t *list_query, const uint64_t *list_begin,
+                      const uint32_t *list_candidates, size_t n_lists, uint32_t *best_pos, double *best_dist,
+                      double *second_dist)
+{
+    for (size_t l = 0; l < n_lists; l++)
+    {
+        // src/dense/dense_stereo.cpp:251-273
+        double best = std::numeric_limits<double>::infinity();
+        double second = std::numeric_limits<double>::infinity();
+        uint32_t bp = 0;
+        const uint64_t *ql = q + (size_t)list_query[l] * DESCRIPTOR_WORDS;
+        for (uint64_t k = list_begin[l]; k < list_begin[l + 1]; k++)
+        {
+            // descriptor_distance, :56-59
+            const double d = hamming512(ql, c + (size_t)list_candidates[k] * DESCRIPTOR_WORDS) * (1.0 / DESCRIPTOR_BITS);
+            if (d < second) // :258
+            {
+                if (d < best) // :260
+                {
+                    second = best;
+                    best = d;
+                    bp = (uint32_t)(k - list_begin[l]);
+                }
+                else
+                {
+                    second = d; // :268
+                }
+            }
+        }
+        best_pos[l] = bp;
+        best_dist[l] = best;
+        second_dist[l] = second;
+    }
+}
+
+bool guided_good_match(size_t list_length, double best_dist, double second_dist)
+{
+    constexpr double RATIO_THRESHOLD = 0.85;                  // src/dense/dense_stereo.cpp:51
+    constexpr double MAX_ABSOLUTE_DESCRIPTOR_DISTANCE = 0.35; // :53
+    if (list_length == 0)
+        return false; // :248-249
+    return list_length >= 2 ? best_dist < RATIO_THRESHOLD * second_dist : best_dist < MAX_ABSOLUTE_DESCRIPTOR_DISTANCE;
+}
+
 void match_col_best(const uint64_t *q, size_t n1, const uint64_t *c, size_t n2, uint32_t *col_best_q)
 {
     for (size_t k = 0; k < n2; k++)

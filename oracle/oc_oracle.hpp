@@ -77,6 +77,18 @@ std::vector<Match> match_features_subset(const uint64_t *desc1, const uint64_t *
 std::vector<size_t> spatially_subsample_feature_indices(const double *xy, const float *strength, size_t n_features,
                                                         double spacing_pixels, size_t count);
 
+// ---- src/dense: guided matcher -----------------------------------------------------------------
+// Inner loop of densifyMesh (src/dense/dense_stereo.cpp:251-273) on packed rows and CSR candidate lists: list l
+// compares q[list_query[l]] with c[list_candidates[list_begin[l] .. list_begin[l+1])] in list order (the order of
+// `nearby`, :244-246). best_pos = POSITION in the list of the first minimum (0 for an empty list, :253), distances in
+// double exactly as descriptor_distance computes them (:56-59); +inf when absent.
+void match_lists_top2(const uint64_t *q, const uint64_t *c, const uint32_t *list_query, const uint64_t *list_begin,
+                      const uint32_t *list_candidates, size_t n_lists, uint32_t *best_pos, double *best_dist,
+                      double *second_dist);
+// The acceptance rule that follows (:275-276): >= 2 candidates: best < 0.85 * second; otherwise best < 0.35.
+// (The reference never reaches it with an empty list, :248-249; an empty list is rejected here.)
+bool guided_good_match(size_t list_length, double best_dist, double second_dist);
+
 // ---- src/model_inliers: residuals ----------------------------------------------------------------
 double error(const Model &m, const Corr &c);                                          // *_model.cpp ::error
 double evaluate(const Model &m, const Corr *c, size_t n, std::vector<bool> &inliers); // *_model.cpp ::evaluate

@@ -82,6 +82,9 @@ class Oracle:
         L.oco_bench_match_pairs.argtypes = [_u64p, _u64p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, _szp]
         L.oco_bench_match_pairs.restype = C.c_double
         L.oco_num_procs.restype = C.c_int
+        L.oco_match_lists.argtypes = [_u64p, _u64p, _u32p, _u64p, _u32p, C.c_size_t, _u32p, _f64p, _f64p, _u8p]
+        L.oco_bench_match_lists.argtypes = [_u64p, _u64p, _u32p, _u64p, _u32p, C.c_size_t, C.c_int, _u32p, _f64p, _f64p]
+        L.oco_bench_match_lists.restype = C.c_double
         L.oco_scene_homography.argtypes = [C.c_size_t, C.c_size_t, C.c_uint, _f64p, _f64p]
         L.oco_scene_homography_near_degenerate.argtypes = [_f64p, _f64p]
         L.oco_scene_fundamental.argtypes = [C.c_size_t, C.c_size_t, C.c_double, C.c_uint, _f64p, _f64p]
@@ -109,6 +112,31 @@ class Oracle:
         bk, bd, sd = np.zeros(n1, np.uint32), np.zeros(n1, np.uint16), np.zeros(n1, np.uint16)
         self.lib.oco_match_top2(q, n1, c, len(c), bk, bd, sd)
         return bk, bd, sd
+
+    def match_lists(self, q, c, list_query, list_begin, list_candidates):
+        """src/dense/dense_stereo.cpp:251-276 -> (best position, best distance, second distance, accepted) per list."""
+        q, c = _rows(q), _rows(c)
+        lq = np.ascontiguousarray(list_query, np.uint32)
+        lb = np.ascontiguousarray(list_begin, np.uint64)
+        lc = np.ascontiguousarray(list_candidates, np.uint32)
+        if len(lc) == 0:
+            lc = np.zeros(1, np.uint32)
+        if len(c) == 0:
+            c = np.zeros((1, 8), np.uint64)
+        nl = len(lq)
+        bp, bd, sd, good = np.zeros(nl, np.uint32), np.zeros(nl), np.zeros(nl), np.zeros(nl, np.uint8)
+        if nl:
+            self.lib.oco_match_lists(q, c, lq, lb, lc, nl, bp, bd, sd, good)
+        return bp, bd, sd, good.astype(bool)
+
+    def bench_match_lists(self, q, c, list_query, list_begin, list_candidates, threads=0):
+        q, c = _rows(q), _rows(c)
+        lq = np.ascontiguousarray(list_query, np.uint32)
+        lb = np.ascontiguousarray(list_begin, np.uint64)
+        lc = np.ascontiguousarray(list_candidates, np.uint32)
+        nl = len(lq)
+        bp, bd, sd = np.zeros(nl, np.uint32), np.zeros(nl), np.zeros(nl)
+        return self.lib.oco_bench_match_lists(q, c, lq, lb, lc, nl, threads, bp, bd, sd)
 
     def match_col_best(self, q, c):
         q, c = _rows(q), _rows(c)
@@ -263,6 +291,8 @@ class Reference:
         L.ocr_bench_match_pairs.argtypes = [_u64p, _u64p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, _szp]
         L.ocr_bench_match_pairs.restype = C.c_double
         L.ocr_num_procs.restype = C.c_int
+        L.ocr_radius_lists.argtypes = [_f64p, C.c_size_t, _f64p, C.c_size_t, C.c_double, C.c_void_p, C.c_void_p]
+        L.ocr_radius_lists.restype = C.c_size_t
 
     @staticmethod
     def available():
@@ -283,6 +313,18 @@ class Reference:
         m = self.lib.ocr_match_features_subset(desc1, len(desc1), desc2, len(desc2), idx1, n1, idx2, len(idx2),
                                                o1, o2, od)
         return o1[:m].copy(), o2[:m].copy(), od[:m].copy()
+
+    def radius_lists(self, cand_xy, pred_xy, radius=150.0):
+        """Candidate lists of the dense stage from the reference's own jk-tree (dense_stereo.cpp:127-131,244-246):
+        -> (begin [n_q + 1] uint64, nearby uint32) in the KD-tree's result order."""
+        cand_xy = np.ascontiguousarray(cand_xy, np.float64).reshape(-1, 2)
+        pred_xy = np.ascontiguousarray(pred_xy, np.float64).reshape(-1, 2)
+        r2 = float(radius) * float(radius)
+        total = self.lib.ocr_radius_lists(cand_xy, len(cand_xy), pred_xy, len(pred_xy), r2, None, None)
+        begin, nearby = np.zeros(len(pred_xy) + 1, np.uint64), np.zeros(max(total, 1), np.uint32)
+        self.lib.ocr_radius_lists(cand_xy, len(cand_xy), pred_xy, len(pred_xy), r2, begin.ctypes.data_as(C.c_void_p),
+                                  nearby.ctypes.data_as(C.c_void_p))
+        return begin, nearby[:total]
 
     def subsample(self, xy, strength, spacing, count=0):
         xy = np.ascontiguousarray(xy, np.float64).reshape(-1, 2)

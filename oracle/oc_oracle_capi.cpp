@@ -2,6 +2,7 @@
 // bench.py's cpu_baseline / --impl reference legs). Not linked by the product.
 #include "oc_oracle.hpp"
 
+#include <algorithm>
 #include <chrono>
 #include <cstring>
 #include <omp.h>
@@ -39,6 +40,35 @@ extern "C"
     void oco_match_col_best(const uint64_t *q, size_t n1, const uint64_t *c, size_t n2, uint32_t *col_best_q)
     {
         match_col_best(q, n1, c, n2, col_best_q);
+    }
+    // -> per list: best position, best / second distance (double), accepted flag (dense_stereo.cpp:251-276)
+    void oco_match_lists(const uint64_t *q, const uint64_t *c, const uint32_t *list_query, const uint64_t *list_begin,
+                         const uint32_t *list_candidates, size_t n_lists, uint32_t *best_pos, double *best_dist,
+                         double *second_dist, uint8_t *good)
+    {
+        match_lists_top2(q, c, list_query, list_begin, list_candidates, n_lists, best_pos, best_dist, second_dist);
+        for (size_t l = 0; l < n_lists; l++)
+            good[l] = guided_good_match(list_begin[l + 1] - list_begin[l], best_dist[l], second_dist[l]);
+    }
+    // the same loop timed under OpenMP over lists (the reference parallelises over source images, :174-175)
+    double oco_bench_match_lists(const uint64_t *q, const uint64_t *c, const uint32_t *list_query,
+                                 const uint64_t *list_begin, const uint32_t *list_candidates, size_t n_lists,
+                                 int threads, uint32_t *best_pos, double *best_dist, double *second_dist)
+    {
+        if (threads <= 0)
+            threads = omp_get_num_procs();
+        const size_t chunk = 256;
+        const long chunks = (long)((n_lists + chunk - 1) / chunk);
+        auto t0 = std::chrono::steady_clock::now();
+#pragma omp parallel for schedule(dynamic) num_threads(threads)
+        for (long b = 0; b < chunks; b++)
+        {
+            const size_t l0 = (size_t)b * chunk, l1 = std::min(n_lists, l0 + chunk);
+            // list_begin offsets are absolute, so a sub-range is the same call on shifted pointers
+            match_lists_top2(q, c, list_query + l0, list_begin + l0, list_candidates, l1 - l0, best_pos + l0,
+                             best_dist + l0, second_dist + l0);
+        }
+        return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     }
     size_t oco_match_features_subset(const uint64_t *desc1, const uint64_t *desc2, const size_t *idx1, size_t n1,
                                      const size_t *idx2, size_t n2, size_t *out_i1, size_t *out_i2, double *out_dist)

@@ -5,7 +5,10 @@
 #include <opencalibration/match/match_features.hpp>
 #include <opencalibration/model_inliers/ransac.hpp>
 
+#include <jk/KDTree.h>
+
 #include <chrono>
+#include <limits>
 #include <cstddef>
 #include <cstring>
 #include <omp.h>
@@ -57,6 +60,34 @@ extern "C"
             out_dist[i] = r[i].distance;
         }
         return r.size();
+    }
+    // The candidate lists of the dense stage exactly as the reference builds them (src/dense/dense_stereo.cpp:
+    // 127-131 tree of an image's features, :244-246 radius search around each predicted position) with the
+    // reference's own vendored jk-tree: list l = payloads of searcher.search(pred[l], radius_sq, max) in result
+    // order. Two passes: out_nearby == NULL counts (returns the total), otherwise fills begin[n_q + 1] and nearby.
+    size_t ocr_radius_lists(const double *cand_xy, size_t n_c, const double *pred_xy, size_t n_q, double radius_sq,
+                            uint64_t *out_begin, uint32_t *out_nearby)
+    {
+        jk::tree::KDTree<size_t, 2, 8> tree;
+        for (size_t i = 0; i < n_c; i++)
+            tree.addPoint({cand_xy[2 * i], cand_xy[2 * i + 1]}, i);
+        auto searcher = tree.searcher();
+        size_t total = 0;
+        for (size_t l = 0; l < n_q; l++)
+        {
+            const auto &nearby =
+                searcher.search({pred_xy[2 * l], pred_xy[2 * l + 1]}, radius_sq, std::numeric_limits<size_t>::max());
+            if (out_nearby)
+            {
+                out_begin[l] = total;
+                for (size_t k = 0; k < nearby.size(); k++)
+                    out_nearby[total + k] = (uint32_t)nearby[k].payload;
+            }
+            total += nearby.size();
+        }
+        if (out_nearby)
+            out_begin[n_q] = total;
+        return total;
     }
     size_t ocr_subsample(const double *xy, const float *strength, size_t n, double spacing, size_t count,
                          size_t *out_idx)
