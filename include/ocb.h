@@ -191,6 +191,16 @@ extern "C"
     int ocb_score_bound(int kind, const double *models, size_t h, double thr, int in_order, double *score,
                         uint32_t *count, uint32_t *inlier_bits);
     int ocb_residuals_bound(int kind, const double *model18, double *e);
+    /* Device-side minimal-sample fits against the bound correspondences (see OCB_REQ_FIT_SCORE_ORDERED below):
+     * samples [h][4] -> models_out [h][18], degenerate [h]; with score != NULL the fitted models are also scored in the
+     * bound evaluation order (score [h], count [h]) in the same submission. */
+    int ocb_fit_score_bound(const uint32_t *samples, size_t h, double thr, double *models_out, uint8_t *degenerate,
+                            double *score, uint32_t *count);
+    /* Stand-alone form: fits h minimal samples of corr [n][7] (replaces homography_model::checkSampleDegeneracy +
+     * homography_model::fit, src/model_inliers/homography_model.cpp:19-50,120-136, for h hypotheses at once).
+     * Replaces the calling thread's ocb_corr_bind binding. */
+    int ocb_fit_homography(const double *corr, size_t n, const uint32_t *samples, size_t h, double *models_out,
+                           uint8_t *degenerate);
 
     /* Batched form for a whole submission of image pairs (the batched LinkStage runner advances the RANSAC runs of
      * all its pairs in lock step): ocb_corr_bind_batch makes `count` correspondence sets resident for the calling
@@ -201,6 +211,13 @@ extern "C"
      *   mode OCB_REQ_EVALUATE       h models in index order -> score[h], count[h], inlier_bits[h][ceil(n/32)]
      *                               (Model::evaluate, homography_model.cpp:99-118 and twins)
      *   mode OCB_REQ_RESIDUALS      one model -> residuals[n] (Model::error per correspondence)
+     *   mode OCB_REQ_FIT_SCORE_ORDERED  (homography only) h minimal samples of 4 correspondence indices each are
+     *                               checked (homography_model::checkSampleDegeneracy, homography_model.cpp:120-136),
+     *                               fitted ON THE DEVICE (homography_model::fit, :19-50: 9x9 DLT system with the
+     *                               h33 == 1 row, full-pivot LU solve, division by H(2,2), 3x3 inverse) and scored
+     *                               like OCB_REQ_SCORE_ORDERED -> models_out[h][18], degenerate[h], score[h],
+     *                               count[h]. This is ransac.cpp:164-196 for h iterations without the host in
+     *                               the loop; the fitted models equal the host adapters' fit bit for bit.
      * Results are bit-identical to ocb_score_models / ocb_residuals on the same inputs. */
     typedef struct ocb_corr_set
     {
@@ -212,7 +229,8 @@ extern "C"
     {
         OCB_REQ_SCORE_ORDERED = 0,
         OCB_REQ_EVALUATE = 1,
-        OCB_REQ_RESIDUALS = 2
+        OCB_REQ_RESIDUALS = 2,
+        OCB_REQ_FIT_SCORE_ORDERED = 3
     };
     typedef struct ocb_score_request
     {
@@ -226,6 +244,10 @@ extern "C"
         uint32_t *count;
         uint32_t *inlier_bits;
         double *residuals;
+        /* OCB_REQ_FIT_SCORE_ORDERED only (models is ignored): */
+        const uint32_t *samples; /* [h][4] correspondence indices of the minimal samples */
+        double *models_out;      /* [h][18] fitted models (NaN for a degenerate sample) */
+        uint8_t *degenerate;     /* [h] 1 = the sample failed checkSampleDegeneracy and was not fitted */
     } ocb_score_request;
     int ocb_corr_bind_batch(const ocb_corr_set *sets, size_t count);
     int ocb_score_requests(const ocb_score_request *requests, size_t count);

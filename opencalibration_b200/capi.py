@@ -59,6 +59,7 @@ def lib():
         "ocb_match_lists_device": (i32, [vp, vp, vp, vp, vp, sz, vp, vp]),
         "ocb_score_models": (i32, [i32, vp, sz, vp, sz, dbl, vp, vp, vp, vp]),
         "ocb_residuals": (i32, [i32, vp, vp, sz, vp]),
+        "ocb_fit_homography": (i32, [vp, sz, vp, sz, vp, vp]),
         "ocb_score_models_device": (i32, [i32, vp, sz, vp, vp, sz, dbl, vp, vp, vp, vp]),
         "ocb_prepare_correspondences_device": (i32, [vp, vp, sz, vp, vp, vp]),
     }
@@ -225,6 +226,16 @@ def residuals(kind, model18, corr):
     e = np.zeros(len(corr), np.float64)
     check(lib().ocb_residuals(kind, _ptr(model18), _ptr(corr), len(corr), _ptr(e)))
     return e
+
+
+def fit_homography(corr, samples):
+    """Minimal-sample homography fits on the device -> (models [h][18], degenerate [h] bool)."""
+    corr = np.ascontiguousarray(corr, np.float64).reshape(-1, 7)
+    samples = np.ascontiguousarray(samples, np.uint32).reshape(-1, 4)
+    h = len(samples)
+    models, deg = np.zeros((h, 18), np.float64), np.zeros(h, np.uint8)
+    check(lib().ocb_fit_homography(_ptr(corr), len(corr), _ptr(samples), h, _ptr(models), _ptr(deg)))
+    return models, deg.astype(bool)
 
 
 # ---- K2 / K3, device buffers ----

@@ -1169,6 +1169,88 @@ extern "C"
         return 0;
     }
 
+    int ocb_fit_score_bound(const uint32_t *samples, size_t h, double thr, double *models_out, uint8_t *degenerate,
+                            double *score, uint32_t *count)
+    {
+        if (h >= 0xFFFFFFFFull)
+            return fail_invalid("sizes must fit in 32 bits");
+        ThreadCtx &cx = t_ctx;
+        int rc = cx.ensure();
+        if (rc)
+            return rc;
+        if (!cx.bound_valid)
+            return fail_invalid("no correspondences bound on this thread (ocb_corr_bind)");
+        if (score && !cx.bound_has_order)
+            return fail_invalid("correspondences were bound without an evaluation order");
+        if (h == 0)
+            return 0;
+        if (!samples || !models_out || !degenerate || (score && !count))
+            return fail_invalid("null pointer");
+        const size_t n = cx.bound_n;
+        for (size_t i = 0; i < h * 4; i++)
+            if (samples[i] >= n)
+                return fail_invalid("sample index out of range");
+        const BoundLayout L = bound_layout(n);
+        const size_t sb = h * 4 * sizeof(uint32_t), mb = h * 18 * sizeof(double);
+        Carver cv; // device: [job][samples] in, [models][degenerate][score][count] out (one copy back)
+        const size_t o_job = cv.take(sizeof(K3FitJob)), o_s = cv.take(sb);
+        const size_t in_bytes = cv.off;
+        const size_t o_m = cv.take(mb), o_dg = cv.take(h), o_sc = cv.take(score ? h * sizeof(double) : 0),
+                     o_cnt = cv.take(score ? h * sizeof(uint32_t) : 0);
+        const size_t out_bytes = cv.off - o_m;
+        if ((rc = cx.dev_reserve(cv.off)) || (rc = cx.pinned_reserve(cv.off)))
+            return rc;
+        char *b = static_cast<char *>(cx.bound.p);
+        char *d = static_cast<char *>(cx.dev.p);
+        char *hp = static_cast<char *>(cx.pinned.p);
+        K3FitJob job;
+        job.c7 = reinterpret_cast<const double *>(b + L.o_c7);
+        job.samples = reinterpret_cast<const uint32_t *>(d + o_s);
+        job.models_out = reinterpret_cast<double *>(d + o_m);
+        job.degenerate = reinterpret_cast<uint8_t *>(d + o_dg);
+        job.h = (uint32_t)h, job.begin = 0;
+        memcpy(hp + o_job, &job, sizeof job);
+        memcpy(hp + o_s, samples, sb);
+        OCB_CUDA(cudaMemcpyAsync(d, hp, in_bytes, cudaMemcpyHostToDevice, cx.stream));
+        if ((rc = k3_fit_samples(reinterpret_cast<const K3FitJob *>(d + o_job), 1, (uint32_t)h, cx.stream)))
+            return rc;
+        if (score)
+        {
+            rc = k2_score(OCB_MODEL_HOMOGRAPHY, reinterpret_cast<double *>(d + o_m), h,
+                          reinterpret_cast<double *>(b + L.o_ord), reinterpret_cast<uint32_t *>(b + L.o_pos), n, thr,
+                          reinterpret_cast<double *>(d + o_sc), reinterpret_cast<uint32_t *>(d + o_cnt), nullptr, nullptr,
+                          cx.stream);
+            if (rc)
+                return rc;
+        }
+        OCB_CUDA(cudaMemcpyAsync(hp + o_m, d + o_m, out_bytes, cudaMemcpyDeviceToHost, cx.stream));
+        OCB_CUDA(cudaStreamSynchronize(cx.stream));
+        memcpy(models_out, hp + o_m, mb);
+        memcpy(degenerate, hp + o_dg, h);
+        if (score)
+        {
+            memcpy(score, hp + o_sc, h * sizeof(double));
+            memcpy(count, hp + o_cnt, h * sizeof(uint32_t));
+        }
+        return 0;
+    }
+
+    int ocb_fit_homography(const double *corr, size_t n, const uint32_t *samples, size_t h, double *models_out,
+                           uint8_t *degenerate)
+    {
+        if (h == 0)
+            return 0;
+        if (!corr || n == 0)
+            return fail_invalid("corr");
+        // fits need no evaluation order: bind in index order for the duration of the call
+        int rc = ocb_corr_bind(corr, n, nullptr);
+        if (rc)
+            return rc;
+        rc = ocb_fit_score_bound(samples, h, 0.0, models_out, degenerate, nullptr, nullptr);
+        ocb_corr_unbind();
+        return rc;
+    }
+
     int ocb_residuals_bound(int kind, const double *model18, double *e)
     {
         if (kind < 0 || kind > 2)
@@ -1273,23 +1355,43 @@ extern "C"
             return rc;
         if (!cx.batch_valid)
             return fail_invalid("no correspondence batch bound on this thread (ocb_corr_bind_batch)");
-        // layout of the per-call device block: [request table][models][outputs]; outputs are read back in one copy
+        // layout of the per-call device block: [request table][fit jobs][models | samples][outputs]; outputs (for
+        // fit requests: the fitted models and degeneracy flags too) are read back in one copy
         Carver in_cv, out_cv;
         const size_t o_tab = in_cv.take(count * sizeof(K2Request));
-        std::vector<size_t> o_models(count), o_score(count), o_count(count), o_aux(count);
+        size_t n_fit = 0;
+        for (size_t i = 0; i < count; i++)
+            n_fit += req[i].mode == OCB_REQ_FIT_SCORE_ORDERED;
+        const size_t o_jobs = in_cv.take(n_fit * sizeof(K3FitJob));
+        std::vector<size_t> o_models(count), o_score(count), o_count(count), o_aux(count), o_flags(count);
         for (size_t i = 0; i < count; i++)
         {
             const ocb_score_request &r = req[i];
-            if (r.kind < 0 || r.kind > 2 || r.mode < 0 || r.mode > 2)
+            if (r.kind < 0 || r.kind > 2 || r.mode < 0 || r.mode > 3)
                 return fail_invalid("request kind / mode");
             if (r.set >= cx.batch_sets.size())
                 return fail_invalid("request references an unbound set");
             const ThreadCtx::BatchSet &bs = cx.batch_sets[r.set];
-            if (!r.models || r.h == 0 || (r.mode == 2 && (r.h != 1 || !r.residuals)) ||
+            const bool fit = r.mode == OCB_REQ_FIT_SCORE_ORDERED;
+            if (r.h == 0 || (!fit && !r.models) || (r.mode == 2 && (r.h != 1 || !r.residuals)) ||
                 (r.mode != 2 && (!r.score || !r.count)) || (r.mode == 1 && !r.inlier_bits))
                 return fail_invalid("request pointers");
-            if (r.mode == 0 && !bs.has_order && bs.n)
+            if (fit && (r.kind != OCB_MODEL_HOMOGRAPHY || !r.samples || !r.models_out || !r.degenerate))
+                return fail_invalid("fit request: homography only; samples, models_out and degenerate are required");
+            if ((r.mode == 0 || fit) && !bs.has_order && bs.n)
                 return fail_invalid("set was bound without an evaluation order");
+            if (fit)
+            {
+                for (size_t k = 0; k < (size_t)r.h * 4; k++)
+                    if (r.samples[k] >= bs.n)
+                        return fail_invalid("sample index out of range");
+                o_aux[i] = in_cv.take((size_t)r.h * 4 * sizeof(uint32_t)); // samples
+                o_models[i] = out_cv.take((size_t)r.h * 18 * sizeof(double));
+                o_flags[i] = out_cv.take(r.h);
+                o_score[i] = out_cv.take((size_t)r.h * sizeof(double));
+                o_count[i] = out_cv.take((size_t)r.h * sizeof(uint32_t));
+                continue;
+            }
             o_models[i] = in_cv.take((size_t)r.h * 18 * sizeof(double));
             const size_t words = (bs.n + 31) / 32;
             if (r.mode == 2)
@@ -1309,20 +1411,38 @@ extern "C"
         char *hp = static_cast<char *>(cx.pinned.p);
         char *b = static_cast<char *>(cx.batch.p);
         K2Request *tab = reinterpret_cast<K2Request *>(hp + o_tab);
-        uint32_t ctas = 0;
+        K3FitJob *jobs = reinterpret_cast<K3FitJob *>(hp + o_jobs);
+        uint32_t ctas = 0, fit_total = 0;
+        size_t j = 0;
         for (size_t i = 0; i < count; i++)
         {
             const ocb_score_request &r = req[i];
             const ThreadCtx::BatchSet &bs = cx.batch_sets[r.set];
-            memcpy(hp + o_models[i], r.models, (size_t)r.h * 18 * sizeof(double));
+            const bool fit = r.mode == OCB_REQ_FIT_SCORE_ORDERED;
             K2Request q;
             memset(&q, 0, sizeof q);
-            q.models = reinterpret_cast<const double *>(d + o_models[i]);
             q.c7 = reinterpret_cast<const double *>(b + bs.o_c7);
-            q.order = (r.mode == 0 && bs.has_order) ? reinterpret_cast<const uint32_t *>(b + bs.o_ord) : nullptr;
+            if (fit)
+            {
+                memcpy(hp + o_aux[i], r.samples, (size_t)r.h * 4 * sizeof(uint32_t));
+                K3FitJob &job = jobs[j++];
+                job.c7 = q.c7;
+                job.samples = reinterpret_cast<const uint32_t *>(d + o_aux[i]);
+                job.models_out = reinterpret_cast<double *>(d_out + o_models[i]);
+                job.degenerate = reinterpret_cast<uint8_t *>(d_out + o_flags[i]);
+                job.h = r.h, job.begin = fit_total;
+                fit_total += r.h;
+                q.models = job.models_out;
+            }
+            else
+            {
+                memcpy(hp + o_models[i], r.models, (size_t)r.h * 18 * sizeof(double));
+                q.models = reinterpret_cast<const double *>(d + o_models[i]);
+            }
+            q.order = ((r.mode == 0 || fit) && bs.has_order) ? reinterpret_cast<const uint32_t *>(b + bs.o_ord) : nullptr;
             q.thr = r.thr;
             q.h = r.h, q.n = (uint32_t)bs.n, q.words = (uint32_t)((bs.n + 31) / 32);
-            q.kind = r.kind, q.mode = r.mode;
+            q.kind = r.kind, q.mode = fit ? 0 : r.mode; // a fit request is scored like OCB_REQ_SCORE_ORDERED
             if (r.mode == 2)
                 q.e = reinterpret_cast<double *>(d_out + o_aux[i]);
             else
@@ -1336,6 +1456,8 @@ extern "C"
             tab[i] = q;
         }
         OCB_CUDA(cudaMemcpyAsync(d, hp, in_bytes, cudaMemcpyHostToDevice, cx.stream));
+        if (n_fit && (rc = k3_fit_samples(reinterpret_cast<const K3FitJob *>(d + o_jobs), n_fit, fit_total, cx.stream)))
+            return rc;
         if ((rc = k2_run_requests(reinterpret_cast<const K2Request *>(d + o_tab), count, ctas, cx.stream)))
             return rc;
         char *hout = hp + in_bytes;
@@ -1354,6 +1476,11 @@ extern "C"
                 memcpy(r.count, hout + o_count[i], (size_t)r.h * sizeof(uint32_t));
                 if (r.mode == 1)
                     memcpy(r.inlier_bits, hout + o_aux[i], (size_t)r.h * words * sizeof(uint32_t));
+                if (r.mode == OCB_REQ_FIT_SCORE_ORDERED)
+                {
+                    memcpy(r.models_out, hout + o_models[i], (size_t)r.h * 18 * sizeof(double));
+                    memcpy(r.degenerate, hout + o_flags[i], r.h);
+                }
             }
         }
         return 0;

@@ -115,6 +115,18 @@ struct K2Request
 uint32_t k2_request_ctas(const K2Request &rq);
 int k2_run_requests(const K2Request *d_requests, size_t n_requests, uint32_t total_ctas, cudaStream_t stream);
 
+// ---- K3 launch interface (fit_models.cu) ---------------------------------------------------------------------
+// One batch of minimal-sample homography fits against one correspondence set (all pointers are device pointers).
+struct K3FitJob
+{
+    const double *c7;        // [n][7] correspondences as given
+    const uint32_t *samples; // [h][4] correspondence indices
+    double *models_out;      // [h][18]
+    uint8_t *degenerate;     // [h] or nullptr
+    uint32_t h, begin;       // begin = index of this job's first hypothesis in the launch
+};
+int k3_fit_samples(const K3FitJob *d_jobs, size_t n_jobs, uint32_t total, cudaStream_t stream);
+
 // ---- PTX helpers: mbarrier + 1-D bulk (TMA) copies -----------------------------------------------------------
 #if defined(__CUDACC__)
 __device__ __forceinline__ uint32_t smem_u32(const void *p)

@@ -45,6 +45,8 @@ def lib():
     L.ocbh_subsample.restype = sz
     L.ocbh_ransac.argtypes = [i32, _f64p, sz, _f64p, _u8p, _f64p, _szp]
     L.ocbh_evaluate.argtypes = [i32, _f64p, dbl, _f64p, sz, _u8p, _f64p]
+    L.ocbh_set_ransac_device_fit.argtypes = [i32]
+    L.ocbh_set_ransac_device_fit.restype = None
     L.ocbh_error.argtypes = [i32, _f64p, _f64p]
     L.ocbh_error.restype = dbl
     L.ocbh_fit.argtypes = [i32, _f64p, sz, _szp, _f64p]
@@ -207,6 +209,11 @@ def ransac(kind, corr):
     stats = dict(iterations=int(st[0]), improvements=int(st[1]), rejected=int(st[2]), degenerate=int(st[3]),
                  scored=int(st[4]), gpu_calls=int(st[5]))
     return float(score[0]), M18, inl[:len(corr)].astype(bool), stats
+
+
+def set_ransac_device_fit(on):
+    """ransac(homography): fit each batch of minimal samples on the device (default) or on the host."""
+    lib().ocbh_set_ransac_device_fit(1 if on else 0)
 
 
 def evaluate(kind, M18, corr, thr=0.0):

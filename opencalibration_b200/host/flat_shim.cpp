@@ -256,6 +256,9 @@ extern "C"
         });
     }
 
+    void ocbh_set_ransac_device_fit(int on) { ocb_host::set_ransac_device_fit(on != 0); }
+    int ocbh_ransac_device_fit() { return ocb_host::ransac_device_fit() ? 1 : 0; }
+
     int ocbh_evaluate(int kind, const double *M18, double thr, const double *corr, size_t n, uint8_t *inliers,
                       double *score)
     {

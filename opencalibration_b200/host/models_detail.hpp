@@ -107,6 +107,24 @@ inline void pack_model(const opencalibration::homography_model &m, double *m18)
         m18[9 + i] = m.homography_inverse.data()[i];
     }
 }
+inline void unpack_model(const double *m18, opencalibration::homography_model &m)
+{
+    for (int i = 0; i < 9; i++)
+    {
+        m.homography.data()[i] = m18[i];
+        m.homography_inverse.data()[i] = m18[9 + i];
+    }
+}
+inline void unpack_model(const double *m18, opencalibration::essential_matrix_model &m)
+{
+    for (int i = 0; i < 9; i++)
+        m.essential_matrix.data()[i] = m18[i];
+}
+inline void unpack_model(const double *m18, opencalibration::fundamental_matrix_model &m)
+{
+    for (int i = 0; i < 9; i++)
+        m.fundamental_matrix.data()[i] = m18[i];
+}
 inline void pack_model(const opencalibration::essential_matrix_model &m, double *m18)
 {
     for (int i = 0; i < 9; i++)

@@ -56,6 +56,10 @@ struct RansacStats
     size_t gpu_calls = 0;
 };
 RansacStats last_ransac_stats();
+// ransac<homography_model>: check, fit and score each batch of minimal samples on the device (default) or fit on the
+// host and score on the device. Both give identical results; the switch exists for A/B tests and timing.
+void set_ransac_device_fit(bool on);
+bool ransac_device_fit();
 
 // Many independent ransac<Model>() runs advanced in lock step (used by the batched LinkStage runner): the result of
 // every job -- model, inliers, returned score -- is what ransac(*matches, *model, *inliers) gives, but each round of

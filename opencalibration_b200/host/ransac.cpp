@@ -18,7 +18,11 @@
 #include "models_detail.hpp"
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cstdio>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <omp.h>
@@ -32,6 +36,11 @@ namespace ocb_host
 namespace
 {
 thread_local RansacStats t_stats;
+// default on; OCB_RANSAC_DEVICE_FIT=0 in the environment selects host fits (A/B timing without rebuilding)
+std::atomic<int> g_device_fit{[] {
+    const char *e = std::getenv("OCB_RANSAC_DEVICE_FIT");
+    return (e && e[0] == '0') ? 0 : 1;
+}()};
 
 template <size_t K> struct HypothesisStream
 {
@@ -155,6 +164,14 @@ RansacStats last_ransac_stats()
 {
     return t_stats;
 }
+void set_ransac_device_fit(bool on)
+{
+    g_device_fit.store(on ? 1 : 0);
+}
+bool ransac_device_fit()
+{
+    return g_device_fit.load() != 0;
+}
 } // namespace ocb_host
 
 namespace opencalibration
@@ -175,6 +192,8 @@ template <typename Model> class RansacRun
     {
         DONE,
         SCORE_BATCH, // request_models(): want x 18, evaluation order -> batch_score, batch_count
+        FIT_SCORE_BATCH, // request_samples(): want x 4 indices -> fitted on the device into batch_m18 / batch_skip,
+                         // then scored like SCORE_BATCH (homography only)
         RESIDUALS,   // request_models(): 1 x 18                      -> residual[N]
         EVALUATE     // request_models(): 1 x 18, index order         -> eval_score, eval_bits
     };
@@ -204,6 +223,9 @@ template <typename Model> class RansacRun
     const uint32_t *order() const { return order32.data(); }
     const double *request_models() const { return request_m18; }
     size_t request_count() const { return request_h; }
+    const uint32_t *request_samples() const { return batch_samples.data(); }
+    double *fitted_models() { return batch_m18.data(); }
+    uint8_t *fitted_degenerate() { return batch_skip.data(); }
 
     Need advance()
     {
@@ -225,9 +247,34 @@ template <typename Model> class RansacRun
                     return Need::EVALUATE;
                 }
                 const size_t want = std::min(batch, MAX_ITERATIONS - i);
-                batch_models.assign(want, model);
                 batch_skip.assign(want, 0);
                 batch_m18.assign(want * 18, 0.0);
+                batch_score.assign(want, 0.0);
+                batch_count.assign(want, 0);
+                batch_size = want;
+                if constexpr (is_homography<Model>)
+                {
+                    if (device_fit)
+                    {
+                        // only the sample stream stays on the host (it is the reference's std:: RNG calls); the
+                        // degeneracy test, the fit and the scoring of the whole batch run on the device
+                        batch_samples.resize(want * K);
+                        for (size_t k = 0; k < want; k++)
+                        {
+                            const std::array<size_t, K> sample = stream->next(i + k);
+                            for (size_t j = 0; j < K; j++)
+                                batch_samples[k * K + j] = static_cast<uint32_t>(sample[j]);
+                        }
+                        stats.gpu_calls++;
+                        stats.scored += want;
+                        b = 0;
+                        request_m18 = nullptr;
+                        request_h = want;
+                        state = State::SCAN;
+                        return Need::FIT_SCORE_BATCH;
+                    }
+                }
+                batch_models.assign(want, model);
                 for (size_t k = 0; k < want; k++)
                 {
                     const std::array<size_t, K> sample = stream->next(i + k);
@@ -242,8 +289,6 @@ template <typename Model> class RansacRun
                     batch_models[k].fit(matches, sample); // ransac.cpp:179
                     pack_model(batch_models[k], &batch_m18[k * 18]);
                 }
-                batch_score.assign(want, 0.0);
-                batch_count.assign(want, 0);
                 stats.gpu_calls++;
                 stats.scored += want;
                 b = 0;
@@ -255,7 +300,7 @@ template <typename Model> class RansacRun
 
             case State::SCAN: {
                 bool requested = false;
-                for (; b < batch_models.size() && i < probability_iterations; b++, i++)
+                for (; b < batch_size && i < probability_iterations; b++, i++)
                 {
                     if (batch_skip[b])
                     {
@@ -265,7 +310,10 @@ template <typename Model> class RansacRun
                     if (!(batch_score[b] > best_score))
                         continue; // rejected early or not, nothing changes (ransac.cpp:204-207)
                     // would-be improver: replay ransac.cpp:183-203 on its residuals
-                    model = batch_models[b];
+                    if (batch_models.empty())
+                        unpack_model(&batch_m18[b * 18], model); // fitted on the device
+                    else
+                        model = batch_models[b];
                     stats.gpu_calls++;
                     request_m18 = &batch_m18[b * 18];
                     request_h = 1;
@@ -277,7 +325,7 @@ template <typename Model> class RansacRun
                     state = State::AFTER_RESIDUALS;
                     return Need::RESIDUALS;
                 }
-                if (b >= batch_models.size())
+                if (b >= batch_size)
                     batch = std::min<size_t>(batch * 2, 2048);
                 state = State::START_BATCH;
                 break;
@@ -436,8 +484,11 @@ template <typename Model> class RansacRun
     size_t batch = 32; // grows geometrically: the adaptive stop usually fires within the first batches
     size_t b = 0;      // cursor in the current batch
     size_t lo_round = 0;
-    std::vector<Model> batch_models;
-    std::vector<char> batch_skip;
+    const bool device_fit = is_homography<Model> && ransac_device_fit();
+    size_t batch_size = 0;
+    std::vector<Model> batch_models; // host fits only; empty when the batch was fitted on the device
+    std::vector<uint8_t> batch_skip;
+    std::vector<uint32_t> batch_samples;
     std::vector<double> batch_m18;
     std::vector<bool> candidate_inliers;
     double eval_m18[18];
@@ -464,6 +515,11 @@ double ransac(const std::vector<correspondence> &matches, Model &model, std::vec
         case Need::SCORE_BATCH:
             gpu_score_in_order(run.kind, run.request_models(), run.request_count(), matches, run.thr, run.order(),
                                run.batch_score.data(), run.batch_count.data());
+            break;
+        case Need::FIT_SCORE_BATCH:
+            gpu_check(ocb_fit_score_bound(run.request_samples(), run.request_count(), run.thr, run.fitted_models(),
+                                          run.fitted_degenerate(), run.batch_score.data(), run.batch_count.data()),
+                      "ocb_fit_score_bound");
             break;
         case Need::RESIDUALS:
             gpu_residuals(run.kind, run.request_models(), matches, run.residual.data());
@@ -515,8 +571,16 @@ template <typename Model> void ransac_batch(std::vector<RansacJob<Model>> &jobs,
     detail::gpu_check(ocb_corr_bind_batch(sets.data(), sets.size()), "ocb_corr_bind_batch");
     std::vector<Need> need(n_jobs, Need::DONE);
     std::vector<ocb_score_request> requests;
+    static const bool profile = std::getenv("OCB_RANSAC_PROFILE") != nullptr;
+    double t_host = 0, t_gpu = 0;
+    size_t rounds = 0, n_req[5] = {0, 0, 0, 0, 0};
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto secs = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+        return std::chrono::duration<double>(b - a).count();
+    };
     while (!active.empty())
     {
+        const auto t0 = now();
 #pragma omp parallel for schedule(dynamic, 1) num_threads(threads)
         for (size_t a = 0; a < active.size(); a++)
         {
@@ -553,6 +617,9 @@ template <typename Model> void ransac_batch(std::vector<RansacJob<Model>> &jobs,
             q.thr = r.thr;
             if (need[j] == Need::SCORE_BATCH)
                 q.mode = OCB_REQ_SCORE_ORDERED, q.score = r.batch_score.data(), q.count = r.batch_count.data();
+            else if (need[j] == Need::FIT_SCORE_BATCH)
+                q.mode = OCB_REQ_FIT_SCORE_ORDERED, q.samples = r.request_samples(), q.models_out = r.fitted_models(),
+                q.degenerate = r.fitted_degenerate(), q.score = r.batch_score.data(), q.count = r.batch_count.data();
             else if (need[j] == Need::RESIDUALS)
                 q.mode = OCB_REQ_RESIDUALS, q.residuals = r.residual.data();
             else
@@ -560,10 +627,22 @@ template <typename Model> void ransac_batch(std::vector<RansacJob<Model>> &jobs,
                 q.inlier_bits = r.eval_bits.data();
             requests.push_back(q);
         }
+        const auto t1 = now();
         if (!requests.empty())
             detail::gpu_check(ocb_score_requests(requests.data(), requests.size()), "ocb_score_requests");
+        if (profile)
+        {
+            t_host += secs(t0, t1), t_gpu += secs(t1, now()), rounds++;
+            for (const ocb_score_request &q : requests)
+                n_req[q.mode]++;
+        }
         active.swap(still);
     }
+    if (profile)
+        std::fprintf(stderr,
+                     "[ocb ransac_batch] jobs %zu threads %d rounds %zu host %.3f ms gpu %.3f ms requests: score %zu "
+                     "evaluate %zu residuals %zu fit+score %zu\n",
+                     n_jobs, threads, rounds, t_host * 1e3, t_gpu * 1e3, n_req[0], n_req[1], n_req[2], n_req[3]);
 }
 template void ransac_batch(std::vector<RansacJob<opencalibration::homography_model>> &, int);
 template void ransac_batch(std::vector<RansacJob<opencalibration::fundamental_matrix_model>> &, int);

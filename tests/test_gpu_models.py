@@ -232,3 +232,63 @@ def test_ransac_batch_equals_single_runs(gpu, hostlib, oracle):
             assert s == s1 and np.array_equal(inl, inl1[:len(c)])
             assert np.array_equal(M[:n], M1[:n], equal_nan=True)
             assert st["iterations"] == st1["iterations"] and st["improvements"] == st1["improvements"]
+
+
+def test_device_fit_bit_exact(gpu, oracle):
+    # K3: checkSampleDegeneracy + fit on the device (homography_model.cpp:19-50,120-136) against the oracle's fit:
+    # identical models (H and H^-1), identical degeneracy verdicts; repeated points, collinear triples, rank-deficient
+    # systems and non-finite coordinates included
+    corr, _ = oracle.scene_homography(300, 200, 17)
+    eo, samples = oracle.hypothesis_stream(0, corr, 400)
+    samples = [list(s) for s in samples]
+    samples += [[5, 5, 6, 7], [1, 2, 3, 1]]                       # repeated correspondence
+    near, _ = oracle.scene_homography_near_degenerate()
+    corr2 = np.concatenate([corr, near])
+    base = len(corr)
+    rng = np.random.default_rng(3)
+    for _ in range(60):
+        samples.append(list(base + rng.choice(len(near), 4, replace=False)))
+    line = np.zeros((4, 7))                                        # three collinear source points
+    line[:, 0:3] = [(0.1, 0.1, 1), (0.2, 0.2, 1), (0.3, 0.3, 1), (0.5, -0.2, 1)]
+    line[:, 3:6] = [(0.1, 0.2, 1), (0.25, 0.2, 1), (0.3, 0.35, 1), (0.5, -0.1, 1)]
+    bad = corr[:4].copy()
+    bad[0, 2] = 0.0                                                # z == 0 -> inf / nan coordinates
+    bad[1, 3] = np.nan
+    corr2 = np.concatenate([corr2, line, bad])
+    o = len(corr2) - 8
+    samples += [[o, o + 1, o + 2, o + 3], [o + 3, o + 2, o + 1, o], [o + 4, o + 5, o + 6, o + 7], [o + 4, 1, 2, 3],
+                [o + 5, 1, 2, 3]]
+    samples = np.array(samples, np.uint32)
+    models, deg = gpu.fit_homography(corr2, samples)
+    n_deg = 0
+    for s, m, d in zip(samples, models, deg):
+        want_deg = bool(oracle.check_sample_degeneracy_h(corr2, s.astype(np.uintp)))
+        assert d == want_deg
+        if want_deg:
+            n_deg += 1
+            assert np.isnan(m).all()
+        else:
+            assert np.array_equal(m, oracle.fit(0, corr2, s.astype(np.uintp)), equal_nan=True)
+    assert n_deg >= 2 and n_deg < len(samples) // 2
+
+
+def test_ransac_device_fit_equals_host_fit(gpu, hostlib, oracle):
+    # the same run with the batch fitted on the device (default) and on the host: identical in every output
+    scenes = [oracle.scene_homography(140, 60, 42)[0], oracle.scene_homography(40, 160, 7)[0],
+              oracle.scene_homography_near_degenerate()[0], oracle.scene_homography(600, 5400, 4)[0]]
+    try:
+        for corr in scenes:
+            hostlib.set_ransac_device_fit(True)
+            a = hostlib.ransac(0, corr)
+            hostlib.set_ransac_device_fit(False)
+            b = hostlib.ransac(0, corr)
+            assert a[0] == b[0] and np.array_equal(a[1], b[1], equal_nan=True) and np.array_equal(a[2], b[2])
+            assert a[3]["iterations"] == b[3]["iterations"] and a[3]["degenerate"] == b[3]["degenerate"]
+        hostlib.set_ransac_device_fit(False)
+        bh = hostlib.ransac_batch(0, scenes, threads=2)
+        hostlib.set_ransac_device_fit(True)
+        bd = hostlib.ransac_batch(0, scenes, threads=2)
+        for x, y in zip(bh, bd):
+            assert x[0] == y[0] and np.array_equal(x[1], y[1], equal_nan=True) and np.array_equal(x[2], y[2])
+    finally:
+        hostlib.set_ransac_device_fit(True)
