@@ -14,7 +14,7 @@ HOST = os.path.join(PKG, "host")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-Wall", "-shared"]
 CUDA_SOURCES = ["hamming_top2.cu", "hamming_lists.cu", "score_models.cu", "fit_models.cu", "pipe_probe.cu", "ocb_capi.cu"]
-HOST_SOURCES = ["linalg.cpp", "models.cpp", "homography_decompose.cpp", "distort_keypoints.cpp", "link_batch.cpp", "match_features.cpp", "guided_match.cpp", "ransac.cpp", "flat_shim.cpp"]
+HOST_SOURCES = ["linalg.cpp", "models.cpp", "homography_decompose.cpp", "distort_keypoints.cpp", "link_batch.cpp", "match_features.cpp", "guided_match.cpp", "ransac.cpp", "graph_wire.cpp", "graph_wire_capi.cpp", "flat_shim.cpp"]
 
 
 def _newer(target, deps):
@@ -50,7 +50,8 @@ def build_host(force=False, verbose=False):
     if not srcs:
         return None
     deps = srcs + [os.path.join(HOST, f) for f in os.listdir(HOST) if f.endswith(".hpp")] + \
-        [os.path.join(ROOT, "include", "ocb.h")]
+        [os.path.join(HOST, "pow10_table.inc"), os.path.join(ROOT, "include", "ocb.h"),
+         os.path.join(ROOT, "include", "ocb_wire.h")]
     if force or _newer(out, deps):
         _run(["g++", "-std=c++17", "-O3", "-fPIC", "-Wall", "-Wextra", "-ffp-contract=off", "-fopenmp", "-shared",
               "-I", os.path.join(ROOT, "include"), "-I", HOST, "-o", out] + srcs +
