@@ -3,8 +3,8 @@
 // Replaces, for a whole batch of RANSAC hypotheses, homography_model::checkSampleDegeneracy
 // (reference src/model_inliers/homography_model.cpp:120-136) and homography_model::fit (:19-50): the 4-point DLT
 // system with the h33 == 1 row (:26-41), P.fullPivLu().solve(rhs) (:44), the renormalisation by H(2,2) (:48) and
-// homography.inverse() (:49); and, for the local-optimisation loop of ransac<> (ransac.cpp:224-245),
-// homography_model::fitInliers (:52-87: the same system over all inliers, (2m+1) x 9) followed by evaluate.
+// homography.inverse() (:49). The all-inlier refit of the local-optimisation loop (fitInliers, :52-87, a
+// (2m+1) x 9 system) stays on the host (host/models.cpp): it runs a handful of times per RANSAC run.
 //
 // Exactness: Eigen is not under /root/reference (un-vendored find_package dependency), so the algorithms are the
 // published Eigen 3.4 ones as restated in host/linalg.cpp (FullPivLU with complete pivoting, cofactor inverse for
@@ -16,11 +16,6 @@
 //   * minimal-sample fits (k3_fit_samples_kernel): one THREAD per hypothesis. The 9x9 system lives in shared
 //     memory, element-major ([81][32 threads]), so the data-dependent pivot indexing costs no local-memory traffic
 //     and no bank conflicts (every thread of the warp touches its own bank column).
-//   * all-inlier refits (k3_refine_kernel): one CTA per RANSAC run. The (2m+1) x 9 system sits column-major in a
-//     global scratch slab (L2 resident); each of the 9 elimination steps is a block-wide pivot search (complete
-//     pivoting with the sequential scan's tie rule: largest magnitude, then smallest column, then smallest row) and
-//     a block-wide rank-1 update; the 9x9 triangular solves are done by one thread. The CTA then evaluates the
-//     refitted model in index order (sequential MSAC sum) and repeats while the score improves, like the reference.
 #include "ocb_internal.cuh"
 
 #include <cfloat>
