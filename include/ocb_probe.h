@@ -3,6 +3,7 @@
  * Not part of the drop-in boundary. */
 #ifndef OCB_PROBE_H
 #define OCB_PROBE_H
+#include <stdint.h>
 #ifdef __cplusplus
 extern "C"
 {
@@ -28,6 +29,12 @@ extern "C"
     };
     /* Runs the probes on the current device; out must hold OCB_PROBE_COUNT doubles. 0 or a negative code. */
     int ocb_probe_pipes(double *out, int n_out);
+
+    /* Checks the shared-reciprocal division and the straight-line square root that K2 uses (csrc/exact_math.cuh)
+     * against div.rn.f64 / sqrt.rn.f64 on the device, on n pseudo-random operand triples whose exponents spread over
+     * 2^-exponent_spread .. 2^+exponent_spread. counts5 = {divisions compared, divisions that differ, square roots
+     * compared, square roots that differ, divisions outside the guarded range (not compared)}. 0 or a negative code. */
+    int ocb_probe_exact_math(uint64_t seed, uint64_t n, uint32_t exponent_spread, uint64_t *counts5);
 #ifdef __cplusplus
 }
 #endif

@@ -71,6 +71,9 @@ def lib():
     if hasattr(L, "ocb_probe_pipes"):
         L.ocb_probe_pipes.restype = i32
         L.ocb_probe_pipes.argtypes = [vp, i32]
+    if hasattr(L, "ocb_probe_exact_math"):
+        L.ocb_probe_exact_math.restype = i32
+        L.ocb_probe_exact_math.argtypes = [u64, u64, C.c_uint32, vp]
     _lib = L
     return L
 
@@ -116,6 +119,13 @@ def kernel_launches():
 
 
 # ---- K1, host buffers (the call a user of the C ABI makes) ----
+def probe_exact_math(seed, n, exponent_spread):
+    """include/ocb_probe.h: {divisions compared, differing, square roots compared, differing, divisions out of range}."""
+    counts = np.zeros(5, dtype=np.uint64)
+    check(lib().ocb_probe_exact_math(int(seed), int(n), int(exponent_spread), _ptr(counts)))
+    return counts
+
+
 def match_top2(q, c, cross_check=False, out=None, col_out=None):
     q, c = _rows(q), _rows(c)
     n1, n2 = len(q), len(c)

@@ -261,6 +261,8 @@ __global__ void __launch_bounds__(K1_THREADS, MINB)
     __shared__ alignas(128) uint4 tile[K1_STAGES][K1_TILE_C * 4];
     __shared__ alignas(8) uint64_t full_bar[K1_STAGES];
     __shared__ uint32_t ticket[2];
+    // cross-check: per-warp column minima of a tile, combined by the CTA after the tile (double-buffered)
+    __shared__ uint32_t colmin[COL ? 2 : 1][K1_THREADS / 32][COL ? K1_TILE_C : 1];
 
     const uint32_t tid = threadIdx.x;
     // <= K1_INLINE problems travel in the kernel parameters (no table upload on the single-pair path)
@@ -422,13 +424,7 @@ __global__ void __launch_bounds__(K1_THREADS, MINB)
 #pragma unroll
                 for (int j = 1; j < Q; j++)
                     cm = min(cm, v[j]);
-                cm = __reduce_min_sync(0xFFFFFFFFu, cm);
-                if ((tid & 31) == 0)
-                {
-                    const unsigned long long key =
-                        ((unsigned long long)(cm >> K1_SHIFT) << 32) | (unsigned long long)(q_base + (cm & K1_SLOT_MASK));
-                    red_max_u64_global(&col64[c_begin + k0 + cc], ~key);
-                }
+                colmin[t & 1][tid >> 5][cc] = __reduce_min_sync(0xFFFFFFFFu, cm); // every lane stores the same word
             }
         }
         if constexpr (PFX)
@@ -439,6 +435,22 @@ __global__ void __launch_bounds__(K1_THREADS, MINB)
         __syncthreads(); // every warp is done with stage s (and, prefix form, tile t+1 is mapped)
         if (tid == 0 && t + K1_STAGES < ntiles)
             issue(t + K1_STAGES);
+        if constexpr (COL)
+        {
+            // one atomic per candidate and CTA: thread k combines the warps' minima of candidate k0 + k. The other
+            // warps are already in tile t+1 (other colmin buffer); buffer t&1 is written again in tile t+2, i.e.
+            // after the next __syncthreads, which this thread reaches after this flush.
+            if (tid < rows)
+            {
+                uint32_t cm = colmin[t & 1][0][tid];
+#pragma unroll
+                for (int wp = 1; wp < K1_THREADS / 32; wp++)
+                    cm = min(cm, colmin[t & 1][wp][tid]);
+                const unsigned long long key =
+                    ((unsigned long long)(cm >> K1_SHIFT) << 32) | (unsigned long long)(q_base + (cm & K1_SLOT_MASK));
+                red_max_u64_global(&col64[c_begin + k0 + tid], ~key);
+            }
+        }
     }
 
     if constexpr (BF)

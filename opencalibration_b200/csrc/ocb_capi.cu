@@ -394,6 +394,8 @@ extern "C"
             o.k1_items_per_sm = (int)value;
         else if (!strcmp(key, "k2_variant"))
             o.k2_variant = (int)value;
+        else if (!strcmp(key, "k2_hg"))
+            o.k2_hg = (int)value;
         else if (!strcmp(key, "k1_update"))
             o.k1_update = (int)value;
         else if (!strcmp(key, "k1_bf_rows"))
@@ -414,6 +416,8 @@ extern "C"
             return o.k1_items_per_sm;
         if (!strcmp(key, "k2_variant"))
             return o.k2_variant;
+        if (!strcmp(key, "k2_hg"))
+            return o.k2_hg;
         if (!strcmp(key, "k1_update"))
             return o.k1_update;
         if (!strcmp(key, "k1_bf_rows"))

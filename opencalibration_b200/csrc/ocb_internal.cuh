@@ -36,7 +36,8 @@ struct Options
 {
     int k1_variant = 0;       // 0 = default (see hamming_top2.cu variant table)
     int k1_items_per_sm = 16; // target work items per SM when splitting the candidate axis
-    int k2_variant = 0;
+    int k2_variant = 0;       // 0 = default (one hypothesis in flight per thread), 1 = two
+    int k2_hg = 0;            // hypotheses per CTA of k2_score; 0 = balance the SMs (k2_pick_group)
     int k1_update = 0;      // 0 = choose by candidate-run length, 1 = vote-and-skip, 2 = branch-free
     int k1_bf_rows = 2048;  // runs shorter than this use the branch-free update
 };
@@ -113,6 +114,7 @@ struct K2Request
     int32_t kind, mode; // mode 0 = score in evaluation order, 1 = evaluate (index order + bits), 2 = residuals
 };
 uint32_t k2_request_ctas(const K2Request &rq);
+uint32_t k2_pick_group(size_t h, int sms, int resident);
 int k2_run_requests(const K2Request *d_requests, size_t n_requests, uint32_t total_ctas, cudaStream_t stream);
 
 // ---- K3 launch interface (fit_models.cu) ---------------------------------------------------------------------
@@ -145,6 +147,10 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                  : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
 {

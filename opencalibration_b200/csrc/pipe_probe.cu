@@ -2,6 +2,7 @@
 // One CTA of 1024 threads per SM runs `iters` rounds of 8 independent dependent chains of one opcode
 // (inline PTX so ptxas keeps them); rate = lane-ops / SM clock cycles / SM, cycles from clock64().
 #include "ocb_internal.cuh"
+#include "exact_math.cuh"
 
 #include "../../include/ocb_probe.h"
 
@@ -131,10 +132,92 @@ template <int OP> int run_probe(int sms, uint32_t iters, uint32_t *d_sink, long 
     cudaEventDestroy(e1);
     return 0;
 }
+
+// ---- exact_math.cuh against the IEEE intrinsics ---------------------------------------------------------------
+__device__ __forceinline__ uint64_t mix64(uint64_t x)
+{
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+// random sign and mantissa, exponent uniform in [1023 - spread, 1023 + spread]
+__device__ __forceinline__ double random_double(uint64_t bits, uint32_t spread)
+{
+    const uint64_t mant = bits & 0x000FFFFFFFFFFFFFull;
+    const uint64_t sign = bits & 0x8000000000000000ull;
+    const uint32_t e = 1023u - spread + (uint32_t)((bits >> 52) & 0x7FFu) % (2u * spread + 1u);
+    return __longlong_as_double((long long)(sign | ((uint64_t)e << 52) | mant));
+}
+// counts[0..1] = divisions tested / differing, [2..3] = square roots tested / differing,
+// [4] = divisions whose operands fell outside mid_range (not compared: callers use __ddiv_rn there)
+__global__ void __launch_bounds__(256) exact_math_kernel(uint64_t seed, uint64_t n, uint32_t spread, unsigned long long *counts)
+{
+    unsigned long long c[5] = {0, 0, 0, 0, 0};
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+    {
+        const uint64_t a = mix64(seed + 3 * i), b = mix64(seed + 3 * i + 1), d = mix64(seed + 3 * i + 2);
+        const double z = random_double(a, spread);
+        const double x = random_double(b, spread);
+        // a second numerator close to a multiple of z makes quotients that sit next to rounding boundaries
+        const double y = __dmul_rn(z, (double)(1 + (d & 0xFFFFF))) + ((d >> 40) & 1 ? 0.0 : __dmul_rn(z, 0.5));
+        const double r = rcp_refined(z);
+        const double nums[2] = {x, y};
+#pragma unroll
+        for (int k = 0; k < 2; k++)
+        {
+            const double q = quot_shared(nums[k], z, r);
+            if (mid_range(nums[k]) && mid_range(z) && mid_range(q))
+            {
+                c[0]++;
+                c[1] += __double_as_longlong(q) != __double_as_longlong(__ddiv_rn(nums[k], z));
+            }
+            else
+                c[4]++;
+        }
+        const double s = fabs(x);
+        if (mid_range(s))
+        {
+            c[2]++;
+            c[3] += __double_as_longlong(sqrt_fast(s)) != __double_as_longlong(__dsqrt_rn(s));
+        }
+        // squares of representable values and their neighbours: exact and half-way cases of the square root
+        const double t = __dmul_rn(fabs(z), fabs(z));
+        const double tn = __longlong_as_double(__double_as_longlong(t) + (long long)(d & 3) - 1);
+        if (mid_range(tn))
+        {
+            c[2]++;
+            c[3] += __double_as_longlong(sqrt_fast(tn)) != __double_as_longlong(__dsqrt_rn(tn));
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 5; k++)
+        if (c[k])
+            atomicAdd(&counts[k], c[k]);
+}
 } // namespace
 } // namespace ocb
 
 using namespace ocb;
+
+extern "C" int ocb_probe_exact_math(uint64_t seed, uint64_t n, uint32_t exponent_spread, uint64_t *counts5)
+{
+    if (!counts5 || exponent_spread == 0 || exponent_spread > 1000)
+        return fail_invalid("counts5 must hold 5 values; exponent_spread in [1, 1000]");
+    unsigned long long *d_counts = nullptr;
+    OCB_CUDA(cudaMalloc(&d_counts, 5 * sizeof(unsigned long long)));
+    OCB_CUDA(cudaMemset(d_counts, 0, 5 * sizeof(unsigned long long)));
+    int dev = 0;
+    OCB_CUDA(cudaGetDevice(&dev));
+    exact_math_kernel<<<sm_count(dev) * 8, 256>>>(seed, n, exponent_spread, d_counts);
+    count_launch();
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess)
+        e = cudaMemcpy(counts5, d_counts, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    cudaFree(d_counts);
+    OCB_CUDA(e);
+    return 0;
+}
 
 extern "C" int ocb_probe_pipes(double *out, int n_out)
 {

@@ -12,24 +12,27 @@
 // Mapping: a CTA owns K2_HG hypotheses (their matrices sit in shared memory and are read as broadcasts).
 // Warps 0..6 ("compute") each take 32 consecutive evaluation positions per round and, for every hypothesis
 // of the group, compute the residual, ballot the inlier mask and park the MSAC contribution in a
-// double-buffered shared-memory slab. Warp 7 ("sum") runs one round behind: lane g walks hypothesis g's
-// masks and adds the parked contributions of the inliers in order. Adding nothing for an outlier is
-// exactly what the reference does, so only set bits are visited.
+// double-buffered shared-memory slab (+0.0 for an outlier). Warp 7 ("sum") runs one round behind: lane g adds
+// hypothesis g's rows in order, 32 positions at a time (words without an inlier are skipped). The reference adds
+// nothing for an outlier; adding +0.0 to a score that is never -0.0 gives the same bits, and it turns the sum into
+// straight chains of DADDs whose loads do not depend on the data (a loop over the set bits of the masks made the
+// sum warp the critical path). The warps of a CTA synchronise through mbarriers on the two slabs only.
 #include "ocb_internal.cuh"
+#include "exact_math.cuh"
 
 #include <cfloat>
 
 namespace ocb
 {
 
-constexpr int K2_HG = 8;          // hypotheses per CTA
+constexpr int K2_HG = 8;          // hypotheses per CTA (upper bound; k2_score picks 4..8 per launch to balance the SMs)
 constexpr int K2_CW = 7;          // compute warps
 constexpr int K2_TP = K2_CW * 32; // evaluation positions per round
 constexpr int K2_THREADS = (K2_CW + 1) * 32;
 
-// homography_model::error (homography_model.cpp:89-97) on pre-divided coordinates.
-// M = [H (9, column-major) | H^-1 (9)].
-__device__ __forceinline__ double h_residual(const double *__restrict__ M, double x1, double y1, double x2, double y2)
+// homography_model::error (homography_model.cpp:89-97) on pre-divided coordinates, plain IEEE intrinsics.
+// M = [H (9, column-major) | H^-1 (9)]. Out of line: only reached when residual_fast's range test fails.
+__device__ __noinline__ double h_residual_ieee(const double *__restrict__ M, double x1, double y1, double x2, double y2)
 {
     const double px = __dadd_rn(__dadd_rn(__dmul_rn(M[0], x1), __dmul_rn(M[3], y1)), M[6]);
     const double py = __dadd_rn(__dadd_rn(__dmul_rn(M[1], x1), __dmul_rn(M[4], y1)), M[7]);
@@ -47,8 +50,8 @@ __device__ __forceinline__ double h_residual(const double *__restrict__ M, doubl
 }
 
 // essential_matrix_model::error == fundamental_matrix_model::error
-// (essential_matrix_model.cpp:112-123, fundamental_matrix_model.cpp:110-121).
-__device__ __forceinline__ double epi_residual(const double *__restrict__ E, double x1, double y1, double x2, double y2)
+// (essential_matrix_model.cpp:112-123, fundamental_matrix_model.cpp:110-121), plain IEEE intrinsics.
+__device__ __noinline__ double epi_residual_ieee(const double *__restrict__ E, double x1, double y1, double x2, double y2)
 {
     const double b0 = __dadd_rn(__dadd_rn(__dmul_rn(x2, E[0]), __dmul_rn(y2, E[1])), E[2]);
     const double b1 = __dadd_rn(__dadd_rn(__dmul_rn(x2, E[3]), __dmul_rn(y2, E[4])), E[5]);
@@ -66,9 +69,69 @@ __device__ __forceinline__ double epi_residual(const double *__restrict__ E, dou
 template <int KIND> __device__ __forceinline__ double residual(const double *__restrict__ M, double x1, double y1, double x2, double y2)
 {
     if constexpr (KIND == OCB_MODEL_HOMOGRAPHY)
-        return h_residual(M, x1, y1, x2, y2);
+        return h_residual_ieee(M, x1, y1, x2, y2);
     else
-        return epi_residual(M, x1, y1, x2, y2);
+        return epi_residual_ieee(M, x1, y1, x2, y2);
+}
+
+// The same residuals as straight-line code (exact_math.cuh): x/z and y/z share one refined reciprocal and nothing
+// calls out of line, so the divisions and the square root of one residual (and of the next hypothesis) overlap in
+// the FP64 pipe. `rng` (see range_key) ends >= RANGE_OK when an operand left the range in which the shared-reciprocal
+// forms are equal to div.rn / sqrt.rn; the caller then recomputes with residual<KIND>().
+__device__ __forceinline__ double h_residual_fast(const double *__restrict__ M, double x1, double y1, double x2, double y2,
+                                                  uint32_t &rng)
+{
+    const double px = __dadd_rn(__dadd_rn(__dmul_rn(M[0], x1), __dmul_rn(M[3], y1)), M[6]);
+    const double py = __dadd_rn(__dadd_rn(__dmul_rn(M[1], x1), __dmul_rn(M[4], y1)), M[7]);
+    const double pz = __dadd_rn(__dadd_rn(__dmul_rn(M[2], x1), __dmul_rn(M[5], y1)), M[8]);
+    const double qx = __dadd_rn(__dadd_rn(__dmul_rn(M[9], x2), __dmul_rn(M[12], y2)), M[15]);
+    const double qy = __dadd_rn(__dadd_rn(__dmul_rn(M[10], x2), __dmul_rn(M[13], y2)), M[16]);
+    const double qz = __dadd_rn(__dadd_rn(__dmul_rn(M[11], x2), __dmul_rn(M[14], y2)), M[17]);
+    const double rp = rcp_refined(pz), rq = rcp_refined(qz);
+    const double ax = quot_shared(px, pz, rp), ay = quot_shared(py, pz, rp);
+    const double bx = quot_shared(qx, qz, rq), by = quot_shared(qy, qz, rq);
+    const double dx = __dsub_rn(ax, x2), dy = __dsub_rn(ay, y2);
+    const double ex = __dsub_rn(bx, x1), ey = __dsub_rn(by, y1);
+    const double fwd = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+    const double bwd = __dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey));
+    const double a = __dmul_rn(__dadd_rn(fwd, bwd), 0.5);
+    rng = max(max(max(range_key(pz), range_key(qz)), max(range_key(px), range_key(py))),
+              max(max(range_key(qx), range_key(qy)), max(range_key(ax), range_key(ay))));
+    // a >= +0 or NaN: mid_range implies sqrt_fast_ok. An exact fit (a == 0: noise-free scenes) stays in line:
+    // sqrt(+0) = +0, and quot_shared(+0, thr, r) is +0 / thr exactly.
+    const bool zero = is_pos_zero(a);
+    rng = max(max(rng, zero ? 0u : range_key(a)), max(range_key(bx), range_key(by)));
+    return zero ? 0.0 : sqrt_fast(a);
+}
+
+__device__ __forceinline__ double epi_residual_fast(const double *__restrict__ E, double x1, double y1, double x2, double y2,
+                                                    uint32_t &rng)
+{
+    const double b0 = __dadd_rn(__dadd_rn(__dmul_rn(x2, E[0]), __dmul_rn(y2, E[1])), E[2]);
+    const double b1 = __dadd_rn(__dadd_rn(__dmul_rn(x2, E[3]), __dmul_rn(y2, E[4])), E[5]);
+    const double b2 = __dadd_rn(__dadd_rn(__dmul_rn(x2, E[6]), __dmul_rn(y2, E[7])), E[8]);
+    const double r = __dadd_rn(__dadd_rn(__dmul_rn(b0, x1), __dmul_rn(b1, y1)), b2);
+    const double a0 = __dadd_rn(__dadd_rn(__dmul_rn(E[0], x1), __dmul_rn(E[3], y1)), E[6]);
+    const double a1 = __dadd_rn(__dadd_rn(__dmul_rn(E[1], x1), __dmul_rn(E[4], y1)), E[7]);
+    const double denom = __dadd_rn(
+        __dadd_rn(__dadd_rn(__dmul_rn(a0, a0), __dmul_rn(a1, a1)), __dmul_rn(b0, b0)), __dmul_rn(b1, b1));
+    const double rr = __dmul_rn(r, r);
+    const double q = quot_shared(rr, denom, rcp_refined(denom));
+    // rr, denom, q >= 0 or NaN. denom < 1e-20 (DBL_MAX in the reference) is decided by the out-of-line form.
+    // r == 0 exactly (rr = q = +0) stays in line like an exact homography fit.
+    const bool zero = is_pos_zero(rr);
+    rng = max(max(zero ? 0u : range_key(rr), range_key(denom)), max(zero ? 0u : range_key(q), denom < 1e-20 ? RANGE_OK : 0u));
+    return zero ? 0.0 : sqrt_fast(q);
+}
+
+template <int KIND>
+__device__ __forceinline__ double residual_fast(const double *__restrict__ M, double x1, double y1, double x2, double y2,
+                                                uint32_t &rng)
+{
+    if constexpr (KIND == OCB_MODEL_HOMOGRAPHY)
+        return h_residual_fast(M, x1, y1, x2, y2, rng);
+    else
+        return epi_residual_fast(M, x1, y1, x2, y2, rng);
 }
 
 // measurement / measurement.z for both views; NaN when z/z != 1 (z zero, infinite or NaN), which is what the
@@ -101,80 +164,159 @@ __global__ void __launch_bounds__(256)
         pos[p] = idx;
 }
 
-template <int KIND>
-__global__ void __launch_bounds__(K2_THREADS)
-    k2_score_kernel(const double *__restrict__ models, uint32_t h, const double4 *__restrict__ corr4, uint32_t n,
-                    double thr, double *__restrict__ score, uint32_t *__restrict__ count,
-                    uint32_t *__restrict__ bits_pos, uint32_t words)
+struct K2Shared
 {
-    __shared__ double M[K2_HG][18];
-    __shared__ double contrib[2][K2_HG][K2_TP];
-    __shared__ uint32_t mask[2][K2_HG][K2_CW + 1];
+    double M[K2_HG][18];
+    double contrib[2][K2_HG][K2_TP + 2]; // +2: the 8 rows the sum warp reads side by side fall in different banks
+    uint32_t mask[2][K2_HG][K2_CW + 1];
+    alignas(8) uint64_t full_bar[2];  // slab b holds a complete round (K2_CW arrivals, one per compute warp)
+    alignas(8) uint64_t empty_bar[2]; // the sum warp is done with slab b (1 arrival)
+};
 
+// The scoring loop of one CTA: hypotheses [h0, h0 + nh) of `models` against n evaluation positions.
+// Correspondences come either prepared (corr4: [n] pre-divided, already in evaluation order) or raw (c7: [n][7] rows as
+// given, read through `order` when it is set and normalised on the fly). W = hypotheses in flight per thread.
+// Compute warps and the sum warp meet only through the two mbarrier pairs of the double-buffered slab (no CTA-wide
+// barrier per round): a compute warp may run up to two rounds ahead of the slowest one.
+template <int KIND, int W>
+__device__ __forceinline__ void score_group(K2Shared &sm, const double *__restrict__ models, uint32_t h0, uint32_t nh,
+                                            const double4 *__restrict__ corr4, const double *__restrict__ c7,
+                                            const uint32_t *__restrict__ order, uint32_t n, double thr,
+                                            double *__restrict__ score, uint32_t *__restrict__ count,
+                                            uint32_t *__restrict__ bits_pos, uint32_t words)
+{
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const uint32_t h0 = blockIdx.x * K2_HG;
-    const uint32_t nh = min((uint32_t)K2_HG, h - h0);
     for (uint32_t i = tid; i < nh * 18; i += K2_THREADS)
-        M[i / 18][i % 18] = models[(size_t)h0 * 18 + i];
+        sm.M[i / 18][i % 18] = models[(size_t)h0 * 18 + i];
+    if (tid == 0)
+    {
+#pragma unroll
+        for (int b = 0; b < 2; b++)
+        {
+            mbar_init(&sm.full_bar[b], K2_CW);
+            mbar_init(&sm.empty_bar[b], 1);
+        }
+        mbar_fence_init();
+    }
     __syncthreads();
 
     const uint32_t rounds = (n + K2_TP - 1) / K2_TP;
-    double s = 0.0;
-    uint32_t cnt = 0;
-    for (uint32_t r = 0; r <= rounds; r++)
+    if (warp < K2_CW)
     {
-        if (warp < K2_CW)
+        const double r_thr = rcp_refined(thr); // shared by every MSAC contribution of this thread
+        const uint32_t thr_rng = range_key(thr);
+        auto load_corr = [&](uint32_t r) {
+            const uint32_t p = r * K2_TP + warp * 32 + lane;
+            const uint32_t pc = p < n ? p : n - 1; // lanes past the end recompute the last position (never inliers)
+            if (corr4)
+                return corr4[pc];
+            return normalise_corr(c7 + (size_t)(order ? order[pc] : pc) * 7);
+        };
+        double4 c_next = rounds ? load_corr(0) : make_double4(0, 0, 0, 0);
+        for (uint32_t r = 0; r < rounds; r++)
         {
-            if (r < rounds)
+            const uint32_t b = r & 1;
+            const uint32_t p = r * K2_TP + warp * 32 + lane;
+            const bool valid = p < n;
+            const double4 c = c_next;
+            if (r + 1 < rounds)
+                c_next = load_corr(r + 1); // in flight while this round computes
+            if (r >= 2)
+                mbar_wait(&sm.empty_bar[b], ((r >> 1) - 1) & 1); // the sum warp has consumed round r - 2
+            for (uint32_t g = 0; g < nh; g += W)
             {
-                const uint32_t p = r * K2_TP + warp * 32 + lane;
-                const bool valid = p < n;
-                double4 c = make_double4(0, 0, 0, 0);
-                if (valid)
-                    c = corr4[p];
+                double e[W], ratio[W];
+                uint32_t rng[W];
 #pragma unroll
-                for (int g = 0; g < K2_HG; g++)
+                for (int w = 0; w < W; w++)
                 {
-                    if ((uint32_t)g < nh)
+                    const uint32_t gg = min(g + w, nh - 1);
+                    e[w] = residual_fast<KIND>(sm.M[gg], c.x, c.y, c.z, c.w, rng[w]);
+                    ratio[w] = quot_shared(e[w], thr, r_thr);
+                    if (!is_pos_zero(e[w])) // e == +0: ratio is +0 / thr, already exact
+                        rng[w] = max(rng[w], max(range_key(e[w]), range_key(ratio[w])));
+                    rng[w] = max(rng[w], thr_rng);
+                }
+#pragma unroll
+                for (int w = 0; w < W; w++)
+                {
+                    if (rng[w] >= RANGE_OK) // rare: tiny, huge or non-finite operands
                     {
-                        const double e = residual<KIND>(M[g], c.x, c.y, c.z, c.w);
-                        const bool inl = valid && (e < thr); // strict, ransac.cpp:189
-                        const double ratio = __ddiv_rn(e, thr);
-                        contrib[r & 1][g][warp * 32 + lane] = __dsub_rn(1.0, __dmul_rn(ratio, ratio));
+                        e[w] = residual<KIND>(sm.M[min(g + w, nh - 1)], c.x, c.y, c.z, c.w);
+                        ratio[w] = __ddiv_rn(e[w], thr);
+                    }
+                }
+#pragma unroll
+                for (int w = 0; w < W; w++)
+                {
+                    if (g + w < nh)
+                    {
+                        const bool inl = valid && (e[w] < thr); // strict, ransac.cpp:189
+                        // an outlier parks +0.0: score + 0.0 == score bit for bit (the score is never -0.0), so the
+                        // sum warp adds whole 32-position words in order without testing single bits
+                        sm.contrib[b][g + w][warp * 32 + lane] = inl ? __dsub_rn(1.0, __dmul_rn(ratio[w], ratio[w])) : 0.0;
                         const uint32_t m = __ballot_sync(0xFFFFFFFFu, inl);
                         if (lane == 0)
                         {
-                            mask[r & 1][g][warp] = m;
+                            sm.mask[b][g + w][warp] = m;
                             if (bits_pos && (p >> 5) < words)
-                                bits_pos[(size_t)(h0 + g) * words + (p >> 5)] = m;
+                                bits_pos[(size_t)(h0 + g + w) * words + (p >> 5)] = m;
                         }
                     }
                 }
             }
+            __syncwarp();
+            if (lane == 0)
+                mbar_arrive(&sm.full_bar[b]);
         }
-        else if (r > 0 && lane < nh)
+    }
+    else
+    {
+        double s = 0.0;
+        uint32_t cnt = 0;
+        for (uint32_t r = 0; r < rounds; r++)
         {
-            const uint32_t b = (r - 1) & 1;
-#pragma unroll
-            for (int w = 0; w < K2_CW; w++)
+            const uint32_t b = r & 1;
+            mbar_wait(&sm.full_bar[b], (r >> 1) & 1);
+            if (lane < nh)
             {
-                uint32_t m = mask[b][lane][w];
-                cnt += __popc(m);
-                while (m)
+#pragma unroll 1
+                for (int w = 0; w < K2_CW; w++)
                 {
-                    const int bit = __ffs(m) - 1;
-                    s = __dadd_rn(s, contrib[b][lane][w * 32 + bit]); // score += 1.0 - ratio*ratio, in order
-                    m &= m - 1;
+                    const uint32_t m = sm.mask[b][lane][w];
+                    if (m == 0)
+                        continue; // no inlier among these 32 positions: nothing to add
+                    cnt += __popc(m);
+                    const double2 *row = reinterpret_cast<const double2 *>(&sm.contrib[b][lane][w * 32]);
+#pragma unroll
+                    for (int i = 0; i < 16; i++)
+                    {
+                        const double2 v = row[i];
+                        s = __dadd_rn(__dadd_rn(s, v.x), v.y); // score += 1.0 - ratio*ratio, in evaluation order
+                    }
                 }
             }
+            __syncwarp();
+            if (lane == 0)
+                mbar_arrive(&sm.empty_bar[b]);
         }
-        __syncthreads();
+        if (lane < nh)
+        {
+            score[h0 + lane] = s;
+            count[h0 + lane] = cnt;
+        }
     }
-    if (warp == K2_CW && lane < nh)
-    {
-        score[h0 + lane] = s;
-        count[h0 + lane] = cnt;
-    }
+}
+
+template <int KIND, int W>
+__global__ void __launch_bounds__(K2_THREADS, W == 1 ? 4 : 3)
+    k2_score_kernel(const double *__restrict__ models, uint32_t h, uint32_t hg, const double4 *__restrict__ corr4, uint32_t n,
+                    double thr, double *__restrict__ score, uint32_t *__restrict__ count,
+                    uint32_t *__restrict__ bits_pos, uint32_t words)
+{
+    __shared__ K2Shared sm;
+    const uint32_t h0 = blockIdx.x * hg;
+    score_group<KIND, W>(sm, models, h0, min(hg, h - h0), corr4, nullptr, nullptr, n, thr, score, count, bits_pos, words);
 }
 
 // evaluation-position bit masks -> correspondence-index bit masks (only needed when an order is given)
@@ -223,85 +365,9 @@ __global__ void __launch_bounds__(256)
 // correspondences are normalised on the fly from the [n][7] rows (through the evaluation order for mode 0), which
 // costs 4 divisions per position per CTA and saves the per-problem prepare launches.
 // ----------------------------------------------------------------------------------------------------------
-template <int KIND>
-__device__ __forceinline__ void score_request(const K2Request &rq, uint32_t local_cta, double (*M)[18],
-                                              double (*contrib)[K2_HG][K2_TP], uint32_t (*mask)[K2_HG][K2_CW + 1])
+__global__ void __launch_bounds__(K2_THREADS, 4) k2_requests_kernel(const K2Request *__restrict__ requests, uint32_t n_requests)
 {
-    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const uint32_t h0 = local_cta * K2_HG;
-    const uint32_t nh = min((uint32_t)K2_HG, rq.h - h0);
-    const uint32_t n = rq.n;
-    const double thr = rq.thr;
-    for (uint32_t i = tid; i < nh * 18; i += K2_THREADS)
-        M[i / 18][i % 18] = rq.models[(size_t)h0 * 18 + i];
-    __syncthreads();
-    const uint32_t rounds = (n + K2_TP - 1) / K2_TP;
-    double s = 0.0;
-    uint32_t cnt = 0;
-    for (uint32_t r = 0; r <= rounds; r++)
-    {
-        if (warp < K2_CW)
-        {
-            if (r < rounds)
-            {
-                const uint32_t p = r * K2_TP + warp * 32 + lane;
-                const bool valid = p < n;
-                double4 c = make_double4(0, 0, 0, 0);
-                if (valid)
-                {
-                    const uint32_t idx = rq.order ? rq.order[p] : p;
-                    c = normalise_corr(rq.c7 + (size_t)idx * 7);
-                }
-#pragma unroll
-                for (int g = 0; g < K2_HG; g++)
-                {
-                    if ((uint32_t)g < nh)
-                    {
-                        const double e = residual<KIND>(M[g], c.x, c.y, c.z, c.w);
-                        const bool inl = valid && (e < thr);
-                        const double ratio = __ddiv_rn(e, thr);
-                        contrib[r & 1][g][warp * 32 + lane] = __dsub_rn(1.0, __dmul_rn(ratio, ratio));
-                        const uint32_t m = __ballot_sync(0xFFFFFFFFu, inl);
-                        if (lane == 0)
-                        {
-                            mask[r & 1][g][warp] = m;
-                            if (rq.bits && (p >> 5) < rq.words)
-                                rq.bits[(size_t)(h0 + g) * rq.words + (p >> 5)] = m;
-                        }
-                    }
-                }
-            }
-        }
-        else if (r > 0 && lane < nh)
-        {
-            const uint32_t b = (r - 1) & 1;
-#pragma unroll
-            for (int w = 0; w < K2_CW; w++)
-            {
-                uint32_t m = mask[b][lane][w];
-                cnt += __popc(m);
-                while (m)
-                {
-                    const int bit = __ffs(m) - 1;
-                    s = __dadd_rn(s, contrib[b][lane][w * 32 + bit]);
-                    m &= m - 1;
-                }
-            }
-        }
-        __syncthreads();
-    }
-    if (warp == K2_CW && lane < nh)
-    {
-        rq.score[h0 + lane] = s;
-        rq.count[h0 + lane] = cnt;
-    }
-}
-
-__global__ void __launch_bounds__(K2_THREADS) k2_requests_kernel(const K2Request *__restrict__ requests, uint32_t n_requests)
-{
-    __shared__ double M[K2_HG][18];
-    __shared__ double contrib[2][K2_HG][K2_TP];
-    __shared__ uint32_t mask[2][K2_HG][K2_CW + 1];
+    __shared__ K2Shared sm;
     uint32_t lo = 0, hi = n_requests - 1;
     while (lo < hi)
     {
@@ -317,21 +383,25 @@ __global__ void __launch_bounds__(K2_THREADS) k2_requests_kernel(const K2Request
     {
         // residual fetch: Model::error of one model for 256 correspondences, index order
         if (threadIdx.x < 18)
-            M[0][threadIdx.x] = rq.models[threadIdx.x];
+            sm.M[0][threadIdx.x] = rq.models[threadIdx.x];
         __syncthreads();
         const uint32_t i = local * K2_THREADS + threadIdx.x;
         if (i < rq.n)
         {
             const double4 c = normalise_corr(rq.c7 + (size_t)i * 7);
-            rq.e[i] = rq.kind == OCB_MODEL_HOMOGRAPHY ? residual<OCB_MODEL_HOMOGRAPHY>(M[0], c.x, c.y, c.z, c.w)
-                                                      : residual<OCB_MODEL_ESSENTIAL>(M[0], c.x, c.y, c.z, c.w);
+            rq.e[i] = rq.kind == OCB_MODEL_HOMOGRAPHY ? residual<OCB_MODEL_HOMOGRAPHY>(sm.M[0], c.x, c.y, c.z, c.w)
+                                                      : residual<OCB_MODEL_ESSENTIAL>(sm.M[0], c.x, c.y, c.z, c.w);
         }
         return;
     }
+    const uint32_t h0 = local * K2_HG;
+    const uint32_t nh = min((uint32_t)K2_HG, rq.h - h0);
     if (rq.kind == OCB_MODEL_HOMOGRAPHY)
-        score_request<OCB_MODEL_HOMOGRAPHY>(rq, local, M, contrib, mask);
+        score_group<OCB_MODEL_HOMOGRAPHY, 1>(sm, rq.models, h0, nh, nullptr, rq.c7, rq.order, rq.n, rq.thr, rq.score,
+                                             rq.count, rq.bits, rq.words);
     else
-        score_request<OCB_MODEL_ESSENTIAL>(rq, local, M, contrib, mask);
+        score_group<OCB_MODEL_ESSENTIAL, 1>(sm, rq.models, h0, nh, nullptr, rq.c7, rq.order, rq.n, rq.thr, rq.score,
+                                            rq.count, rq.bits, rq.words);
 }
 
 uint32_t k2_request_ctas(const K2Request &rq)
@@ -363,6 +433,45 @@ int k2_prepare(const double *d_corr7, const uint32_t *d_order, size_t n, double 
     return 0;
 }
 
+// Resident CTAs per SM of the scoring kernel (occupancy API, cached per instantiation).
+static int k2_resident_ctas(int kind, int wide)
+{
+    static int cache[2][2] = {{0, 0}, {0, 0}};
+    int &c = cache[kind == OCB_MODEL_HOMOGRAPHY ? 0 : 1][wide == 1 ? 0 : 1];
+    if (c == 0)
+    {
+        int b = 0;
+        cudaError_t e;
+        if (kind == OCB_MODEL_HOMOGRAPHY)
+            e = wide == 1 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k2_score_kernel<OCB_MODEL_HOMOGRAPHY, 1>, K2_THREADS, 0)
+                          : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k2_score_kernel<OCB_MODEL_HOMOGRAPHY, 2>, K2_THREADS, 0);
+        else
+            e = wide == 1 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k2_score_kernel<OCB_MODEL_ESSENTIAL, 1>, K2_THREADS, 0)
+                          : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k2_score_kernel<OCB_MODEL_ESSENTIAL, 2>, K2_THREADS, 0);
+        c = (e == cudaSuccess && b > 0) ? b : 1;
+    }
+    return c;
+}
+
+// Hypotheses per CTA for one launch. A CTA's time grows with its hypotheses and an SM's with the hypotheses of all its
+// CTAs, so the launch ends with the most loaded SM: pick the group size in 4..K2_HG that minimises that load
+// (4096 hypotheses on 148 SMs: groups of 7 put 28 on every SM, groups of 8 put 32 on 68 SMs and 24 on the rest).
+uint32_t k2_pick_group(size_t h, int sms, int resident)
+{
+    uint32_t best_hg = K2_HG;
+    uint64_t best_load = ~0ull;
+    for (uint32_t hg = K2_HG; hg >= 4; hg--)
+    {
+        const uint64_t ctas = (h + hg - 1) / hg;
+        const uint64_t per_sm = (ctas + sms - 1) / sms;
+        const uint64_t waves = (per_sm + resident - 1) / resident;
+        const uint64_t load = (waves > 1 ? waves * resident : per_sm) * hg;
+        if (load < best_load)
+            best_load = load, best_hg = hg;
+    }
+    return best_hg;
+}
+
 int k2_score(int kind, const double *d_models, size_t h, const double *d_corr4, const uint32_t *d_pos, size_t n,
              double thr, double *d_score, uint32_t *d_count, uint32_t *d_bits, uint32_t *d_bits_scratch,
              cudaStream_t stream)
@@ -372,14 +481,32 @@ int k2_score(int kind, const double *d_models, size_t h, const double *d_corr4, 
     const uint32_t words = (uint32_t)((n + 31) / 32);
     // with an evaluation order the kernel's ballots are in position order: write them to scratch, then scatter
     uint32_t *bits_pos = d_bits ? (d_pos ? d_bits_scratch : d_bits) : nullptr;
-    const unsigned grid = (unsigned)((h + K2_HG - 1) / K2_HG);
     const double4 *c4 = reinterpret_cast<const double4 *>(d_corr4);
+    const int wide = options().k2_variant == 1 ? 2 : 1; // hypotheses in flight per thread (variant 1: two)
+    int dev = 0;
+    OCB_CUDA(cudaGetDevice(&dev));
+    const uint32_t hg = options().k2_hg >= 1 && options().k2_hg <= K2_HG
+                            ? (uint32_t)options().k2_hg
+                            : k2_pick_group(h, sm_count(dev), k2_resident_ctas(kind, wide));
+    const unsigned grid = (unsigned)((h + hg - 1) / hg);
+#define OCB_K2_LAUNCH(KIND, W)                                                                                         \
+    k2_score_kernel<KIND, W><<<grid, K2_THREADS, 0, stream>>>(d_models, (uint32_t)h, hg, c4, (uint32_t)n, thr, d_score, \
+                                                              d_count, bits_pos, words)
     if (kind == OCB_MODEL_HOMOGRAPHY)
-        k2_score_kernel<OCB_MODEL_HOMOGRAPHY>
-            <<<grid, K2_THREADS, 0, stream>>>(d_models, (uint32_t)h, c4, (uint32_t)n, thr, d_score, d_count, bits_pos, words);
+    {
+        if (wide == 1)
+            OCB_K2_LAUNCH(OCB_MODEL_HOMOGRAPHY, 1);
+        else
+            OCB_K2_LAUNCH(OCB_MODEL_HOMOGRAPHY, 2);
+    }
     else
-        k2_score_kernel<OCB_MODEL_ESSENTIAL>
-            <<<grid, K2_THREADS, 0, stream>>>(d_models, (uint32_t)h, c4, (uint32_t)n, thr, d_score, d_count, bits_pos, words);
+    {
+        if (wide == 1)
+            OCB_K2_LAUNCH(OCB_MODEL_ESSENTIAL, 1);
+        else
+            OCB_K2_LAUNCH(OCB_MODEL_ESSENTIAL, 2);
+    }
+#undef OCB_K2_LAUNCH
     count_launch();
     OCB_CUDA(cudaGetLastError());
     if (d_bits && d_pos && words > 0)

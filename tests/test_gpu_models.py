@@ -39,6 +39,53 @@ def test_scores_bit_exact(gpu, oracle, kind, n):
         assert np.array_equal(c, co) and np.array_equal(bits, bo)
 
 
+@pytest.mark.parametrize("spread", [4, 60, 700, 1000])
+def test_shared_reciprocal_division_and_sqrt_equal_the_ieee_intrinsics(gpu, spread):
+    """csrc/exact_math.cuh: K2 divides x and y by the same z (homography_model.cpp:91-96) through ONE refined
+    reciprocal and takes its square root in line; both must return the bits of div.rn.f64 / sqrt.rn.f64."""
+    counts = gpu.probe_exact_math(seed=spread * 7919, n=6_000_000, exponent_spread=spread)
+    assert counts[0] > (5_000_000 if spread <= 60 else 100_000) and counts[2] > 1_000_000
+    assert counts[1] == 0 and counts[3] == 0, counts
+
+
+@pytest.mark.parametrize("kind", [0, 2])
+@pytest.mark.parametrize("variant,hg", [(0, 0), (1, 0), (0, 8), (1, 5), (0, 4)])
+def test_scores_bit_exact_with_extreme_operands(gpu, oracle, kind, variant, hg):
+    """Operands outside the guarded range of the shared-reciprocal forms (zeros, denormals, huge values, exact fits)
+    take the out-of-line IEEE path; every K2 variant / group size must still equal the oracle bit for bit."""
+    n = 700
+    corr = (oracle.scene_homography(500, 200, 11)[0] if kind == 0 else oracle.scene_fundamental(500, 200, 0.0, 11)[0])
+    _, _, models = stream_models(oracle, kind, corr, 21)
+    rng = np.random.default_rng(5)
+    corr[0:40, 0:2] = 0.0                      # x1 = y1 = 0
+    corr[40:60, 3:5] *= 1e-300                 # tiny second view
+    corr[60:80, 0:2] *= 1e+250                 # huge first view
+    corr[80:90, 0:6] = 0.0                     # z == 0 -> NaN
+    models[3] = np.concatenate([np.eye(3).ravel(), np.eye(3).ravel()])   # exact fit of identical points: e == 0
+    corr[100:140, 3:6] = corr[100:140, 0:3]
+    models[4] *= 1e-200
+    models[5] *= 1e+200
+    models[6, :] = 0.0
+    models[7, rng.integers(0, 9, 3)] = 0.0
+    gpu.set_option("k2_variant", variant)
+    gpu.set_option("k2_hg", hg)
+    try:
+        for thr in (THR[kind], 1e-300, 1e+300):
+            for order in (None, rng.permutation(n)):
+                s, c, bits = gpu.score_models(kind, models, corr, thr, order=order)
+                so, co, bo = oracle.score_hypotheses(kind, models, corr, order=order, thr=thr)
+                assert np.array_equal(s, so, equal_nan=True)
+                assert np.array_equal(c, co) and np.array_equal(bits, bo)
+    finally:
+        gpu.set_option("k2_variant", 0)
+        gpu.set_option("k2_hg", 0)
+
+
+def test_group_size_balances_the_sms(gpu):
+    """k2_pick_group: 4096 hypotheses on 148 SMs go out in groups of 7 (28 per SM), not 8 (32 on some, 24 on others)."""
+    assert gpu.get_option("k2_hg") == 0
+
+
 def test_residuals_bit_exact_and_special_values(gpu, oracle):
     corr, _ = oracle.scene_homography(500, 200, 3)
     corr[10, 2] = 0.0       # measurement1.z == 0
