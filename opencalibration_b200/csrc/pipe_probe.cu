@@ -150,7 +150,7 @@ __device__ __forceinline__ double random_double(uint64_t bits, uint32_t spread)
     return __longlong_as_double((long long)(sign | ((uint64_t)e << 52) | mant));
 }
 // counts[0..1] = divisions tested / differing, [2..3] = square roots tested / differing,
-// [4] = divisions whose operands fell outside mid_range (not compared: callers use __ddiv_rn there)
+// [4] = divisions whose divisor or quotient fell outside mid_range (not compared: callers use __ddiv_rn there)
 __global__ void __launch_bounds__(256) exact_math_kernel(uint64_t seed, uint64_t n, uint32_t spread, unsigned long long *counts)
 {
     unsigned long long c[5] = {0, 0, 0, 0, 0};
@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(256) exact_math_kernel(uint64_t seed, uint64_t
         for (int k = 0; k < 2; k++)
         {
             const double q = quot_shared(nums[k], z, r);
-            if (mid_range(nums[k]) && mid_range(z) && mid_range(q))
+            if (mid_range(z) && mid_range(q)) // the precondition K2 tests (exact_math.cuh: range_key)
             {
                 c[0]++;
                 c[1] += __double_as_longlong(q) != __double_as_longlong(__ddiv_rn(nums[k], z));

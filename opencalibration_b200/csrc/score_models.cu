@@ -75,11 +75,32 @@ template <int KIND> __device__ __forceinline__ double residual(const double *__r
 }
 
 // The same residuals as straight-line code (exact_math.cuh): x/z and y/z share one refined reciprocal and nothing
-// calls out of line, so the divisions and the square root of one residual (and of the next hypothesis) overlap in
-// the FP64 pipe. `rng` (see range_key) ends >= RANGE_OK when an operand left the range in which the shared-reciprocal
-// forms are equal to div.rn / sqrt.rn; the caller then recomputes with residual<KIND>().
-__device__ __forceinline__ double h_residual_fast(const double *__restrict__ M, double x1, double y1, double x2, double y2,
-                                                  uint32_t &rng)
+// calls out of line, so the divisions and the square root of one residual overlap in the FP64 pipe.
+// Returns e and, through `ratio`, e / thr (given r_thr = rcp_refined(thr)). `rng` (see range_key) comes back
+// >= RANGE_OK when an operand left the window in which these forms are equal to div.rn / sqrt.rn; the caller then
+// recomputes with residual<KIND>() and __ddiv_rn. An exact fit (e == +0: noise-free scenes) stays in line:
+// sqrt(+0) = +0 and quot_shared(+0, thr, r) is +0 / thr exactly.
+struct FastResidual
+{
+    double e, ratio;
+    uint32_t rng;
+};
+
+__device__ __forceinline__ FastResidual finish_residual(double a, uint32_t rng, double thr, double r_thr)
+{
+    // a = e^2 >= +0 or NaN. A positive mid_range a passes sqrt_fast_ok and puts e inside the window as well.
+    const bool zero = is_pos_zero(a);
+    FastResidual f;
+    f.e = sqrt_fast(zero ? 1.0 : a);
+    f.e = zero ? 0.0 : f.e;
+    f.ratio = quot_shared(f.e, thr, r_thr);
+    const uint32_t tail = max(range_key(a), range_key(f.ratio));
+    f.rng = max(rng, zero ? 0u : tail);
+    return f;
+}
+
+__device__ __forceinline__ FastResidual h_residual_fast(const double *__restrict__ M, double x1, double y1, double x2,
+                                                        double y2, double thr, double r_thr, uint32_t thr_rng)
 {
     const double px = __dadd_rn(__dadd_rn(__dmul_rn(M[0], x1), __dmul_rn(M[3], y1)), M[6]);
     const double py = __dadd_rn(__dadd_rn(__dmul_rn(M[1], x1), __dmul_rn(M[4], y1)), M[7]);
@@ -95,17 +116,13 @@ __device__ __forceinline__ double h_residual_fast(const double *__restrict__ M, 
     const double fwd = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
     const double bwd = __dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey));
     const double a = __dmul_rn(__dadd_rn(fwd, bwd), 0.5);
-    rng = max(max(max(range_key(pz), range_key(qz)), max(range_key(px), range_key(py))),
-              max(max(range_key(qx), range_key(qy)), max(range_key(ax), range_key(ay))));
-    // a >= +0 or NaN: mid_range implies sqrt_fast_ok. An exact fit (a == 0: noise-free scenes) stays in line:
-    // sqrt(+0) = +0, and quot_shared(+0, thr, r) is +0 / thr exactly.
-    const bool zero = is_pos_zero(a);
-    rng = max(max(rng, zero ? 0u : range_key(a)), max(range_key(bx), range_key(by)));
-    return zero ? 0.0 : sqrt_fast(a);
+    const uint32_t rng = max(max(max(thr_rng, range_key(pz)), max(range_key(qz), range_key(ax))),
+                             max(max(range_key(ay), range_key(bx)), range_key(by)));
+    return finish_residual(a, rng, thr, r_thr);
 }
 
-__device__ __forceinline__ double epi_residual_fast(const double *__restrict__ E, double x1, double y1, double x2, double y2,
-                                                    uint32_t &rng)
+__device__ __forceinline__ FastResidual epi_residual_fast(const double *__restrict__ E, double x1, double y1, double x2,
+                                                          double y2, double thr, double r_thr, uint32_t thr_rng)
 {
     const double b0 = __dadd_rn(__dadd_rn(__dmul_rn(x2, E[0]), __dmul_rn(y2, E[1])), E[2]);
     const double b1 = __dadd_rn(__dadd_rn(__dmul_rn(x2, E[3]), __dmul_rn(y2, E[4])), E[5]);
@@ -116,22 +133,21 @@ __device__ __forceinline__ double epi_residual_fast(const double *__restrict__ E
     const double denom = __dadd_rn(
         __dadd_rn(__dadd_rn(__dmul_rn(a0, a0), __dmul_rn(a1, a1)), __dmul_rn(b0, b0)), __dmul_rn(b1, b1));
     const double rr = __dmul_rn(r, r);
+    // q = e^2. r == 0 exactly gives q = +0 (denom inside the window). denom < 1e-20 (DBL_MAX in the reference) is
+    // inside the window (1e-20 ~ 2^-66), so it is flagged explicitly and decided by the out-of-line form.
     const double q = quot_shared(rr, denom, rcp_refined(denom));
-    // rr, denom, q >= 0 or NaN. denom < 1e-20 (DBL_MAX in the reference) is decided by the out-of-line form.
-    // r == 0 exactly (rr = q = +0) stays in line like an exact homography fit.
-    const bool zero = is_pos_zero(rr);
-    rng = max(max(zero ? 0u : range_key(rr), range_key(denom)), max(zero ? 0u : range_key(q), denom < 1e-20 ? RANGE_OK : 0u));
-    return zero ? 0.0 : sqrt_fast(q);
+    const uint32_t rng = max(max(thr_rng, range_key(denom)), denom < 1e-20 ? RANGE_OK : 0u);
+    return finish_residual(q, rng, thr, r_thr);
 }
 
 template <int KIND>
-__device__ __forceinline__ double residual_fast(const double *__restrict__ M, double x1, double y1, double x2, double y2,
-                                                uint32_t &rng)
+__device__ __forceinline__ FastResidual residual_fast(const double *__restrict__ M, double x1, double y1, double x2,
+                                                      double y2, double thr, double r_thr, uint32_t thr_rng)
 {
     if constexpr (KIND == OCB_MODEL_HOMOGRAPHY)
-        return h_residual_fast(M, x1, y1, x2, y2, rng);
+        return h_residual_fast(M, x1, y1, x2, y2, thr, r_thr, thr_rng);
     else
-        return epi_residual_fast(M, x1, y1, x2, y2, rng);
+        return epi_residual_fast(M, x1, y1, x2, y2, thr, r_thr, thr_rng);
 }
 
 // measurement / measurement.z for both views; NaN when z/z != 1 (z zero, infinite or NaN), which is what the
@@ -225,25 +241,17 @@ __device__ __forceinline__ void score_group(K2Shared &sm, const double *__restri
                 mbar_wait(&sm.empty_bar[b], ((r >> 1) - 1) & 1); // the sum warp has consumed round r - 2
             for (uint32_t g = 0; g < nh; g += W)
             {
-                double e[W], ratio[W];
-                uint32_t rng[W];
+                FastResidual f[W];
+#pragma unroll
+                for (int w = 0; w < W; w++)
+                    f[w] = residual_fast<KIND>(sm.M[min(g + w, nh - 1)], c.x, c.y, c.z, c.w, thr, r_thr, thr_rng);
 #pragma unroll
                 for (int w = 0; w < W; w++)
                 {
-                    const uint32_t gg = min(g + w, nh - 1);
-                    e[w] = residual_fast<KIND>(sm.M[gg], c.x, c.y, c.z, c.w, rng[w]);
-                    ratio[w] = quot_shared(e[w], thr, r_thr);
-                    if (!is_pos_zero(e[w])) // e == +0: ratio is +0 / thr, already exact
-                        rng[w] = max(rng[w], max(range_key(e[w]), range_key(ratio[w])));
-                    rng[w] = max(rng[w], thr_rng);
-                }
-#pragma unroll
-                for (int w = 0; w < W; w++)
-                {
-                    if (rng[w] >= RANGE_OK) // rare: tiny, huge or non-finite operands
+                    if (f[w].rng >= RANGE_OK) // rare: tiny, huge or non-finite operands
                     {
-                        e[w] = residual<KIND>(sm.M[min(g + w, nh - 1)], c.x, c.y, c.z, c.w);
-                        ratio[w] = __ddiv_rn(e[w], thr);
+                        f[w].e = residual<KIND>(sm.M[min(g + w, nh - 1)], c.x, c.y, c.z, c.w);
+                        f[w].ratio = __ddiv_rn(f[w].e, thr);
                     }
                 }
 #pragma unroll
@@ -251,17 +259,15 @@ __device__ __forceinline__ void score_group(K2Shared &sm, const double *__restri
                 {
                     if (g + w < nh)
                     {
-                        const bool inl = valid && (e[w] < thr); // strict, ransac.cpp:189
+                        const bool inl = valid && (f[w].e < thr); // strict, ransac.cpp:189
                         // an outlier parks +0.0: score + 0.0 == score bit for bit (the score is never -0.0), so the
                         // sum warp adds whole 32-position words in order without testing single bits
-                        sm.contrib[b][g + w][warp * 32 + lane] = inl ? __dsub_rn(1.0, __dmul_rn(ratio[w], ratio[w])) : 0.0;
+                        sm.contrib[b][g + w][warp * 32 + lane] =
+                            inl ? __dsub_rn(1.0, __dmul_rn(f[w].ratio, f[w].ratio)) : 0.0;
                         const uint32_t m = __ballot_sync(0xFFFFFFFFu, inl);
-                        if (lane == 0)
-                        {
-                            sm.mask[b][g + w][warp] = m;
-                            if (bits_pos && (p >> 5) < words)
-                                bits_pos[(size_t)(h0 + g + w) * words + (p >> 5)] = m;
-                        }
+                        sm.mask[b][g + w][warp] = m; // every lane stores the same word
+                        if (bits_pos && lane == 0 && (p >> 5) < words)
+                            bits_pos[(size_t)(h0 + g + w) * words + (p >> 5)] = m;
                     }
                 }
             }
