@@ -25,6 +25,7 @@ extern "C"
         OCB_PROBE_DFMA,
         OCB_PROBE_DDIV,  /* IEEE divisions */
         OCB_PROBE_DSQRT, /* IEEE square roots (+1 add) */
+        OCB_PROBE_DFMA3, /* DFMA with three distinct register operands (register-file bandwidth bound) */
         OCB_PROBE_COUNT
     };
     /* Runs the probes on the current device; out must hold OCB_PROBE_COUNT doubles. 0 or a negative code. */

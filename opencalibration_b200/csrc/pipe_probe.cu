@@ -27,6 +27,7 @@ enum ProbeOp
     P_DFMA,
     P_DDIV,
     P_DSQRT,
+    P_DFMA3, // fma with three distinct register operands per instruction (no operand reuse between neighbours)
     P_COUNT
 };
 
@@ -41,6 +42,13 @@ template <int OP> __global__ void __launch_bounds__(1024, 1) probe_kernel(uint32
         d[i] = 1.0 + 1e-9 * (double)(x[i] & 1023);
     }
     const double dy = 1.0 + 1e-12 * (double)(seed & 7), dz = 1e-13;
+    double e3[8], f3[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+    {
+        e3[i] = 1.0 + 1e-12 * (double)((seed + i) & 15);
+        f3[i] = 1e-13 * (double)(1 + ((seed >> 3) + i) % 7);
+    }
     __syncthreads();
     const long long t0 = clock64();
     for (uint32_t it = 0; it < iters; it++)
@@ -85,6 +93,8 @@ template <int OP> __global__ void __launch_bounds__(1024, 1) probe_kernel(uint32
                     asm volatile("mul.rn.f64 %0, %0, %1;" : "+d"(d[i]) : "d"(dy));
                 else if (OP == P_DFMA)
                     asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(d[i]) : "d"(dy), "d"(dz));
+                else if (OP == P_DFMA3)
+                    asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(d[i]) : "d"(e3[i]), "d"(f3[i]));
                 else if (OP == P_DDIV)
                     d[i] = __ddiv_rn(d[i], dy);
                 else if (OP == P_DSQRT)
@@ -253,6 +263,7 @@ extern "C" int ocb_probe_pipes(double *out, int n_out)
     RUN(P_DFMA, OCB_PROBE_DFMA, it / 4)
     RUN(P_DDIV, OCB_PROBE_DDIV, it / 32)
     RUN(P_DSQRT, OCB_PROBE_DSQRT, it / 32)
+    RUN(P_DFMA3, OCB_PROBE_DFMA3, it / 4)
 #undef RUN
     out[OCB_PROBE_SMS] = sms;
     cudaFree(d_sink);

@@ -29,6 +29,8 @@ constexpr int K2_HG = 8;          // hypotheses per CTA (upper bound; k2_score p
 constexpr int K2_CW = 7;          // compute warps
 constexpr int K2_TP = K2_CW * 32; // evaluation positions per round
 constexpr int K2_THREADS = (K2_CW + 1) * 32;
+constexpr int K2_SUBS = 4;     // hypothesis groups per CTA of k2_score_kernel (one 1024-thread CTA per SM)
+constexpr int K2_LOCKSTEP = 8; // rounds between the CTA-wide barriers that keep those groups together
 
 // homography_model::error (homography_model.cpp:89-97) on pre-divided coordinates, plain IEEE intrinsics.
 // M = [H (9, column-major) | H^-1 (9)]. Out of line: only reached when residual_fast's range test fails.
@@ -194,14 +196,18 @@ struct K2Shared
 // given, read through `order` when it is set and normalised on the fly). W = hypotheses in flight per thread.
 // Compute warps and the sum warp meet only through the two mbarrier pairs of the double-buffered slab (no CTA-wide
 // barrier per round): a compute warp may run up to two rounds ahead of the slowest one.
-template <int KIND, int W>
+// SUBS > 1: the CTA holds SUBS such groups side by side (256 threads each, `sm` is this thread's group); nh == 0 marks a
+// group without work. The groups of one CTA meet at a CTA-wide barrier every K2_LOCKSTEP rounds so that none of them
+// runs ahead: four independent CTAs per SM drift apart (the warp scheduler favours the oldest), the early ones retire
+// and the SM finishes the launch with a quarter of its warps.
+template <int KIND, int W, int SUBS>
 __device__ __forceinline__ void score_group(K2Shared &sm, const double *__restrict__ models, uint32_t h0, uint32_t nh,
                                             const double4 *__restrict__ corr4, const double *__restrict__ c7,
                                             const uint32_t *__restrict__ order, uint32_t n, double thr,
                                             double *__restrict__ score, uint32_t *__restrict__ count,
                                             uint32_t *__restrict__ bits_pos, uint32_t words)
 {
-    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t tid = threadIdx.x % K2_THREADS, warp = tid >> 5, lane = tid & 31;
     for (uint32_t i = tid; i < nh * 18; i += K2_THREADS)
         sm.M[i / 18][i % 18] = models[(size_t)h0 * 18 + i];
     if (tid == 0)
@@ -217,6 +223,12 @@ __device__ __forceinline__ void score_group(K2Shared &sm, const double *__restri
     __syncthreads();
 
     const uint32_t rounds = (n + K2_TP - 1) / K2_TP;
+    if (SUBS > 1 && nh == 0)
+    {
+        for (uint32_t r = K2_LOCKSTEP; r < rounds; r += K2_LOCKSTEP)
+            __syncthreads();
+        return;
+    }
     if (warp < K2_CW)
     {
         const double r_thr = rcp_refined(thr); // shared by every MSAC contribution of this thread
@@ -231,6 +243,8 @@ __device__ __forceinline__ void score_group(K2Shared &sm, const double *__restri
         double4 c_next = rounds ? load_corr(0) : make_double4(0, 0, 0, 0);
         for (uint32_t r = 0; r < rounds; r++)
         {
+            if (SUBS > 1 && r > 0 && r % K2_LOCKSTEP == 0)
+                __syncthreads();
             const uint32_t b = r & 1;
             const uint32_t p = r * K2_TP + warp * 32 + lane;
             const bool valid = p < n;
@@ -282,6 +296,8 @@ __device__ __forceinline__ void score_group(K2Shared &sm, const double *__restri
         uint32_t cnt = 0;
         for (uint32_t r = 0; r < rounds; r++)
         {
+            if (SUBS > 1 && r > 0 && r % K2_LOCKSTEP == 0)
+                __syncthreads();
             const uint32_t b = r & 1;
             mbar_wait(&sm.full_bar[b], (r >> 1) & 1);
             if (lane < nh)
@@ -314,15 +330,18 @@ __device__ __forceinline__ void score_group(K2Shared &sm, const double *__restri
     }
 }
 
-template <int KIND, int W>
-__global__ void __launch_bounds__(K2_THREADS, W == 1 ? 4 : 3)
+template <int KIND, int W, int SUBS>
+__global__ void __launch_bounds__(K2_THREADS *SUBS, SUBS > 1 ? 1 : (W == 1 ? 4 : 3))
     k2_score_kernel(const double *__restrict__ models, uint32_t h, uint32_t hg, const double4 *__restrict__ corr4, uint32_t n,
                     double thr, double *__restrict__ score, uint32_t *__restrict__ count,
                     uint32_t *__restrict__ bits_pos, uint32_t words)
 {
-    __shared__ K2Shared sm;
-    const uint32_t h0 = blockIdx.x * hg;
-    score_group<KIND, W>(sm, models, h0, min(hg, h - h0), corr4, nullptr, nullptr, n, thr, score, count, bits_pos, words);
+    extern __shared__ __align__(16) unsigned char k2_dynamic_smem[]; // SUBS x K2Shared (above the 48 KB static limit)
+    K2Shared *sm = reinterpret_cast<K2Shared *>(k2_dynamic_smem);
+    const uint32_t sub = threadIdx.x / K2_THREADS;
+    const uint32_t h0 = min((blockIdx.x * SUBS + sub) * hg, h);
+    score_group<KIND, W, SUBS>(sm[sub], models, h0, min(hg, h - h0), corr4, nullptr, nullptr, n, thr, score, count,
+                               bits_pos, words);
 }
 
 // evaluation-position bit masks -> correspondence-index bit masks (only needed when an order is given)
@@ -403,10 +422,10 @@ __global__ void __launch_bounds__(K2_THREADS, 4) k2_requests_kernel(const K2Requ
     const uint32_t h0 = local * K2_HG;
     const uint32_t nh = min((uint32_t)K2_HG, rq.h - h0);
     if (rq.kind == OCB_MODEL_HOMOGRAPHY)
-        score_group<OCB_MODEL_HOMOGRAPHY, 1>(sm, rq.models, h0, nh, nullptr, rq.c7, rq.order, rq.n, rq.thr, rq.score,
+        score_group<OCB_MODEL_HOMOGRAPHY, 1, 1>(sm, rq.models, h0, nh, nullptr, rq.c7, rq.order, rq.n, rq.thr, rq.score,
                                              rq.count, rq.bits, rq.words);
     else
-        score_group<OCB_MODEL_ESSENTIAL, 1>(sm, rq.models, h0, nh, nullptr, rq.c7, rq.order, rq.n, rq.thr, rq.score,
+        score_group<OCB_MODEL_ESSENTIAL, 1, 1>(sm, rq.models, h0, nh, nullptr, rq.c7, rq.order, rq.n, rq.thr, rq.score,
                                             rq.count, rq.bits, rq.words);
 }
 
@@ -439,26 +458,6 @@ int k2_prepare(const double *d_corr7, const uint32_t *d_order, size_t n, double 
     return 0;
 }
 
-// Resident CTAs per SM of the scoring kernel (occupancy API, cached per instantiation).
-static int k2_resident_ctas(int kind, int wide)
-{
-    static int cache[2][2] = {{0, 0}, {0, 0}};
-    int &c = cache[kind == OCB_MODEL_HOMOGRAPHY ? 0 : 1][wide == 1 ? 0 : 1];
-    if (c == 0)
-    {
-        int b = 0;
-        cudaError_t e;
-        if (kind == OCB_MODEL_HOMOGRAPHY)
-            e = wide == 1 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k2_score_kernel<OCB_MODEL_HOMOGRAPHY, 1>, K2_THREADS, 0)
-                          : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k2_score_kernel<OCB_MODEL_HOMOGRAPHY, 2>, K2_THREADS, 0);
-        else
-            e = wide == 1 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k2_score_kernel<OCB_MODEL_ESSENTIAL, 1>, K2_THREADS, 0)
-                          : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k2_score_kernel<OCB_MODEL_ESSENTIAL, 2>, K2_THREADS, 0);
-        c = (e == cudaSuccess && b > 0) ? b : 1;
-    }
-    return c;
-}
-
 // Hypotheses per CTA for one launch. A CTA's time grows with its hypotheses and an SM's with the hypotheses of all its
 // CTAs, so the launch ends with the most loaded SM: pick the group size in 4..K2_HG that minimises that load
 // (4096 hypotheses on 148 SMs: groups of 7 put 28 on every SM, groups of 8 put 32 on 68 SMs and 24 on the rest).
@@ -488,29 +487,44 @@ int k2_score(int kind, const double *d_models, size_t h, const double *d_corr4, 
     // with an evaluation order the kernel's ballots are in position order: write them to scratch, then scatter
     uint32_t *bits_pos = d_bits ? (d_pos ? d_bits_scratch : d_bits) : nullptr;
     const double4 *c4 = reinterpret_cast<const double4 *>(d_corr4);
-    const int wide = options().k2_variant == 1 ? 2 : 1; // hypotheses in flight per thread (variant 1: two)
     int dev = 0;
     OCB_CUDA(cudaGetDevice(&dev));
-    const uint32_t hg = options().k2_hg >= 1 && options().k2_hg <= K2_HG
-                            ? (uint32_t)options().k2_hg
-                            : k2_pick_group(h, sm_count(dev), k2_resident_ctas(kind, wide));
-    const unsigned grid = (unsigned)((h + hg - 1) / hg);
-#define OCB_K2_LAUNCH(KIND, W)                                                                                         \
-    k2_score_kernel<KIND, W><<<grid, K2_THREADS, 0, stream>>>(d_models, (uint32_t)h, hg, c4, (uint32_t)n, thr, d_score, \
-                                                              d_count, bits_pos, words)
+    const int sms = sm_count(dev);
+    // four groups are resident per SM either way (64 registers x 256 threads each)
+    const uint32_t hg = options().k2_hg >= 1 && options().k2_hg <= K2_HG ? (uint32_t)options().k2_hg
+                                                                          : k2_pick_group(h, sms, K2_SUBS);
+    const uint32_t groups = (uint32_t)((h + hg - 1) / hg);
+    // lock-step form (K2_SUBS groups in one 1024-thread CTA) once every SM would host several groups anyway;
+    // option k2_variant: 0 = by size, 1 = always independent CTAs, 2 = always lock-step
+    const int v = options().k2_variant;
+    const bool lockstep = v == 2 || (v == 0 && groups > 2u * (uint32_t)sms);
+    static bool attr_set_on[64] = {false}; // the attribute is per device
+    bool &attr_set = attr_set_on[dev & 63];
+    if (lockstep && !attr_set)
+    {
+        const int bytes = (int)(K2_SUBS * sizeof(K2Shared));
+        OCB_CUDA(cudaFuncSetAttribute(k2_score_kernel<OCB_MODEL_HOMOGRAPHY, 1, K2_SUBS>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        OCB_CUDA(cudaFuncSetAttribute(k2_score_kernel<OCB_MODEL_ESSENTIAL, 1, K2_SUBS>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        attr_set = true;
+    }
+#define OCB_K2_LAUNCH(KIND, SUBS)                                                                                      \
+    k2_score_kernel<KIND, 1, SUBS><<<(groups + SUBS - 1) / SUBS, K2_THREADS * SUBS, SUBS * sizeof(K2Shared), stream>>>( \
+        d_models, (uint32_t)h, hg, c4, (uint32_t)n, thr, d_score, d_count, bits_pos, words)
     if (kind == OCB_MODEL_HOMOGRAPHY)
     {
-        if (wide == 1)
-            OCB_K2_LAUNCH(OCB_MODEL_HOMOGRAPHY, 1);
+        if (lockstep)
+            OCB_K2_LAUNCH(OCB_MODEL_HOMOGRAPHY, K2_SUBS);
         else
-            OCB_K2_LAUNCH(OCB_MODEL_HOMOGRAPHY, 2);
+            OCB_K2_LAUNCH(OCB_MODEL_HOMOGRAPHY, 1);
     }
     else
     {
-        if (wide == 1)
-            OCB_K2_LAUNCH(OCB_MODEL_ESSENTIAL, 1);
+        if (lockstep)
+            OCB_K2_LAUNCH(OCB_MODEL_ESSENTIAL, K2_SUBS);
         else
-            OCB_K2_LAUNCH(OCB_MODEL_ESSENTIAL, 2);
+            OCB_K2_LAUNCH(OCB_MODEL_ESSENTIAL, 1);
     }
 #undef OCB_K2_LAUNCH
     count_launch();

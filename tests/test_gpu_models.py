@@ -49,7 +49,7 @@ def test_shared_reciprocal_division_and_sqrt_equal_the_ieee_intrinsics(gpu, spre
 
 
 @pytest.mark.parametrize("kind", [0, 2])
-@pytest.mark.parametrize("variant,hg", [(0, 0), (1, 0), (0, 8), (1, 5), (0, 4)])
+@pytest.mark.parametrize("variant,hg", [(0, 0), (1, 0), (2, 0), (1, 8), (2, 5), (2, 4)])
 def test_scores_bit_exact_with_extreme_operands(gpu, oracle, kind, variant, hg):
     """Operands outside the guarded range of the shared-reciprocal forms (zeros, denormals, huge values, exact fits)
     take the out-of-line IEEE path; every K2 variant / group size must still equal the oracle bit for bit."""
@@ -81,9 +81,24 @@ def test_scores_bit_exact_with_extreme_operands(gpu, oracle, kind, variant, hg):
         gpu.set_option("k2_hg", 0)
 
 
-def test_group_size_balances_the_sms(gpu):
-    """k2_pick_group: 4096 hypotheses on 148 SMs go out in groups of 7 (28 per SM), not 8 (32 on some, 24 on others)."""
-    assert gpu.get_option("k2_hg") == 0
+@pytest.mark.parametrize("kind", [0, 1])
+@pytest.mark.parametrize("h,n", [(1200, 500), (4096, 2000), (601, 225)])
+def test_lockstep_and_independent_forms_agree_with_the_oracle(gpu, oracle, kind, h, n):
+    """Many hypotheses go out as 1024-thread CTAs holding four hypothesis groups in lock-step, few as one group per
+    CTA (k2_variant 2 / 1; 0 picks by size). Scores, counts and masks must not depend on the form."""
+    corr = (oracle.scene_homography(int(n * 0.7), n - int(n * 0.7), 9)[0] if kind == 0 else
+            oracle.scene_fundamental(int(n * 0.7), n - int(n * 0.7), 0.0, 9)[0])
+    _, _, base = stream_models(oracle, kind, corr, 32)
+    models = np.tile(base, (h // 32 + 1, 1))[:h] * np.linspace(1.0, 1.5, h)[:, None]
+    eo = np.random.default_rng(h).permutation(n)
+    so, co, bo = oracle.score_hypotheses(kind, models, corr, order=eo, thr=THR[kind])
+    try:
+        for variant in (0, 1, 2):
+            gpu.set_option("k2_variant", variant)
+            s, c, bits = gpu.score_models(kind, models, corr, THR[kind], order=eo)
+            assert np.array_equal(s, so) and np.array_equal(c, co) and np.array_equal(bits, bo), variant
+    finally:
+        gpu.set_option("k2_variant", 0)
 
 
 def test_residuals_bit_exact_and_special_values(gpu, oracle):

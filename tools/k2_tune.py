@@ -10,7 +10,7 @@ from opencalibration_b200 import capi, host, synthetic
 import oc_oracle as O
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--variants", default="0,1")
+ap.add_argument("--variants", default="1,2")
 ap.add_argument("--hg", default="0,8,7,6")
 ap.add_argument("--reps", type=int, default=10)
 args = ap.parse_args()
