@@ -567,7 +567,8 @@ struct K1Variant
             "q" #Q_ "f" #F_ "a" #A_ "p" #P_                                                                            \
     }
 static const K1Variant k1_variants[] = {
-    K1V(4, 9, true, 4, true),    // 0: default: prefix form, 9 adders (27 LOP3 + 7 POPC + 7 IMAD per comparison)
+    K1V(2, 9, true, 6, true),    // 0: default: prefix form, 9 adders (27 LOP3 + 7 POPC + 7 IMAD per comparison), two
+                                 //    queries per thread so that six CTAs (24 warps) are resident per SM
     K1V(4, 0, false, 4, false),  // 1: plain 16-POPC form (the "naive POPC roofline" shape)
     K1V(4, 7, true, 4, false),   // 2: first-round default: plain carry-save form, 7 adders (30 LOP3 + 9 POPC)
     K1V(4, 8, true, 4, true),    // 3
@@ -575,7 +576,7 @@ static const K1Variant k1_variants[] = {
     K1V(4, 9, false, 4, true),   // 5: compiler-chosen accumulation (IADD3/LEA on the ALU pipe)
     K1V(3, 9, true, 4, true),    // 6
     K1V(3, 9, true, 5, true),    // 7
-    K1V(2, 9, true, 6, true),    // 8
+    K1V(4, 9, true, 4, true),    // 8: four queries per thread (half the shared-memory reads, 16 warps per SM)
     K1V(4, 11, true, 4, true),   // 9
 };
 constexpr int K1_NUM_VARIANTS = sizeof(k1_variants) / sizeof(k1_variants[0]);

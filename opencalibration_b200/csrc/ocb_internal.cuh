@@ -35,11 +35,11 @@ inline void count_launch(uint64_t n = 1)
 struct Options
 {
     int k1_variant = 0;       // 0 = default (see hamming_top2.cu variant table)
-    int k1_items_per_sm = 16; // target work items per SM when splitting the candidate axis
+    int k1_items_per_sm = 32; // target work items per SM when splitting the candidate axis
     int k2_variant = 0;       // k2_score form: 0 = by size, 1 = one hypothesis group per CTA, 2 = four in lock-step
     int k2_hg = 0;            // hypotheses per CTA of k2_score; 0 = balance the SMs (k2_pick_group)
     int k1_update = 0;      // 0 = choose by candidate-run length, 1 = vote-and-skip, 2 = branch-free
-    int k1_bf_rows = 2048;  // runs shorter than this use the branch-free update
+    int k1_bf_rows = 1 << 20; // runs shorter than this use the branch-free update (measured: it wins at every length)
 };
 Options &options();
 

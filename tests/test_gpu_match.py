@@ -21,7 +21,8 @@ def assert_top2_equal(r, oracle_out):
 def default_options(gpu):
     yield
     gpu.set_option("k1_variant", 0)
-    gpu.set_option("k1_items_per_sm", 16)
+    gpu.set_option("k1_items_per_sm", 32)
+    gpu.set_option("k1_update", 0)
 
 
 SHAPES = [(1, 1), (1, 2), (2, 1), (3, 63), (5, 64), (7, 65), (31, 129), (128, 1), (129, 200), (511, 513),
@@ -74,6 +75,24 @@ def test_all_kernel_variants(gpu, oracle, default_options, variant):
             r, col = gpu.match_top2(a, b, cross_check=True)
             assert_top2_equal(r, oracle.match_top2(a, b))
             assert np.array_equal(col, oracle.match_col_best(a, b))
+
+
+@pytest.mark.parametrize("update", [1, 2])
+@pytest.mark.parametrize("variant", [0, 1, 8])
+def test_both_update_forms(gpu, oracle, default_options, variant, update):
+    """k1_update 1 = compare, vote and skip; 2 = branch-free two-smallest (the default at every run length)."""
+    gpu.set_option("k1_variant", variant)
+    gpu.set_option("k1_update", update)
+    for items in (1, 32):
+        gpu.set_option("k1_items_per_sm", items)
+        for n1, n2 in ((513, 3000), (64, 70)):
+            a, b = synthetic.config2_pair(n1, n2, seed=variant * 31 + update)
+            b[n2 - 1] = b[0]
+            b[n2 // 2] = b[0]
+            r, col = gpu.match_top2(a, b, cross_check=True)
+            assert_top2_equal(r, oracle.match_top2(a, b))
+            assert np.array_equal(col, oracle.match_col_best(a, b))
+            assert_top2_equal(gpu.match_top2(a, b), oracle.match_top2(a, b))
 
 
 def test_split_merge_keeps_position_order(gpu, oracle, default_options):

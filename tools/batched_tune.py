@@ -12,8 +12,8 @@ for i, im in enumerate(images):
 plist = [(1000 + a, 1000 + b) for a, b in pairs]
 nq = [n_desc] * len(plist)
 res = np.zeros(len(plist) * n_desc, capi.TOP2_DTYPE)
-for upd in (1, 2):
-    for variant in (0, 6, 8):
+for upd in (0, 1, 2):
+    for variant in (0, 7, 8):
         capi.set_option("k1_update", upd); capi.set_option("k1_variant", variant)
         capi.match_pairs(plist[:8], nq[:8], out=res)
         for npairs in (64, 256, len(plist)):
