@@ -87,8 +87,8 @@ class ClockSampler(threading.Thread):
 # (16 lanes/clk/SM), 8 IMAD on the FMA pipe; the fused cross-check is ~1.5 of the ALU ops.
 K1_ALU_OPS, K1_XU_OPS = 33.25, 7.0
 # dram__bytes_read.sum + dram__bytes_write.sum of one K1 launch of this workload, from the committed
-# `ncu --set full` capture (profiles/r1_k1_pfx_ncu_full.csv); null would mean "not captured"
-K1_NCU_DRAM_BYTES = 1508608
+# `ncu --set full` capture (profiles/r1s8_k1_ncu_full.csv); null would mean "not captured"
+K1_NCU_DRAM_BYTES = 1501952
 
 
 def roofline(achieved, sm_max, held, peak_src, ms_per_step, peaks):
