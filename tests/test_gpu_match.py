@@ -282,3 +282,35 @@ def test_concurrent_callers(gpu, oracle):
     assert not errs
     for t in range(8):
         assert_top2_equal(got[t], want[t])
+
+
+def test_concurrent_batched_submissions(gpu, oracle):
+    """ocb_match_pairs from several host threads at once (include/ocb.h: host-buffer entry points are thread-safe;
+    each thread has its own streams and staging areas, the registered sets are shared)."""
+    import threading
+    images, pos, pairs = synthetic.grid_survey(3, 4, 600, seed=11)
+    for i, d in enumerate(images):
+        gpu.register_descriptors(3000 + i, d)
+    plist = [(3000 + a, 3000 + b) for a, b in pairs]
+    nq = [len(images[a]) for a, _ in pairs]
+    want, offs = gpu.match_pairs(plist, nq)
+    for p, (a, b) in enumerate(pairs[:6]):
+        assert_top2_equal(want[int(offs[p]):int(offs[p]) + nq[p]], oracle.match_top2(images[a], images[b]))
+    errs, got = [], [None] * 4
+
+    def work(t):
+        try:
+            for rep in range(6):
+                lo = (t * 7 + rep * 3) % (len(plist) - 5)
+                out, _ = gpu.match_pairs(plist[lo:], nq[lo:])
+                if not np.array_equal(out, want[int(offs[lo]):]):
+                    errs.append(f"thread {t} rep {rep}: records differ")
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+
+    th = [threading.Thread(target=work, args=(t,)) for t in range(4)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    for i in range(len(images)):
+        gpu.unregister_descriptors(3000 + i)
+    assert not errs, errs
