@@ -1,5 +1,8 @@
 // Batched LinkStage runner -- see link_batch.hpp. Reference: src/pipeline/link_stage.cpp:41-117.
 #include "link_batch.hpp"
+
+#include <cstdio>
+#include <cstdlib>
 #include "models_detail.hpp"
 
 #include <algorithm>
@@ -270,6 +273,7 @@ std::vector<camera_relations> link_pairs(const std::vector<LinkImage> &images, c
     std::vector<camera_relations> relations(n_pairs);
     std::atomic<size_t> next_chunk{0}, total_matches{0}, total_inliers{0};
     double tail_seconds = 0, gpu_seconds = 0;
+    double phase_seconds[3] = {0, 0, 0}; // consumer wall time in (a) ratio test + rays, (b) RANSAC rounds, (c) finish
     auto fail = [&](const std::string &what) {
         std::lock_guard<std::mutex> lk(mu);
         if (error.empty())
@@ -321,6 +325,8 @@ std::vector<camera_relations> link_pairs(const std::vector<LinkImage> &images, c
                 }
             }
             const double gpu_s = sl.gpu_seconds;
+            const double t_a = since(t0);
+            double t_b = t_a;
             {
                 // the K1 records have been consumed: the slot can take the next submission
                 std::lock_guard<std::mutex> lk(mu);
@@ -344,6 +350,7 @@ std::vector<camera_relations> link_pairs(const std::vector<LinkImage> &images, c
                 {
                     local_error = e.what();
                 }
+                t_b = since(t0);
                 // (c) decomposition + inlier assembly (link_stage.cpp:95-108)
                 if (local_error.empty())
                 {
@@ -370,8 +377,10 @@ std::vector<camera_relations> link_pairs(const std::vector<LinkImage> &images, c
             total_inliers += n_inl;
             {
                 std::lock_guard<std::mutex> lk(mu);
-                tail_seconds += since(t0);
+                const double t_c = since(t0);
+                tail_seconds += t_c;
                 gpu_seconds += gpu_s;
+                phase_seconds[0] += t_a, phase_seconds[1] += t_b - t_a, phase_seconds[2] += t_c - t_b;
             }
             if (!local_error.empty())
             {
@@ -405,6 +414,12 @@ std::vector<camera_relations> link_pairs(const std::vector<LinkImage> &images, c
     st.matches = total_matches.load();
     st.ransac_inliers = total_inliers.load();
     st.seconds_total = since(t_begin);
+    if (std::getenv("OCB_LINK_TRACE"))
+        std::fprintf(stderr,
+                     "link_pairs: %zu pairs, %zu chunks, %d consumers x %d threads: upload %.3f s, match (GPU, summed) %.3f s, "
+                     "tail %.3f s = ratio/rays %.3f + ransac %.3f + finish %.3f, total %.3f s\n",
+                     n_pairs, n_chunks, workers, team, st.seconds_subsample_upload, gpu_seconds, tail_seconds,
+                     phase_seconds[0], phase_seconds[1], phase_seconds[2], st.seconds_total);
     if (stats)
         *stats = st;
     return relations;
