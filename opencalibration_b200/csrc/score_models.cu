@@ -20,6 +20,7 @@
 #include "ocb_internal.cuh"
 #include "exact_math.cuh"
 
+#include <atomic>
 #include <cfloat>
 
 namespace ocb
@@ -498,16 +499,16 @@ int k2_score(int kind, const double *d_models, size_t h, const double *d_corr4, 
     // option k2_variant: 0 = by size, 1 = always independent CTAs, 2 = always lock-step
     const int v = options().k2_variant;
     const bool lockstep = v == 2 || (v == 0 && groups > 2u * (uint32_t)sms);
-    static bool attr_set_on[64] = {false}; // the attribute is per device
-    bool &attr_set = attr_set_on[dev & 63];
-    if (lockstep && !attr_set)
+    static std::atomic<bool> attr_set_on[64]; // the attribute is per device; setting it twice is harmless
+    std::atomic<bool> &attr_set = attr_set_on[dev & 63];
+    if (lockstep && !attr_set.load(std::memory_order_acquire))
     {
         const int bytes = (int)(K2_SUBS * sizeof(K2Shared));
         OCB_CUDA(cudaFuncSetAttribute(k2_score_kernel<OCB_MODEL_HOMOGRAPHY, 1, K2_SUBS>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
         OCB_CUDA(cudaFuncSetAttribute(k2_score_kernel<OCB_MODEL_ESSENTIAL, 1, K2_SUBS>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-        attr_set = true;
+        attr_set.store(true, std::memory_order_release);
     }
 #define OCB_K2_LAUNCH(KIND, SUBS)                                                                                      \
     k2_score_kernel<KIND, 1, SUBS><<<(groups + SUBS - 1) / SUBS, K2_THREADS * SUBS, SUBS * sizeof(K2Shared), stream>>>( \
