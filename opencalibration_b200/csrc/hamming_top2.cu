@@ -362,7 +362,7 @@ __global__ void __launch_bounds__(K1_THREADS, MINB)
         const uint32_t rows = min((uint32_t)K1_TILE_C, c_cnt - t * K1_TILE_C);
         const uint4 *__restrict__ tl = &tile[s][0];
         const uint32_t k0 = t * K1_TILE_C;
-#pragma unroll 2
+#pragma unroll(Q <= 2 ? 4 : 2)
         for (uint32_t cc = 0; cc < rows; cc++)
         {
             uint4 c[4];
