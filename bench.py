@@ -82,10 +82,10 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(self.mhz)}
 
 
-# K1 instruction mix of the default variant, counted in the SASS of its inner loop: per comparison
-# 27 LOP3 + 3.25 VIMNMX + 2.5 integer adds + 0.5 compare/vote on the ALU pipe (64 lanes/clk/SM), 7 POPC on the XU pipe
-# (16 lanes/clk/SM), 8 IMAD on the FMA pipe; the fused cross-check is ~1.5 of the ALU ops.
-K1_ALU_OPS, K1_XU_OPS = 33.25, 7.0
+# K1 instruction mix of the default variant WITH the fused cross-check, counted in the SASS of its
+# inner loop: per comparison 23 LOP3 + 3.4 VIMNMX + 2 integer adds + 0.2 compare on the ALU pipe (64 lanes/clk/SM),
+# 9 POPC on the XU pipe (16 lanes/clk/SM), 9.75 IMAD on the FMA pipe. (The plain sweep uses 27 LOP3 + 7 POPC.)
+K1_ALU_OPS, K1_XU_OPS = 28.6, 9.0
 # dram__bytes_read.sum + dram__bytes_write.sum of one K1 launch of this workload, from the committed
 # `ncu --set full` capture (profiles/r1s8_k1_ncu_full.csv); null would mean "not captured"
 K1_NCU_DRAM_BYTES = 1501952

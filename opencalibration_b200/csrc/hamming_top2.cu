@@ -566,9 +566,19 @@ struct K1Variant
              {k1_top2_kernel<Q_, F_, A_, false, MINB_, P_, true>, k1_top2_kernel<Q_, F_, A_, true, MINB_, P_, true>}}, \
             "q" #Q_ "f" #F_ "a" #A_ "p" #P_                                                                            \
     }
+// FC_ = adders of the cross-check instantiations: the cross-check's own work sits on the ALU pipe, so its best
+// balance has fewer adders (more POPCs on the XU pipe) than the plain sweep's
+#define K1V2(Q_, F_, FC_, A_, MINB_, P_)                                                                               \
+    {                                                                                                                  \
+        Q_, F_,                                                                                                        \
+            {{k1_top2_kernel<Q_, F_, A_, false, MINB_, P_, false>, k1_top2_kernel<Q_, FC_, A_, true, MINB_, P_, false>},\
+             {k1_top2_kernel<Q_, F_, A_, false, MINB_, P_, true>, k1_top2_kernel<Q_, FC_, A_, true, MINB_, P_, true>}}, \
+            "q" #Q_ "f" #F_ "c" #FC_ "a" #A_ "p" #P_                                                                   \
+    }
 static const K1Variant k1_variants[] = {
-    K1V(2, 9, true, 6, true),    // 0: default: prefix form, 9 adders (27 LOP3 + 7 POPC + 7 IMAD per comparison), two
-                                 //    queries per thread so that six CTAs (24 warps) are resident per SM
+    K1V2(2, 9, 7, true, 6, true), // 0: default: prefix form, two queries per thread so that six CTAs (24 warps) are
+                                  //    resident per SM; 9 adders (27 LOP3 + 7 POPC + 7 IMAD per comparison) for the
+                                  //    plain sweep, 7 (23 LOP3 + 9 POPC + 9 IMAD) with the fused cross-check
     K1V(4, 0, false, 4, false),  // 1: plain 16-POPC form (the "naive POPC roofline" shape)
     K1V(4, 7, true, 4, false),   // 2: first-round default: plain carry-save form, 7 adders (30 LOP3 + 9 POPC)
     K1V(4, 8, true, 4, true),    // 3
