@@ -487,7 +487,7 @@ def run_survey(args):
     sets = [host.FeatureSet(d, xy, st) for d, xy, st in images]
     cams = [survey.camera8()] * len(sets)
     local_pairs = [(local_index[a], local_index[b]) for a, b in shard.pairs]
-    threads = max(1, (os.cpu_count() or 1) // world)
+    threads = max(1, (os.cpu_count() or 1) // world - 1)  # one core per rank stays free for the submission thread
     spacing = args.spacing
 
     def barrier():

@@ -10,6 +10,9 @@
 #include <chrono>
 #include <cstring>
 #include <condition_variable>
+#include <deque>
+#include <functional>
+#include <future>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -104,6 +107,56 @@ void finish_pair(const ocb_host::LinkImage &img, const ocb_host::LinkImage &near
                         relations.inlier_matches);
     }
 }
+
+// Long-lived helper threads for link_pairs (the submission thread and the extra tail consumers). libocb keeps a
+// per-thread context (two streams, device and page-locked staging areas, bound correspondences); a std::thread per
+// call would build and tear that context down every time, which costs tens of milliseconds - far more when the
+// process holds contexts on several GPUs. The threads are created on demand, parked between calls and never joined
+// (the pool is leaked on purpose: they must not run destructors after the CUDA runtime has shut down).
+class HelperThreads
+{
+  public:
+    std::future<void> run(std::function<void()> fn)
+    {
+        std::packaged_task<void()> task(std::move(fn));
+        std::future<void> done = task.get_future();
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            queue_.push_back(std::move(task));
+            if (idle_ < queue_.size())
+                std::thread(&HelperThreads::loop, this).detach();
+        }
+        cv_.notify_one();
+        return done;
+    }
+    static HelperThreads &instance()
+    {
+        static HelperThreads *pool = new HelperThreads;
+        return *pool;
+    }
+
+  private:
+    void loop()
+    {
+        for (;;)
+        {
+            std::packaged_task<void()> task;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                ++idle_;
+                cv_.wait(lk, [&] { return !queue_.empty(); });
+                --idle_;
+                task = std::move(queue_.front());
+                queue_.pop_front();
+            }
+            task();
+        }
+    }
+    std::mutex mu_;
+    std::condition_variable cv_;
+    std::deque<std::packaged_task<void()>> queue_;
+    size_t idle_ = 0;
+};
 } // namespace
 
 namespace ocb_host
@@ -191,7 +244,7 @@ std::vector<camera_relations> link_pairs(const std::vector<LinkImage> &images, c
     LinkStats st;
     st.seconds_subsample_upload = since(t_begin);
 
-    // ---- submissions: one long-lived producer thread keeps the GPU matching the next chunks (into page-locked
+    // ---- submissions: one producer (a parked helper thread, see HelperThreads) keeps the GPU matching the next chunks (into page-locked
     // result buffers, one per slot) while `tail_workers` consumer threads, each with its own OpenMP team, finish the
     // chunks already matched. Several consumers are needed because a chunk's RANSAC rounds are a serial chain of
     // GPU round trips: with one consumer the chain's latency, not the host cores, bounds the tail.
@@ -232,7 +285,7 @@ std::vector<camera_relations> link_pairs(const std::vector<LinkImage> &images, c
     std::mutex mu;
     std::condition_variable cv;
     bool stop = false; // set on the first error: everybody drains
-    std::thread producer([&]() {
+    std::future<void> producer = HelperThreads::instance().run([&]() {
         for (size_t c = 0; c < n_chunks; c++)
         {
             Slot &sl = slot[c % n_slots];
@@ -389,18 +442,18 @@ std::vector<camera_relations> link_pairs(const std::vector<LinkImage> &images, c
             }
         }
     };
-    std::vector<std::thread> consumers;
+    std::vector<std::future<void>> consumers;
     for (int w = 1; w < workers; w++)
-        consumers.emplace_back(consume);
+        consumers.push_back(HelperThreads::instance().run(consume));
     consume();
-    for (std::thread &t : consumers)
-        t.join();
+    for (std::future<void> &t : consumers)
+        t.wait();
     {
         std::lock_guard<std::mutex> lk(mu);
         stop = true;
         cv.notify_all();
     }
-    producer.join();
+    producer.wait();
     st.seconds_match_gpu = gpu_seconds;
     st.seconds_tail = tail_seconds;
     const auto t_release = clock_type::now();
