@@ -88,7 +88,7 @@ class ClockSampler(threading.Thread):
 K1_ALU_OPS, K1_XU_OPS = 28.6, 9.0
 # dram__bytes_read.sum + dram__bytes_write.sum of one K1 launch of this workload, from the committed
 # `ncu --set full` capture (profiles/r1s8_k1_ncu_full.csv); null would mean "not captured"
-K1_NCU_DRAM_BYTES = 1501952
+K1_NCU_DRAM_BYTES = 1512192
 
 
 def roofline(achieved, sm_max, held, peak_src, ms_per_step, peaks):
