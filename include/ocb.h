@@ -218,6 +218,12 @@ extern "C"
      *                               like OCB_REQ_SCORE_ORDERED -> models_out[h][18], degenerate[h], score[h],
      *                               count[h]. This is ransac.cpp:164-196 for h iterations without the host in
      *                               the loop; the fitted models equal the host adapters' fit bit for bit.
+     *   mode OCB_REQ_REFIT_EVALUATE (homography only, h == 1) one step of the local optimisation of
+     *                               src/model_inliers/ransac.cpp:224-245 without the host in between: the model is
+     *                               refitted ON THE DEVICE to the correspondences whose bit is set in refit_bits
+     *                               (homography_model::fitInliers, homography_model.cpp:52-87: the (2m+1) x 9 DLT
+     *                               system, full-pivot LU solve, division by H(2,2), 3x3 inverse) and then evaluated
+     *                               like OCB_REQ_EVALUATE -> models_out[18], score[1], count[1], inlier_bits.
      * Results are bit-identical to ocb_score_models / ocb_residuals on the same inputs. */
     typedef struct ocb_corr_set
     {
@@ -230,7 +236,8 @@ extern "C"
         OCB_REQ_SCORE_ORDERED = 0,
         OCB_REQ_EVALUATE = 1,
         OCB_REQ_RESIDUALS = 2,
-        OCB_REQ_FIT_SCORE_ORDERED = 3
+        OCB_REQ_FIT_SCORE_ORDERED = 3,
+        OCB_REQ_REFIT_EVALUATE = 4
     };
     typedef struct ocb_score_request
     {
@@ -248,6 +255,8 @@ extern "C"
         const uint32_t *samples; /* [h][4] correspondence indices of the minimal samples */
         double *models_out;      /* [h][18] fitted models (NaN for a degenerate sample) */
         uint8_t *degenerate;     /* [h] 1 = the sample failed checkSampleDegeneracy and was not fitted */
+        /* OCB_REQ_REFIT_EVALUATE only (models is ignored, models_out receives the refitted model): */
+        const uint32_t *refit_bits; /* [ceil(n/32)] the inliers to refit to, index order */
     } ocb_score_request;
     int ocb_corr_bind_batch(const ocb_corr_set *sets, size_t count);
     int ocb_score_requests(const ocb_score_request *requests, size_t count);

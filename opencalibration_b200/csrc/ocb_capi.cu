@@ -1359,27 +1359,46 @@ extern "C"
             return rc;
         if (!cx.batch_valid)
             return fail_invalid("no correspondence batch bound on this thread (ocb_corr_bind_batch)");
-        // layout of the per-call device block: [request table][fit jobs][models | samples][outputs]; outputs (for
-        // fit requests: the fitted models and degeneracy flags too) are read back in one copy
-        Carver in_cv, out_cv;
+        // layout of the per-call device block: [request table][fit jobs][refit jobs][models | samples | masks][outputs]
+        // [refit scratch]; outputs (for fit requests: the fitted models and degeneracy flags too) are read back in one copy
+        Carver in_cv, out_cv, scratch_cv;
         const size_t o_tab = in_cv.take(count * sizeof(K2Request));
-        size_t n_fit = 0;
+        size_t n_fit = 0, n_refit = 0;
         for (size_t i = 0; i < count; i++)
+        {
             n_fit += req[i].mode == OCB_REQ_FIT_SCORE_ORDERED;
+            n_refit += req[i].mode == OCB_REQ_REFIT_EVALUATE;
+        }
         const size_t o_jobs = in_cv.take(n_fit * sizeof(K3FitJob));
-        std::vector<size_t> o_models(count), o_score(count), o_count(count), o_aux(count), o_flags(count);
+        const size_t o_rjobs = in_cv.take(n_refit * sizeof(K3InlierJob));
+        std::vector<size_t> o_models(count), o_score(count), o_count(count), o_aux(count), o_flags(count), o_mask(count),
+            o_scratch(count);
         for (size_t i = 0; i < count; i++)
         {
             const ocb_score_request &r = req[i];
-            if (r.kind < 0 || r.kind > 2 || r.mode < 0 || r.mode > 3)
+            if (r.kind < 0 || r.kind > 2 || r.mode < 0 || r.mode > 4)
                 return fail_invalid("request kind / mode");
             if (r.set >= cx.batch_sets.size())
                 return fail_invalid("request references an unbound set");
             const ThreadCtx::BatchSet &bs = cx.batch_sets[r.set];
             const bool fit = r.mode == OCB_REQ_FIT_SCORE_ORDERED;
-            if (r.h == 0 || (!fit && !r.models) || (r.mode == 2 && (r.h != 1 || !r.residuals)) ||
-                (r.mode != 2 && (!r.score || !r.count)) || (r.mode == 1 && !r.inlier_bits))
+            const bool refit = r.mode == OCB_REQ_REFIT_EVALUATE;
+            if (r.h == 0 || (!fit && !refit && !r.models) || (r.mode == 2 && (r.h != 1 || !r.residuals)) ||
+                (r.mode != 2 && (!r.score || !r.count)) || ((r.mode == 1 || refit) && !r.inlier_bits))
                 return fail_invalid("request pointers");
+            if (refit)
+            {
+                if (r.kind != OCB_MODEL_HOMOGRAPHY || r.h != 1 || !r.refit_bits || !r.models_out)
+                    return fail_invalid("refit request: homography only, h == 1; refit_bits and models_out are required");
+                const size_t words = (bs.n + 31) / 32;
+                o_mask[i] = in_cv.take(words * sizeof(uint32_t));
+                o_models[i] = out_cv.take(18 * sizeof(double));
+                o_score[i] = out_cv.take(sizeof(double));
+                o_count[i] = out_cv.take(sizeof(uint32_t));
+                o_aux[i] = out_cv.take(words * sizeof(uint32_t));
+                o_scratch[i] = scratch_cv.take(k3_inlier_scratch_bytes(bs.n));
+                continue;
+            }
             if (fit && (r.kind != OCB_MODEL_HOMOGRAPHY || !r.samples || !r.models_out || !r.degenerate))
                 return fail_invalid("fit request: homography only; samples, models_out and degenerate are required");
             if ((r.mode == 0 || fit) && !bs.has_order && bs.n)
@@ -1408,25 +1427,39 @@ extern "C"
             }
         }
         const size_t in_bytes = in_cv.off, out_bytes = out_cv.off;
-        if ((rc = cx.dev_reserve(in_bytes + out_bytes)) || (rc = cx.pinned_reserve(in_bytes + out_bytes)))
+        if ((rc = cx.dev_reserve(in_bytes + out_bytes + scratch_cv.off)) || (rc = cx.pinned_reserve(in_bytes + out_bytes)))
             return rc;
         char *d = static_cast<char *>(cx.dev.p);
         char *d_out = d + in_bytes;
+        char *d_scratch = d_out + out_bytes;
         char *hp = static_cast<char *>(cx.pinned.p);
         char *b = static_cast<char *>(cx.batch.p);
         K2Request *tab = reinterpret_cast<K2Request *>(hp + o_tab);
         K3FitJob *jobs = reinterpret_cast<K3FitJob *>(hp + o_jobs);
+        K3InlierJob *rjobs = reinterpret_cast<K3InlierJob *>(hp + o_rjobs);
         uint32_t ctas = 0, fit_total = 0;
-        size_t j = 0;
+        size_t j = 0, jr = 0;
         for (size_t i = 0; i < count; i++)
         {
             const ocb_score_request &r = req[i];
             const ThreadCtx::BatchSet &bs = cx.batch_sets[r.set];
             const bool fit = r.mode == OCB_REQ_FIT_SCORE_ORDERED;
+            const bool refit = r.mode == OCB_REQ_REFIT_EVALUATE;
             K2Request q;
             memset(&q, 0, sizeof q);
             q.c7 = reinterpret_cast<const double *>(b + bs.o_c7);
-            if (fit)
+            if (refit)
+            {
+                memcpy(hp + o_mask[i], r.refit_bits, (bs.n + 31) / 32 * sizeof(uint32_t));
+                K3InlierJob &job = rjobs[jr++];
+                job.c7 = q.c7;
+                job.bits = reinterpret_cast<const uint32_t *>(d + o_mask[i]);
+                job.P = reinterpret_cast<double *>(d_scratch + o_scratch[i]);
+                job.model_out = reinterpret_cast<double *>(d_out + o_models[i]);
+                job.n = (uint32_t)bs.n;
+                q.models = job.model_out;
+            }
+            else if (fit)
             {
                 memcpy(hp + o_aux[i], r.samples, (size_t)r.h * 4 * sizeof(uint32_t));
                 K3FitJob &job = jobs[j++];
@@ -1446,14 +1479,15 @@ extern "C"
             q.order = ((r.mode == 0 || fit) && bs.has_order) ? reinterpret_cast<const uint32_t *>(b + bs.o_ord) : nullptr;
             q.thr = r.thr;
             q.h = r.h, q.n = (uint32_t)bs.n, q.words = (uint32_t)((bs.n + 31) / 32);
-            q.kind = r.kind, q.mode = fit ? 0 : r.mode; // a fit request is scored like OCB_REQ_SCORE_ORDERED
+            // a fit request is scored like OCB_REQ_SCORE_ORDERED, a refit request evaluated like OCB_REQ_EVALUATE
+            q.kind = r.kind, q.mode = fit ? 0 : (refit ? 1 : r.mode);
             if (r.mode == 2)
                 q.e = reinterpret_cast<double *>(d_out + o_aux[i]);
             else
             {
                 q.score = reinterpret_cast<double *>(d_out + o_score[i]);
                 q.count = reinterpret_cast<uint32_t *>(d_out + o_count[i]);
-                q.bits = r.mode == 1 ? reinterpret_cast<uint32_t *>(d_out + o_aux[i]) : nullptr;
+                q.bits = (r.mode == 1 || refit) ? reinterpret_cast<uint32_t *>(d_out + o_aux[i]) : nullptr;
             }
             q.cta_begin = ctas;
             ctas += k2_request_ctas(q);
@@ -1461,6 +1495,8 @@ extern "C"
         }
         OCB_CUDA(cudaMemcpyAsync(d, hp, in_bytes, cudaMemcpyHostToDevice, cx.stream));
         if (n_fit && (rc = k3_fit_samples(reinterpret_cast<const K3FitJob *>(d + o_jobs), n_fit, fit_total, cx.stream)))
+            return rc;
+        if (n_refit && (rc = k3_fit_inliers(reinterpret_cast<const K3InlierJob *>(d + o_rjobs), n_refit, cx.stream)))
             return rc;
         if ((rc = k2_run_requests(reinterpret_cast<const K2Request *>(d + o_tab), count, ctas, cx.stream)))
             return rc;
@@ -1478,8 +1514,10 @@ extern "C"
             {
                 memcpy(r.score, hout + o_score[i], (size_t)r.h * sizeof(double));
                 memcpy(r.count, hout + o_count[i], (size_t)r.h * sizeof(uint32_t));
-                if (r.mode == 1)
+                if (r.mode == 1 || r.mode == OCB_REQ_REFIT_EVALUATE)
                     memcpy(r.inlier_bits, hout + o_aux[i], (size_t)r.h * words * sizeof(uint32_t));
+                if (r.mode == OCB_REQ_REFIT_EVALUATE)
+                    memcpy(r.models_out, hout + o_models[i], 18 * sizeof(double));
                 if (r.mode == OCB_REQ_FIT_SCORE_ORDERED)
                 {
                     memcpy(r.models_out, hout + o_models[i], (size_t)r.h * 18 * sizeof(double));

@@ -128,6 +128,17 @@ struct K3FitJob
     uint32_t h, begin;       // begin = index of this job's first hypothesis in the launch
 };
 int k3_fit_samples(const K3FitJob *d_jobs, size_t n_jobs, uint32_t total, cudaStream_t stream);
+// One all-inlier refit (homography_model::fitInliers): the correspondences whose bit is set in `bits` (index order).
+struct K3InlierJob
+{
+    const double *c7;     // [n][7] correspondences as given
+    const uint32_t *bits; // [ceil(n/32)] inlier mask in index order
+    double *P;            // scratch for the (2m+1) x 9 system: room for (2n+1) * 9 doubles
+    double *model_out;    // [18]
+    uint32_t n;
+};
+size_t k3_inlier_scratch_bytes(size_t n);
+int k3_fit_inliers(const K3InlierJob *d_jobs, size_t n_jobs, cudaStream_t stream);
 
 // ---- PTX helpers: mbarrier + 1-D bulk (TMA) copies -----------------------------------------------------------
 #if defined(__CUDACC__)

@@ -195,7 +195,9 @@ template <typename Model> class RansacRun
         FIT_SCORE_BATCH, // request_samples(): want x 4 indices -> fitted on the device into batch_m18 / batch_skip,
                          // then scored like SCORE_BATCH (homography only)
         RESIDUALS,   // request_models(): 1 x 18                      -> residual[N]
-        EVALUATE     // request_models(): 1 x 18, index order         -> eval_score, eval_bits
+        EVALUATE,    // request_models(): 1 x 18, index order         -> eval_score, eval_bits
+        REFIT_EVALUATE // refit_bits (the current inliers): fitInliers on the device -> refit_m18, then like EVALUATE
+                       // (homography only; drivers that cannot serve it leave device_refit off)
     };
 
     RansacRun(const std::vector<correspondence> &matches_, Model &model_, std::vector<bool> &inliers_)
@@ -370,11 +372,9 @@ template <typename Model> class RansacRun
                     state = State::AFTER_DEGEN_EVAL;
                     return Need::EVALUATE;
                 }
-                model.fitInliers(matches, inliers); // ransac.cpp:224
                 lo_round = 0;
-                request_evaluate();
                 state = State::AFTER_LO_EVAL;
-                return Need::EVALUATE;
+                return refit_and_evaluate(); // ransac.cpp:224
             }
 
             case State::AFTER_DEGEN_EVAL: {
@@ -384,15 +384,18 @@ template <typename Model> class RansacRun
                     best_model = model;
                     best_score = degen_score;
                 }
-                model.fitInliers(matches, inliers);
                 lo_round = 0;
-                request_evaluate();
                 state = State::AFTER_LO_EVAL;
-                return Need::EVALUATE;
+                return refit_and_evaluate();
             }
 
             case State::AFTER_LO_EVAL: {
                 // ransac.cpp:225-245: keep refitting on the inliers of the last evaluate while the score improves
+                if (pending_refit)
+                {
+                    unpack_model(refit_m18, model); // fitted on the device
+                    pending_refit = false;
+                }
                 const double inlier_score = take_evaluate();
                 const bool better = inlier_score > best_score;
                 if (better)
@@ -403,9 +406,7 @@ template <typename Model> class RansacRun
                 if (better && lo_round + 1 < MAX_INNER_ITERATIONS)
                 {
                     lo_round++;
-                    model.fitInliers(matches, inliers);
-                    request_evaluate();
-                    return Need::EVALUATE;
+                    return refit_and_evaluate();
                 }
                 const double omega = best_score / N; // ransac.cpp:247-251
                 const double omega_n = small_pow<(int)K>(omega);
@@ -438,6 +439,10 @@ template <typename Model> class RansacRun
     std::vector<uint32_t> batch_count, eval_bits;
     double eval_score = 0;
     uint32_t eval_count = 0;
+    // ---- all-inlier refits on the device (set by drivers that serve Need::REFIT_EVALUATE)
+    bool device_refit = false;
+    std::vector<uint32_t> refit_bits; // the inliers to refit to, index order
+    double refit_m18[18];             // the refitted model
 
   private:
     enum class State
@@ -457,6 +462,28 @@ template <typename Model> class RansacRun
     {
         b++, i++;
         state = State::SCAN;
+    }
+    // model.fitInliers(matches, inliers) followed by the evaluate request (ransac.cpp:224-226, :233-235)
+    Need refit_and_evaluate()
+    {
+        if constexpr (is_homography<Model>)
+        {
+            if (device_refit)
+            {
+                refit_bits.assign((N + 31) / 32, 0u);
+                for (size_t k = 0; k < N; k++)
+                    if (inliers[k])
+                        refit_bits[k >> 5] |= 1u << (k & 31);
+                pending_refit = true;
+                request_m18 = nullptr;
+                request_h = 1;
+                stats.gpu_calls++;
+                return Need::REFIT_EVALUATE;
+            }
+        }
+        model.fitInliers(matches, inliers);
+        request_evaluate();
+        return Need::EVALUATE;
     }
     void request_evaluate()
     {
@@ -484,6 +511,7 @@ template <typename Model> class RansacRun
     size_t batch = 32; // grows geometrically: the adaptive stop usually fires within the first batches
     size_t b = 0;      // cursor in the current batch
     size_t lo_round = 0;
+    bool pending_refit = false;
     const bool device_fit = is_homography<Model> && ransac_device_fit();
     size_t batch_size = 0;
     std::vector<Model> batch_models; // host fits only; empty when the batch was fitted on the device
@@ -528,6 +556,7 @@ double ransac(const std::vector<correspondence> &matches, Model &model, std::vec
             gpu_evaluate_bits(run.kind, run.request_models(), run.thr, matches, &run.eval_score, &run.eval_count,
                               run.eval_bits.data());
             break;
+        case Need::REFIT_EVALUATE: // never requested: device_refit is off in this driver
         case Need::DONE:
             break;
         }
@@ -555,7 +584,10 @@ template <typename Model> void ransac_batch(std::vector<RansacJob<Model>> &jobs,
     std::string error;
 #pragma omp parallel for schedule(dynamic, 1) num_threads(threads)
     for (size_t j = 0; j < n_jobs; j++)
+    {
         runs[j].reset(new Run(*jobs[j].matches, *jobs[j].model, *jobs[j].inliers));
+        runs[j]->device_refit = opencalibration::ransac_device_fit(); // only the homography run ever asks for it
+    }
     std::vector<ocb_corr_set> sets(n_jobs);
     std::vector<size_t> active;
     for (size_t j = 0; j < n_jobs; j++)
@@ -573,7 +605,7 @@ template <typename Model> void ransac_batch(std::vector<RansacJob<Model>> &jobs,
     std::vector<ocb_score_request> requests;
     static const bool profile = std::getenv("OCB_RANSAC_PROFILE") != nullptr;
     double t_host = 0, t_gpu = 0;
-    size_t rounds = 0, n_req[5] = {0, 0, 0, 0, 0};
+    size_t rounds = 0, n_req[6] = {0, 0, 0, 0, 0, 0};
     auto now = [] { return std::chrono::steady_clock::now(); };
     auto secs = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
         return std::chrono::duration<double>(b - a).count();
@@ -620,6 +652,9 @@ template <typename Model> void ransac_batch(std::vector<RansacJob<Model>> &jobs,
             else if (need[j] == Need::FIT_SCORE_BATCH)
                 q.mode = OCB_REQ_FIT_SCORE_ORDERED, q.samples = r.request_samples(), q.models_out = r.fitted_models(),
                 q.degenerate = r.fitted_degenerate(), q.score = r.batch_score.data(), q.count = r.batch_count.data();
+            else if (need[j] == Need::REFIT_EVALUATE)
+                q.mode = OCB_REQ_REFIT_EVALUATE, q.refit_bits = r.refit_bits.data(), q.models_out = r.refit_m18,
+                q.score = &r.eval_score, q.count = &r.eval_count, q.inlier_bits = r.eval_bits.data();
             else if (need[j] == Need::RESIDUALS)
                 q.mode = OCB_REQ_RESIDUALS, q.residuals = r.residual.data();
             else
@@ -641,8 +676,8 @@ template <typename Model> void ransac_batch(std::vector<RansacJob<Model>> &jobs,
     if (profile)
         std::fprintf(stderr,
                      "[ocb ransac_batch] jobs %zu threads %d rounds %zu host %.3f ms gpu %.3f ms requests: score %zu "
-                     "evaluate %zu residuals %zu fit+score %zu\n",
-                     n_jobs, threads, rounds, t_host * 1e3, t_gpu * 1e3, n_req[0], n_req[1], n_req[2], n_req[3]);
+                     "evaluate %zu residuals %zu fit+score %zu refit+evaluate %zu\n",
+                     n_jobs, threads, rounds, t_host * 1e3, t_gpu * 1e3, n_req[0], n_req[1], n_req[2], n_req[3], n_req[4]);
 }
 template void ransac_batch(std::vector<RansacJob<opencalibration::homography_model>> &, int);
 template void ransac_batch(std::vector<RansacJob<opencalibration::fundamental_matrix_model>> &, int);

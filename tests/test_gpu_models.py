@@ -296,6 +296,32 @@ def test_ransac_batch_equals_single_runs(gpu, hostlib, oracle):
             assert st["iterations"] == st1["iterations"] and st["improvements"] == st1["improvements"]
 
 
+def test_device_refit_equals_host_refit(gpu, hostlib, oracle):
+    """The lock-step driver refits on the device (OCB_REQ_REFIT_EVALUATE: homography_model::fitInliers,
+    homography_model.cpp:52-87, a (2m+1) x 9 full-pivot LU per image pair), the single-run driver on the host; models,
+    inlier sets, scores and iteration counts must be identical for every system size, including systems shorter than
+    nine rows, all-inlier sets, repeated points and outlier-dominated sets."""
+    rng = np.random.default_rng(21)
+    scenes = []
+    for n_in, n_out, seed in ((4, 0, 1), (5, 1, 2), (9, 0, 3), (33, 31, 4), (257, 3, 5), (2100, 0, 6), (1500, 900, 7),
+                              (64, 600, 8)):
+        scenes.append(oracle.scene_homography(n_in, n_out, seed)[0])
+    dup = oracle.scene_homography(120, 40, 9)[0].copy()
+    dup[10:60] = dup[10]                      # fifty copies of one correspondence
+    scenes.append(dup)
+    noisy = oracle.scene_homography(800, 200, 10)[0].copy()
+    noisy[:, 0:2] += rng.normal(0, 2e-4, (len(noisy), 2))
+    scenes.append(noisy)
+    batch = hostlib.ransac_batch(0, scenes, threads=4)
+    for c, (s, M, inl, st) in zip(scenes, batch):
+        s1, M1, inl1, st1 = hostlib.ransac(0, c)
+        assert s == s1 and np.array_equal(inl, inl1[:len(c)])
+        assert np.array_equal(M, M1, equal_nan=True)
+        assert st["iterations"] == st1["iterations"] and st["improvements"] == st1["improvements"]
+        so, Mo, io, tr = oracle.ransac(0, c)
+        assert s == so and np.array_equal(M, Mo, equal_nan=True) and np.array_equal(inl, io)
+
+
 def test_device_fit_bit_exact(gpu, oracle):
     # K3: checkSampleDegeneracy + fit on the device (homography_model.cpp:19-50,120-136) against the oracle's fit:
     # identical models (H and H^-1), identical degeneracy verdicts; repeated points, collinear triples, rank-deficient
