@@ -175,87 +175,116 @@ std::vector<camera_relations> link_pairs(const std::vector<LinkImage> &images, c
             throw std::invalid_argument("link_pairs: image without features");
 
     // ---- per image, once: the subsample every closure of that image would compute (link_stage.cpp:63-65,80-81) and
-    // the upload of those rows. Only images that occur in a pair are touched.
-    std::vector<char> used(n_img, 0);
-    for (const LinkPair &p : pairs)
-        used[p.image_1] = used[p.image_2] = 1;
+    // the upload of those rows. Only images that occur in a pair are touched. The images are prepared in the order
+    // in which the submissions need them, by a helper thread that runs ahead of the matching: the first submission
+    // starts as soon as its own images are resident, and the rest of the preparation hides behind the GPU.
+    const size_t per = std::max<size_t>(1, options.pairs_per_submission);
+    const size_t n_chunks = (n_pairs + per - 1) / per;
+    std::vector<size_t> order;               // used images, by first use
+    std::vector<size_t> position(n_img, ~(size_t)0); // image -> index in `order`
+    std::vector<size_t> chunk_needs(n_chunks, 0);    // images of `order` that must be resident before chunk c starts
+    for (size_t c = 0; c < n_chunks; c++)
+    {
+        for (size_t p = c * per; p < std::min(n_pairs, (c + 1) * per); p++)
+            for (size_t i : {pairs[p].image_1, pairs[p].image_2})
+                if (position[i] == ~(size_t)0)
+                {
+                    position[i] = order.size();
+                    order.push_back(i);
+                }
+        chunk_needs[c] = order.size();
+    }
     std::vector<std::vector<size_t>> indices(n_img);
     const uint64_t id_base = g_next_set_id.fetch_add(n_img + 1);
     std::string error;
-    // every worker (and the submission thread) runs on the process's default device: the one of its first ocb_init
-#pragma omp parallel for schedule(dynamic, 1) num_threads(threads)
-    for (size_t i = 0; i < n_img; i++)
-    {
-        if (!used[i])
-            continue;
-        try
-        {
-            indices[i] = spatially_subsample_feature_indices(*images[i].features, options.coarse_spacing_pixels,
-                                                             images[i].num_sparse_features);
-        }
-        catch (const std::exception &e)
-        {
-#pragma omp critical(ocb_link_error)
-            error = e.what();
-        }
-    }
-    // upload: one batched registration (one device allocation, pipelined gather + copy) per worker, rows taken
-    // straight from the feature vectors through the subsample indices
-    std::vector<size_t> used_ids;
-    for (size_t i = 0; i < n_img; i++)
-        if (used[i])
-            used_ids.push_back(i);
     std::vector<char> registered(n_img, 0);
-    const int groups = (int)std::min<size_t>((size_t)std::min(threads, 8), std::max<size_t>(used_ids.size(), 1));
-    if (error.empty())
-    {
-#pragma omp parallel for schedule(static, 1) num_threads(groups)
-        for (int g = 0; g < groups; g++)
+    std::mutex mu;
+    std::condition_variable cv;
+    bool stop = false;       // set on the first error: everybody drains
+    size_t prepared = 0;     // images of `order` that are subsampled and resident
+    double prepare_seconds = 0;
+    // every worker (and the helper threads) runs on the process's default device: the one of its first ocb_init
+    std::future<void> preparer = HelperThreads::instance().run([&]() {
+        const size_t batch = (size_t)std::max(32, 4 * threads);
+        for (size_t begin = 0; begin < order.size(); begin += batch)
         {
-            std::vector<ocb_set_source> src;
-            for (size_t u = (size_t)g; u < used_ids.size(); u += (size_t)groups)
             {
-                const size_t i = used_ids[u];
-                const std::vector<feature_2d> &f = *images[i].features;
-                src.push_back(ocb_set_source{id_base + i, f.empty() ? nullptr : static_cast<const void *>(&f[0].descriptor),
-                                             sizeof(feature_2d), indices[i].data(), indices[i].size()});
+                std::lock_guard<std::mutex> lk(mu);
+                if (stop)
+                    return;
             }
-            const int rc = ocb_register_descriptors_batch(src.data(), src.size());
-#pragma omp critical(ocb_link_error)
+            const auto t0 = clock_type::now();
+            const size_t end = std::min(order.size(), begin + batch);
+            std::string local_error;
+#pragma omp parallel for schedule(dynamic, 1) num_threads(threads)
+            for (size_t u = begin; u < end; u++)
             {
-                if (rc)
-                    error = std::string("ocb_register_descriptors_batch: ") + ocb_last_error();
+                const size_t i = order[u];
+                try
+                {
+                    indices[i] = spatially_subsample_feature_indices(*images[i].features, options.coarse_spacing_pixels,
+                                                                     images[i].num_sparse_features);
+                }
+                catch (const std::exception &e)
+                {
+#pragma omp critical(ocb_link_error)
+                    local_error = e.what();
+                }
+            }
+            // upload: one batched registration (one device allocation, pipelined gather + copy), rows taken straight
+            // from the feature vectors through the subsample indices
+            if (local_error.empty())
+            {
+                std::vector<ocb_set_source> src;
+                for (size_t u = begin; u < end; u++)
+                {
+                    const size_t i = order[u];
+                    const std::vector<feature_2d> &f = *images[i].features;
+                    src.push_back(ocb_set_source{id_base + i,
+                                                 f.empty() ? nullptr : static_cast<const void *>(&f[0].descriptor),
+                                                 sizeof(feature_2d), indices[i].data(), indices[i].size()});
+                }
+                if (ocb_register_descriptors_batch(src.data(), src.size()))
+                    local_error = std::string("ocb_register_descriptors_batch: ") + ocb_last_error();
                 else
                     for (const ocb_set_source &sset : src)
                         registered[sset.set_id - id_base] = 1;
             }
+            std::lock_guard<std::mutex> lk(mu);
+            prepare_seconds += since(t0);
+            if (!local_error.empty())
+            {
+                if (error.empty())
+                    error = local_error;
+                stop = true;
+            }
+            else
+                prepared = end;
+            cv.notify_all();
+            if (stop)
+                return;
         }
-    }
+    });
     auto release_sets = [&]() {
         for (size_t i = 0; i < n_img; i++)
             if (registered[i])
                 ocb_unregister_descriptors(id_base + i);
     };
-    if (!error.empty())
-    {
-        release_sets();
-        throw std::runtime_error(error);
-    }
     LinkStats st;
-    st.seconds_subsample_upload = since(t_begin);
 
-    // ---- submissions: one producer (a parked helper thread, see HelperThreads) keeps the GPU matching the next chunks (into page-locked
-    // result buffers, one per slot) while `tail_workers` consumer threads, each with its own OpenMP team, finish the
-    // chunks already matched. Several consumers are needed because a chunk's RANSAC rounds are a serial chain of
-    // GPU round trips: with one consumer the chain's latency, not the host cores, bounds the tail.
-    const size_t per = std::max<size_t>(1, options.pairs_per_submission);
-    const size_t n_chunks = (n_pairs + per - 1) / per;
-    size_t max_rows = 1;
+    // ---- submissions: one producer (a parked helper thread, see HelperThreads) keeps the GPU matching the next
+    // chunks (into page-locked result buffers, one per slot) while `tail_workers` consumer threads, each with its own
+    // OpenMP team, finish the chunks already matched. Several consumers are needed because a chunk's RANSAC rounds
+    // are a serial chain of GPU round trips: with one consumer the chain's latency, not the host cores, bounds the tail.
+    size_t max_rows = 1; // upper bound: the subsample keeps at most the sparse features of an image
     for (size_t c = 0; c < n_chunks; c++)
     {
         size_t rows = 0;
         for (size_t p = c * per; p < std::min(n_pairs, (c + 1) * per); p++)
-            rows += indices[pairs[p].image_1].size();
+        {
+            const LinkImage &im = images[pairs[p].image_1];
+            rows += im.num_sparse_features ? std::min(im.num_sparse_features, im.features->size()) : im.features->size();
+        }
         max_rows = std::max(max_rows, rows);
     }
     const int workers = options.run_ransac ? std::max(1, std::min(options.tail_workers, threads)) : 1;
@@ -275,23 +304,25 @@ std::vector<camera_relations> link_pairs(const std::vector<LinkImage> &images, c
     ResultBuffers buffers = take_result_buffers(n_slots, max_rows * sizeof(ocb_top2));
     if (buffers.p.size() != n_slots)
     {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            stop = true;
+        }
+        preparer.wait();
         give_back_result_buffers(buffers);
         release_sets();
         throw std::runtime_error(std::string("ocb_host_alloc: ") + ocb_last_error());
     }
     for (size_t k = 0; k < n_slots; k++)
         slot[k].top = static_cast<ocb_top2 *>(buffers.p[k]);
-    st.seconds_setup = since(t_begin) - st.seconds_subsample_upload;
-    std::mutex mu;
-    std::condition_variable cv;
-    bool stop = false; // set on the first error: everybody drains
+    st.seconds_setup = since(t_begin);
     std::future<void> producer = HelperThreads::instance().run([&]() {
         for (size_t c = 0; c < n_chunks; c++)
         {
             Slot &sl = slot[c % n_slots];
             {
                 std::unique_lock<std::mutex> lk(mu);
-                cv.wait(lk, [&] { return !sl.full || stop; });
+                cv.wait(lk, [&] { return (!sl.full && prepared >= chunk_needs[c]) || stop; });
                 if (stop)
                     return;
             }
@@ -454,6 +485,8 @@ std::vector<camera_relations> link_pairs(const std::vector<LinkImage> &images, c
         cv.notify_all();
     }
     producer.wait();
+    preparer.wait();
+    st.seconds_subsample_upload = prepare_seconds; // overlapped with the matching after the first submission
     st.seconds_match_gpu = gpu_seconds;
     st.seconds_tail = tail_seconds;
     const auto t_release = clock_type::now();
