@@ -2,10 +2,11 @@
 // (image, neighbour) pair (reference src/pipeline/link_stage.cpp:63-65,75-112), for a whole batch of pairs at once.
 //   reference: one closure per pair on an OpenMP worker: subsample -> match_features_subset -> distort_keypoints ->
 //              ransac<homography_model> -> decompose -> assembleInliers, all on that worker's core;
-//   here:      the packed descriptor rows of every image are uploaded ONCE (ocb_register_descriptors), the pairs are
-//              matched in large submissions (ocb_match_pairs: one K1 launch per submission), and the per-pair tail
-//              (ratio test + sort, rays, RANSAC with GPU scoring, decomposition, inlier assembly) runs on OpenMP
-//              workers while the next submission is on the GPU.
+//   here:      the packed descriptor rows of every image are uploaded ONCE (ocb_register_descriptors), in the order
+//              of first use and ahead of the matching; the pairs are matched in large submissions (ocb_match_pairs:
+//              one K1 launch per submission), and the per-pair tail (ratio test + sort, rays, RANSAC with device
+//              fits, refits and scoring, decomposition, inlier assembly) runs on OpenMP workers while the next
+//              submission is on the GPU.
 // Results are returned in pair order (the order LinkStage::finalize restores, link_stage.cpp:119-131) and are
 // identical to running the reference-signature functions of opencalibration_api.hpp pair by pair.
 #pragma once
