@@ -89,6 +89,9 @@ K1_ALU_OPS, K1_XU_OPS = 28.6, 9.0
 # dram__bytes_read.sum + dram__bytes_write.sum of one K1 launch of this workload, from the committed
 # `ncu --set full` capture (profiles/r1s8_k1_ncu_full.csv); null would mean "not captured"
 K1_NCU_DRAM_BYTES = 1512192
+# pipe utilisation of the same capture (sm__inst_executed_pipe_{xu,alu}.avg.pct_of_peak_sustained_active)
+K1_NCU_PIPES = {"xu_pct_of_peak": 86.4, "alu_pct_of_peak": 69.2, "issue_slots_pct": 64.0,
+                "source": "profiles/r1s8_k1_ncu_full.csv"}
 
 
 def roofline(achieved, sm_max, held, peak_src, ms_per_step, peaks):
@@ -104,7 +107,7 @@ def roofline(achieved, sm_max, held, peak_src, ms_per_step, peaks):
             "peak_source": f"148 SMs x 16 POPC/clk/SM (probed on this pool: 16.0) x {sm_max:.0f} MHz "
                            f"({peak_src} sm_max_mhz) / 16 POPC per comparison (plain XOR+POPC form)",
             "frac_at_held_clock": achieved / (148 * 16 * held * 1e6 / 16 / 1e9),
-            "mix_peak": mix_peak, "mix_frac": achieved / mix_peak,
+            "mix_peak": mix_peak, "mix_frac": achieved / mix_peak, "ncu_pipes": K1_NCU_PIPES,
             "mix": {"alu_ops_per_cmp": K1_ALU_OPS, "xu_ops_per_cmp": K1_XU_OPS,
                     "note": "prefix carry-save form trades POPCs for LOP3s, so it exceeds the plain-POPC roofline; "
                             "mix_peak = 148 SMs x clock / max(alu/64, xu/16)"},
