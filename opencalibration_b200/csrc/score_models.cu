@@ -228,28 +228,37 @@ __device__ __forceinline__ void score_group(K2Shared &sm, const double *__restri
     __syncthreads();
 
     const uint32_t rounds = (n + K2_TP - 1) / K2_TP;
-    if (SUBS > 1 && nh == 0)
+    // One loop over the rounds for both roles (and for groups without work), so that the lock-step barrier is ONE
+    // __syncthreads reached by every thread of the CTA under a CTA-uniform condition.
+    const bool active = nh > 0;
+    const bool computes = warp < K2_CW;
+    auto load_corr = [&](uint32_t r) {
+        const uint32_t p = r * K2_TP + warp * 32 + lane;
+        const uint32_t pc = p < n ? p : n - 1; // lanes past the end recompute the last position (never inliers)
+        if (corr4)
+            return corr4[pc];
+        return normalise_corr(c7 + (size_t)(order ? order[pc] : pc) * 7);
+    };
+    double r_thr = 0.0;     // compute warps: reciprocal shared by every MSAC contribution of this thread
+    uint32_t thr_rng = 0;
+    double4 c_next = make_double4(0, 0, 0, 0);
+    if (active && computes)
     {
-        for (uint32_t r = K2_LOCKSTEP; r < rounds; r += K2_LOCKSTEP)
-            __syncthreads();
-        return;
+        r_thr = rcp_refined(thr);
+        thr_rng = range_key(thr);
+        if (rounds)
+            c_next = load_corr(0);
     }
-    if (warp < K2_CW)
+    double s = 0.0; // sum warp: lane g accumulates hypothesis g
+    uint32_t cnt = 0;
+    for (uint32_t r = 0; r < rounds; r++)
     {
-        const double r_thr = rcp_refined(thr); // shared by every MSAC contribution of this thread
-        const uint32_t thr_rng = range_key(thr);
-        auto load_corr = [&](uint32_t r) {
-            const uint32_t p = r * K2_TP + warp * 32 + lane;
-            const uint32_t pc = p < n ? p : n - 1; // lanes past the end recompute the last position (never inliers)
-            if (corr4)
-                return corr4[pc];
-            return normalise_corr(c7 + (size_t)(order ? order[pc] : pc) * 7);
-        };
-        double4 c_next = rounds ? load_corr(0) : make_double4(0, 0, 0, 0);
-        for (uint32_t r = 0; r < rounds; r++)
+        if (SUBS > 1 && r > 0 && r % K2_LOCKSTEP == 0)
+            __syncthreads();
+        if (!active)
+            continue;
+        if (computes)
         {
-            if (SUBS > 1 && r > 0 && r % K2_LOCKSTEP == 0)
-                __syncthreads();
             const uint32_t b = r & 1;
             const uint32_t p = r * K2_TP + warp * 32 + lane;
             const bool valid = p < n;
@@ -292,17 +301,10 @@ __device__ __forceinline__ void score_group(K2Shared &sm, const double *__restri
             }
             __syncwarp();
             if (lane == 0)
-                mbar_arrive(&sm.full_bar[b]);
+                mbar_arrive(&sm.full_bar[r & 1]);
         }
-    }
-    else
-    {
-        double s = 0.0;
-        uint32_t cnt = 0;
-        for (uint32_t r = 0; r < rounds; r++)
+        else
         {
-            if (SUBS > 1 && r > 0 && r % K2_LOCKSTEP == 0)
-                __syncthreads();
             const uint32_t b = r & 1;
             mbar_wait(&sm.full_bar[b], (r >> 1) & 1);
             if (lane < nh)
@@ -325,13 +327,13 @@ __device__ __forceinline__ void score_group(K2Shared &sm, const double *__restri
             }
             __syncwarp();
             if (lane == 0)
-                mbar_arrive(&sm.empty_bar[b]);
+                mbar_arrive(&sm.empty_bar[r & 1]);
         }
-        if (lane < nh)
-        {
-            score[h0 + lane] = s;
-            count[h0 + lane] = cnt;
-        }
+    }
+    if (active && !computes && lane < nh)
+    {
+        score[h0 + lane] = s;
+        count[h0 + lane] = cnt;
     }
 }
 
