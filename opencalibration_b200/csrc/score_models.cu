@@ -199,8 +199,8 @@ struct K2Shared
 // barrier per round): a compute warp may run up to two rounds ahead of the slowest one. Ordering: a warp's slab
 // accesses -> __syncwarp -> lane 0's mbarrier.arrive (release.cta) -> the other side's try_wait.parity (acquire.cta).
 // A barrier is never more than one phase ahead of a waiter, so the parity test is unambiguous. (compute-sanitizer's
-// racecheck does not follow try_wait.parity phases and lists the slab accesses as hazards; memcheck is clean and the
-// scores are compared bit for bit against the oracle in every test.)
+// racecheck does not follow try_wait.parity phases and lists the slab accesses as hazards; memcheck and synccheck are
+// clean and the scores are compared bit for bit against the oracle in every test.)
 // SUBS > 1: the CTA holds SUBS such groups side by side (256 threads each, `sm` is this thread's group); nh == 0 marks a
 // group without work. The groups of one CTA meet at a CTA-wide barrier every K2_LOCKSTEP rounds so that none of them
 // runs ahead: four independent CTAs per SM drift apart (the warp scheduler favours the oldest), the early ones retire
