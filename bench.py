@@ -529,6 +529,19 @@ def run_survey(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(agg, op=dist.ReduceOp.SUM)
     summaries = sharding.gather_results(shard.pair_ids, [0] * len(shard.pair_ids), len(pairs), dist)
+    # the same pairs through the DROP-IN entry point, the way the unmodified reference calls it: one
+    # match_features_subset(std::vector<feature_2d>...) closure per pair on OpenMP workers (pipeline.cpp:42-49), every
+    # call packing, uploading and matching its own two images (rank 0, a bounded sample of its pairs)
+    drop_in = None
+    if rank == 0 and not args.no_secondary and local_pairs:
+        sample = local_pairs[:min(len(local_pairs), 768)]
+        sq, sc = [sets[a] for a, _ in sample], [sets[b] for _, b in sample]
+        host.run_parallel_handles(sq[:64], sc[:64], threads=threads)  # sizes the workers' staging areas
+        d_secs, d_matches = host.run_parallel_handles(sq, sc, threads=threads)
+        drop_in = {"pairs_per_s": len(sample) / d_secs, "pairs": len(sample), "host_threads": threads,
+                   "matches": d_matches,
+                   "api": "match_features_subset(std::vector<feature_2d>...) per pair, all features of both images, "
+                          "one closure per OpenMP worker like run_parallel (src/pipeline/pipeline.cpp:42-49)"}
     if rank == 0:
         assert summaries is not None and len(summaries) == len(pairs)
         secs = float(t.item())
@@ -545,7 +558,8 @@ def run_survey(args):
                        "comparisons_per_step": cmps, "Gcmp_per_s": cmps / secs / 1e9, "matches": int(matches),
                        "ransac_inliers": int(inliers), "pairs_with_relation": int(kept_all),
                        "resident_images_all_ranks": int(resident_all), "host_threads_per_rank": threads,
-                       "rank0_breakdown_s": {k: v for k, v in stats.items() if k.startswith("seconds")}},
+                       "rank0_breakdown_s": {k: v for k, v in stats.items() if k.startswith("seconds")},
+                       "drop_in_per_pair_calls": drop_in},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": n_pairs / secs, "unit": "pairs/s",
                     "h2d_bytes_per_step": int(resident_all) * 8192 * 64, "d2h_bytes_per_step": int(n_pairs) * 8192 * 8,
