@@ -513,13 +513,17 @@ def run_survey(args):
     barrier()
     t0 = time.perf_counter()
     stats = None
+    res = None
     for _ in range(steps):
+        if res is not None:
+            res.close()
         res = step()
         stats = res.stats
-        kept = sum(1 for p in range(res.n_pairs) if res.sizes(p)[0] > 0)
-        res.close()
     barrier()
     secs = (time.perf_counter() - t0) / steps
+    # a statistic for the JSON line, counted after the clock stopped (9000 Python-level accessor calls)
+    kept = sum(1 for p in range(res.n_pairs) if res.sizes(p)[0] > 0)
+    res.close()
     clocks = sampler.result()
     launches = capi.kernel_launches() - launches0
     t = torch.tensor([secs], dtype=torch.float64, device="cuda")

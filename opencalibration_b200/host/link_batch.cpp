@@ -272,7 +272,7 @@ std::vector<camera_relations> link_pairs(const std::vector<LinkImage> &images, c
     };
     LinkStats st;
 
-    // ---- submissions: one producer (a parked helper thread, see HelperThreads) keeps the GPU matching the next
+    // ---- submissions: producers (parked helper threads, see HelperThreads) keep the GPU matching the next
     // chunks (into page-locked result buffers, one per slot) while `tail_workers` consumer threads, each with its own
     // OpenMP team, finish the chunks already matched. Several consumers are needed because a chunk's RANSAC rounds
     // are a serial chain of GPU round trips: with one consumer the chain's latency, not the host cores, bounds the tail.
@@ -289,7 +289,10 @@ std::vector<camera_relations> link_pairs(const std::vector<LinkImage> &images, c
     }
     const int workers = options.run_ransac ? std::max(1, std::min(options.tail_workers, threads)) : 1;
     const int team = std::max(1, threads / workers);
-    const size_t n_slots = (size_t)workers + 1;
+    // two submissions in flight (two producers on alternate chunks, each with its own stream): while one submission
+    // drains its last CTAs, returns its records and the next problem table is built, the other one fills the SMs
+    const size_t n_producers = std::min<size_t>(2, std::max<size_t>(n_chunks, 1));
+    const size_t n_slots = (size_t)workers + n_producers;
     struct Slot
     {
         ocb_top2 *top = nullptr;
@@ -297,6 +300,7 @@ std::vector<camera_relations> link_pairs(const std::vector<LinkImage> &images, c
         double gpu_seconds = 0;
         size_t chunk = 0; // which submission the records belong to
         bool full = false;
+        bool busy = false; // claimed by a producer that is still matching into it
     };
     std::vector<Slot> slot(n_slots);
     // page-locked result buffers are expensive to create (the driver maps them into every visible GPU), so they are
@@ -316,15 +320,16 @@ std::vector<camera_relations> link_pairs(const std::vector<LinkImage> &images, c
     for (size_t k = 0; k < n_slots; k++)
         slot[k].top = static_cast<ocb_top2 *>(buffers.p[k]);
     st.seconds_setup = since(t_begin);
-    std::future<void> producer = HelperThreads::instance().run([&]() {
-        for (size_t c = 0; c < n_chunks; c++)
+    auto produce = [&](size_t first) {
+        for (size_t c = first; c < n_chunks; c += n_producers)
         {
             Slot &sl = slot[c % n_slots];
             {
                 std::unique_lock<std::mutex> lk(mu);
-                cv.wait(lk, [&] { return (!sl.full && prepared >= chunk_needs[c]) || stop; });
+                cv.wait(lk, [&] { return (!sl.full && !sl.busy && prepared >= chunk_needs[c]) || stop; });
                 if (stop)
                     return;
+                sl.busy = true;
             }
             const size_t begin = c * per, end = std::min(n_pairs, begin + per);
             std::vector<ocb_pair> sub(end - begin);
@@ -348,11 +353,15 @@ std::vector<camera_relations> link_pairs(const std::vector<LinkImage> &images, c
             }
             sl.chunk = c;
             sl.full = true;
+            sl.busy = false;
             cv.notify_all();
             if (rc)
                 return;
         }
-    });
+    };
+    std::vector<std::future<void>> producers;
+    for (size_t k = 0; k < n_producers; k++)
+        producers.push_back(HelperThreads::instance().run([&produce, k]() { produce(k); }));
 
     std::vector<camera_relations> relations(n_pairs);
     std::atomic<size_t> next_chunk{0}, total_matches{0}, total_inliers{0};
@@ -484,10 +493,11 @@ std::vector<camera_relations> link_pairs(const std::vector<LinkImage> &images, c
         stop = true;
         cv.notify_all();
     }
-    producer.wait();
+    for (std::future<void> &t : producers)
+        t.wait();
     preparer.wait();
     st.seconds_subsample_upload = prepare_seconds; // overlapped with the matching after the first submission
-    st.seconds_match_gpu = gpu_seconds;
+    st.seconds_match_gpu = gpu_seconds; // summed over submissions, two of which are in flight at a time
     st.seconds_tail = tail_seconds;
     const auto t_release = clock_type::now();
     give_back_result_buffers(buffers);
