@@ -16,16 +16,18 @@
 //     popcounts per comparison is traded for carry-save adders (F full adders = 2 LOP3 each, each removes one
 //     POPC) and the weighted sum of the remaining popcounts is accumulated with IMADs (runtime multiplier, so
 //     ptxas cannot turn them back into ALU shifts/adds) into a packed value
-//           v = (distance << 20) | query_slot_in_tile
-//     Within one query, v orders by distance alone (the low bits are that query's constant), which is what the
-//     reference's strict-less-than updates need because candidates arrive in position order; across the queries
-//     of a column it orders by (distance, query position), which is what the cross-check needs;
-//   * per query the two smallest values (s1 <= s2) and the position of the first minimum are kept. Updates are
-//     rare after the first few candidates: the common path is one compare per comparison and a warp-uniform
-//     branch around the update;
-//   * cross-check: per candidate the warp-wide minimum of v (REDUX) goes to a 64-bit atomic max on the
-//     complemented (distance, query) key in global memory (complemented so that the zero-initialised workspace
-//     means "nothing yet");
+//           v = (distance << 20) | low bits
+//     The low bits are the candidate position (branch-free update: within one query v then orders by (distance,
+//     position), i.e. the first-seen minimum wins like the reference's strict-less-than updates) or the query's
+//     slot in the tile (vote form and cross-check: across the queries of a column v orders by (distance, query
+//     position));
+//   * per query the two smallest values (s1 <= s2) are kept branch-free (two min, one max) with the candidate
+//     position in the low bits of v; the alternative - one compare per comparison and a warp-uniform branch around
+//     the rare update, the position kept apart - is selectable (k1_update) and lost at every run length measured;
+//   * cross-check: per candidate the warp-wide minimum of v (REDUX) is parked in a double-buffered shared-memory
+//     array; after every tile 64 threads combine the warps' minima and issue one 64-bit atomic max per candidate
+//     and CTA on the complemented (distance, query) key in global memory (complemented so that the
+//     zero-initialised workspace means "nothing yet");
 //   * when a single pair cannot fill 148 SMs the candidate axis is split across CTAs; every CTA folds its
 //     per-query (d1, position, d2) into a global per-query state with two atomics (64-bit max on the
 //     complemented (distance, position) key; 32-bit max on the complemented distance of every key that loses) and
