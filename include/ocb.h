@@ -196,6 +196,12 @@ extern "C"
      * bound evaluation order (score [h], count [h]) in the same submission. */
     int ocb_fit_score_bound(const uint32_t *samples, size_t h, double thr, double *models_out, uint8_t *degenerate,
                             double *score, uint32_t *count);
+    /* One step of the local optimisation of src/model_inliers/ransac.cpp:224-245 against the bound correspondences:
+     * homography_model::fitInliers (homography_model.cpp:52-87) ON THE DEVICE for the correspondences whose bit is set
+     * in refit_bits [ceil(n/32)] (index order), then Model::evaluate of the refitted model -> model_out [18],
+     * score [1], count [1], inlier_bits [ceil(n/32)]. Equals the host fitInliers + ocb_score_bound bit for bit. */
+    int ocb_refit_evaluate_bound(const uint32_t *refit_bits, double thr, double *model_out, double *score,
+                                 uint32_t *count, uint32_t *inlier_bits);
     /* Stand-alone form: fits h minimal samples of corr [n][7] (replaces homography_model::checkSampleDegeneracy +
      * homography_model::fit, src/model_inliers/homography_model.cpp:19-50,120-136, for h hypotheses at once).
      * Replaces the calling thread's ocb_corr_bind binding. */

@@ -1239,6 +1239,61 @@ extern "C"
         return 0;
     }
 
+    int ocb_refit_evaluate_bound(const uint32_t *refit_bits, double thr, double *model_out, double *score,
+                                 uint32_t *count, uint32_t *inlier_bits)
+    {
+        ThreadCtx &cx = t_ctx;
+        int rc = cx.ensure();
+        if (rc)
+            return rc;
+        if (!cx.bound_valid)
+            return fail_invalid("no correspondences bound on this thread (ocb_corr_bind)");
+        if (!refit_bits || !model_out || !score || !count || !inlier_bits)
+            return fail_invalid("null pointer");
+        const size_t n = cx.bound_n, words = (n + 31) / 32;
+        if (n == 0)
+            return fail_invalid("empty correspondence set");
+        const BoundLayout L = bound_layout(n);
+        const size_t wb = words * sizeof(uint32_t);
+        Carver cv; // device: [job][mask] in, [model][score][count][bits] out (one copy back), [system] scratch
+        const size_t o_job = cv.take(sizeof(K3InlierJob)), o_mask = cv.take(wb);
+        const size_t in_bytes = cv.off;
+        const size_t o_m = cv.take(18 * sizeof(double)), o_sc = cv.take(sizeof(double)), o_cnt = cv.take(sizeof(uint32_t)),
+                     o_bits = cv.take(wb);
+        const size_t out_bytes = cv.off - o_m;
+        const size_t io_bytes = cv.off;
+        const size_t o_sys = cv.take(k3_inlier_scratch_bytes(n));
+        if ((rc = cx.dev_reserve(cv.off)) || (rc = cx.pinned_reserve(io_bytes)))
+            return rc;
+        char *b = static_cast<char *>(cx.bound.p);
+        char *d = static_cast<char *>(cx.dev.p);
+        char *hp = static_cast<char *>(cx.pinned.p);
+        K3InlierJob job;
+        job.c7 = reinterpret_cast<const double *>(b + L.o_c7);
+        job.bits = reinterpret_cast<const uint32_t *>(d + o_mask);
+        job.P = reinterpret_cast<double *>(d + o_sys);
+        job.model_out = reinterpret_cast<double *>(d + o_m);
+        job.n = (uint32_t)n;
+        memcpy(hp + o_job, &job, sizeof job);
+        memcpy(hp + o_mask, refit_bits, wb);
+        OCB_CUDA(cudaMemcpyAsync(d, hp, in_bytes, cudaMemcpyHostToDevice, cx.stream));
+        if ((rc = k3_fit_inliers(reinterpret_cast<const K3InlierJob *>(d + o_job), 1, cx.stream)))
+            return rc;
+        // Model::evaluate: index order, inlier mask out
+        rc = k2_score(OCB_MODEL_HOMOGRAPHY, reinterpret_cast<double *>(d + o_m), 1, reinterpret_cast<double *>(b + L.o_nat),
+                      nullptr, n, thr, reinterpret_cast<double *>(d + o_sc), reinterpret_cast<uint32_t *>(d + o_cnt),
+                      reinterpret_cast<uint32_t *>(d + o_bits), nullptr, cx.stream);
+        if (rc)
+            return rc;
+        OCB_CUDA(cudaMemcpyAsync(hp + o_m, d + o_m, out_bytes, cudaMemcpyDeviceToHost, cx.stream));
+        OCB_CUDA(cudaStreamSynchronize(cx.stream));
+        memcpy(model_out, hp + o_m, 18 * sizeof(double));
+        memcpy(score, hp + o_sc, sizeof(double));
+        memcpy(count, hp + o_cnt, sizeof(uint32_t));
+        memcpy(inlier_bits, hp + o_bits, wb);
+        return 0;
+    }
+
     int ocb_fit_homography(const double *corr, size_t n, const uint32_t *samples, size_t h, double *models_out,
                            uint8_t *degenerate)
     {

@@ -533,6 +533,7 @@ double ransac(const std::vector<correspondence> &matches, Model &model, std::vec
         t_stats = run.stats;
         return 0;
     }
+    run.device_refit = ransac_device_fit(); // only the homography run ever asks for it
     // the correspondences stay on the GPU for the whole run: every request below sends only its models
     const BoundCorrespondences resident(matches, run.order());
     using Need = typename RansacRun<Model>::Need;
@@ -556,7 +557,11 @@ double ransac(const std::vector<correspondence> &matches, Model &model, std::vec
             gpu_evaluate_bits(run.kind, run.request_models(), run.thr, matches, &run.eval_score, &run.eval_count,
                               run.eval_bits.data());
             break;
-        case Need::REFIT_EVALUATE: // never requested: device_refit is off in this driver
+        case Need::REFIT_EVALUATE:
+            gpu_check(ocb_refit_evaluate_bound(run.refit_bits.data(), run.thr, run.refit_m18, &run.eval_score,
+                                               &run.eval_count, run.eval_bits.data()),
+                      "ocb_refit_evaluate_bound");
+            break;
         case Need::DONE:
             break;
         }
