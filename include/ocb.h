@@ -83,7 +83,14 @@ extern "C"
     const char *ocb_version(void);
     /* Number of kernels this library has launched since load (all threads). */
     uint64_t ocb_kernel_launches(void);
-    /* Tuning knobs for experiments ("k1_variant", "k1_items_per_sm", ...). Unknown key: OCB_E_INVALID. */
+    /* Tuning knobs for experiments; results never depend on them (every setting is parity-tested). Unknown key:
+     * OCB_E_INVALID.
+     *   "k1_variant"       0 = default; instantiations of the Hamming kernel (queries per thread, adders, form)
+     *   "k1_items_per_sm"  work items per SM when one pair's candidate axis is split (default 32)
+     *   "k1_update"        0 = by run length, 1 = compare + vote + skip, 2 = branch-free two-smallest
+     *   "k1_bf_rows"       runs shorter than this use the branch-free update when k1_update == 0
+     *   "k2_variant"       0 = by size, 1 = one hypothesis group per CTA, 2 = four groups per CTA in lock-step
+     *   "k2_hg"            hypotheses per group (1..8); 0 = balance the SMs */
     int ocb_set_option(const char *key, int64_t value);
     int64_t ocb_get_option(const char *key);
 
