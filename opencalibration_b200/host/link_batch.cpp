@@ -157,6 +157,27 @@ class HelperThreads
     std::deque<std::packaged_task<void()>> queue_;
     size_t idle_ = 0;
 };
+
+// The helper threads of one link_pairs call work on that call's stack variables. Whatever way the call is left
+// (an allocation failure between two stages included), this guard tells them to drain and waits for them first.
+struct HelperGuard
+{
+    std::mutex &mu;
+    std::condition_variable &cv;
+    bool &stop;
+    std::vector<std::future<void>> tasks;
+    ~HelperGuard()
+    {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            stop = true;
+        }
+        cv.notify_all();
+        for (std::future<void> &t : tasks)
+            if (t.valid())
+                t.wait();
+    }
+};
 } // namespace
 
 namespace ocb_host
@@ -204,7 +225,7 @@ std::vector<camera_relations> link_pairs(const std::vector<LinkImage> &images, c
     size_t prepared = 0;     // images of `order` that are subsampled and resident
     double prepare_seconds = 0;
     // every worker (and the helper threads) runs on the process's default device: the one of its first ocb_init
-    std::future<void> preparer = HelperThreads::instance().run([&]() {
+    auto prepare = [&]() {
         const size_t batch = (size_t)std::max(32, 4 * threads);
         for (size_t begin = 0; begin < order.size(); begin += batch)
         {
@@ -264,7 +285,7 @@ std::vector<camera_relations> link_pairs(const std::vector<LinkImage> &images, c
             if (stop)
                 return;
         }
-    });
+    };
     auto release_sets = [&]() {
         for (size_t i = 0; i < n_img; i++)
             if (registered[i])
@@ -308,13 +329,7 @@ std::vector<camera_relations> link_pairs(const std::vector<LinkImage> &images, c
     ResultBuffers buffers = take_result_buffers(n_slots, max_rows * sizeof(ocb_top2));
     if (buffers.p.size() != n_slots)
     {
-        {
-            std::lock_guard<std::mutex> lk(mu);
-            stop = true;
-        }
-        preparer.wait();
         give_back_result_buffers(buffers);
-        release_sets();
         throw std::runtime_error(std::string("ocb_host_alloc: ") + ocb_last_error());
     }
     for (size_t k = 0; k < n_slots; k++)
@@ -359,9 +374,6 @@ std::vector<camera_relations> link_pairs(const std::vector<LinkImage> &images, c
                 return;
         }
     };
-    std::vector<std::future<void>> producers;
-    for (size_t k = 0; k < n_producers; k++)
-        producers.push_back(HelperThreads::instance().run([&produce, k]() { produce(k); }));
 
     std::vector<camera_relations> relations(n_pairs);
     std::atomic<size_t> next_chunk{0}, total_matches{0}, total_inliers{0};
@@ -482,20 +494,21 @@ std::vector<camera_relations> link_pairs(const std::vector<LinkImage> &images, c
             }
         }
     };
-    std::vector<std::future<void>> consumers;
-    for (int w = 1; w < workers; w++)
-        consumers.push_back(HelperThreads::instance().run(consume));
-    consume();
-    for (std::future<void> &t : consumers)
-        t.wait();
     {
-        std::lock_guard<std::mutex> lk(mu);
-        stop = true;
-        cv.notify_all();
+        // Everything the helper tasks touch is declared above; the guard is the innermost object, so whichever way
+        // this scope is left it stops and joins the tasks before any of that state goes away.
+        HelperGuard helpers{mu, cv, stop, {}};
+        helpers.tasks.reserve(2 + n_producers + (size_t)workers);
+        helpers.tasks.push_back(HelperThreads::instance().run(prepare));
+        for (size_t k = 0; k < n_producers; k++)
+            helpers.tasks.push_back(HelperThreads::instance().run([&produce, k]() { produce(k); }));
+        const size_t first_consumer = helpers.tasks.size();
+        for (int w = 1; w < workers; w++)
+            helpers.tasks.push_back(HelperThreads::instance().run(consume));
+        consume();
+        for (size_t k = first_consumer; k < helpers.tasks.size(); k++)
+            helpers.tasks[k].wait(); // every chunk is consumed (or an error stopped the run); the guard releases the rest
     }
-    for (std::future<void> &t : producers)
-        t.wait();
-    preparer.wait();
     st.seconds_subsample_upload = prepare_seconds; // overlapped with the matching after the first submission
     st.seconds_match_gpu = gpu_seconds; // summed over submissions, two of which are in flight at a time
     st.seconds_tail = tail_seconds;
