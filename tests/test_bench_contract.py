@@ -1,0 +1,55 @@
+"""bench.py contract checks that need no GPU: the reference arm (the reference's own CPU object code, oracle/_ref) must
+print exactly ONE JSON line with the keys the driver reads, alone and under a 2-rank torchrun launch (rank 0 prints,
+the other rank exits 0 without work); the product arm must refuse to run without a CUDA device (no CPU fallback)."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REQUIRED = {"impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+            "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"}
+
+
+def run(cmd, timeout=600):
+    env = dict(os.environ, OMP_NUM_THREADS="4")
+    return subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=timeout, env=env)
+
+
+def check_line(stdout, n_gpus, steps, warmup):
+    lines = [l for l in stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    assert REQUIRED <= set(d), REQUIRED - set(d)
+    assert d["impl"] == "reference" and d["metric"] == "hamming_comparisons_per_s" and d["unit"] == "Gcmp/s"
+    assert d["n_gpus"] == n_gpus and d["steps"] == steps and d["warmup"] == warmup and d["value"] > 0
+    assert d["higher_is_better"] is True and d["vs_baseline"] is None and d["data"] == "synthetic"
+    assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] >= 1
+    assert d["cpu_baseline"]["value"] == d["value"] and d["e2e"]["value"] == d["value"]
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert "workload" in d["config"] and "model" not in d["config"]
+    return d
+
+
+def test_reference_arm_prints_one_contract_line():
+    r = run([sys.executable, "bench.py", "--impl", "reference", "--steps", "2", "--warmup", "1"])
+    assert r.returncode == 0, r.stderr[-2000:]
+    check_line(r.stdout, 1, 2, 1)
+
+
+def test_reference_arm_under_torchrun_rank0_only():
+    r = run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+             "127.0.0.1", "--master-port", "29617", "bench.py", "--impl", "reference", "--gpus", "2", "--steps", "2",
+             "--warmup", "1"])
+    assert r.returncode == 0, r.stderr[-2000:]
+    check_line(r.stdout, 2, 2, 1)
+
+
+def test_product_arm_needs_a_gpu():
+    import torch
+    if torch.cuda.is_available():
+        return  # this check is for the CPU-only container
+    r = run([sys.executable, "bench.py", "--steps", "1", "--warmup", "1"], timeout=300)
+    assert r.returncode != 0
+    assert not [l for l in r.stdout.splitlines() if l.strip().startswith("{")]
+    assert "no CPU fallback" in (r.stderr + r.stdout)
