@@ -53,3 +53,30 @@ def test_product_arm_needs_a_gpu():
     assert r.returncode != 0
     assert not [l for l in r.stdout.splitlines() if l.strip().startswith("{")]
     assert "no CPU fallback" in (r.stderr + r.stdout)
+
+
+import pytest
+
+
+@pytest.mark.gpu
+def test_product_arm_line_has_every_contract_key():
+    """The default run (configs[1] on one B200): one JSON line with the base contract's keys plus roofline,
+    cpu_baseline, e2e with host<->device bytes, clocks without thermal / hardware slowdown, and a launch count."""
+    r = run([sys.executable, "bench.py", "--steps", "20", "--warmup", "3"], timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    need = (REQUIRED - {"impl"}) | {"roofline", "clocks", "gpu_launches"}
+    assert need <= set(d), need - set(d)
+    assert d["metric"] == "hamming_comparisons_per_s" and d["n_gpus"] == 1 and d["steps"] == 20 and d["warmup"] == 3
+    assert d["scaling"] == "weak" and d["dtype"] == "u32" and d["gpu_launches"] >= 20
+    assert d["value"] > 100 and d["e2e"]["value"] > 50                       # Gcmp/s: far above any CPU path
+    assert d["e2e"]["h2d_bytes_per_step"] == 2 * 10000 * 64 and d["e2e"]["d2h_bytes_per_step"] > 0
+    rf = d["roofline"]
+    assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(rf)
+    assert abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-9 and rf["traffic"] > 1_000_000
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "reference" and cb["cores"] >= 1 and 0 < cb["value"] < d["value"]
+    assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    assert d["config"]["parity_spot_check"] is True
