@@ -78,6 +78,7 @@ extern "C"
      * src/pipeline/pipeline.cpp:42-49, in a one-process-per-GPU job). */
     int ocb_init(int device);
     int ocb_set_device(int device); /* device used by the calling thread's host-buffer calls */
+    int ocb_current_device(void);   /* the device the calling thread's next host-buffer call will use */
     void ocb_shutdown(void);        /* frees cached staging buffers and registered descriptor sets */
     const char *ocb_last_error(void);
     const char *ocb_version(void);
@@ -124,12 +125,15 @@ extern "C"
      * i.e. set[indices[k]] for the indices spatially_subsample_feature_indices returned
      * (src/pipeline/link_stage.cpp:63-65,80-81). Re-registering an id replaces it. */
     int ocb_register_descriptors(uint64_t set_id, const uint64_t *rows, size_t n);
+    /* A set must not be unregistered or re-registered while an ocb_match_pairs call that names it is in flight on
+     * another thread (the storage goes back to the device's memory pool without waiting for other threads' streams). */
     int ocb_unregister_descriptors(uint64_t set_id);
     /* Registers many sets with ONE device allocation and a pipelined gather -> page-locked staging -> device copy
      * (the per-image cudaMalloc + synchronous copy of ocb_register_descriptors dominates when a LinkStage batch
      * uploads hundreds of images). Row k of a set is the 64 bytes at rows + idx[k] * stride (idx == NULL: k * stride):
      * pass &features[0].descriptor, sizeof(feature_2d) and the subsample indices to upload straight from
-     * std::vector<feature_2d>. The allocation is released when the last of its sets is unregistered / replaced. */
+     * std::vector<feature_2d>. The allocation is released when the last of its sets is unregistered / replaced.
+     * A set_id may appear only once per batch (OCB_E_INVALID otherwise). */
     typedef struct ocb_set_source
     {
         uint64_t set_id;
@@ -175,7 +179,8 @@ extern "C"
      *   corr:    [n][7] doubles = std::vector<correspondence>::data()
      *            (include/opencalibration/types/correspondence.hpp:8-13).
      *   order:   nullable [n] permutation: the MSAC sum of each hypothesis is accumulated sequentially in
-     *            this order (ransac.cpp's shuffled eval_order); NULL = index order (evaluate).
+     *            this order (ransac.cpp's shuffled eval_order); NULL = index order (evaluate). An entry >= n gives
+     *            OCB_E_INVALID (here, in ocb_corr_bind and in ocb_corr_bind_batch).
      *   score:   [h] sum of 1-(e/thr)^2 over inliers (e < thr, strict), IEEE double, each operation rounded
      *            individually (no FMA contraction), summed in `order`.
      *   count:   [h] number of inliers.

@@ -323,6 +323,18 @@ bool aligned16(const void *p)
     return (reinterpret_cast<uintptr_t>(p) & 15u) == 0;
 }
 
+// An evaluation order indexes the correspondences on the device (score_models.cu: c7 + order[p] * 7); an entry out of
+// range would be a wild device read, so it is rejected on the host like sample and list indices are.
+bool order_in_range(const uint32_t *order, size_t n)
+{
+    if (!order)
+        return true;
+    uint32_t worst = 0;
+    for (size_t p = 0; p < n; p++)
+        worst = std::max(worst, order[p]);
+    return n == 0 || worst < n;
+}
+
 } // namespace
 } // namespace ocb
 
@@ -355,6 +367,11 @@ extern "C"
     {
         t_ctx.device = device;
         return 0;
+    }
+
+    int ocb_current_device(void)
+    {
+        return t_ctx.device >= 0 ? t_ctx.device : g_default_device.load();
     }
 
     void ocb_shutdown(void)
@@ -659,6 +676,16 @@ extern "C"
             if (sources[i].n && (!sources[i].rows || sources[i].stride < OCB_ROW_BYTES))
                 return fail_invalid("rows / stride");
             total_rows += sources[i].n;
+        }
+        {
+            // the same id twice in one batch would release the first entry's share of the arena while the batch is
+            // still being entered
+            std::vector<uint64_t> ids(count);
+            for (size_t i = 0; i < count; i++)
+                ids[i] = sources[i].set_id;
+            std::sort(ids.begin(), ids.end());
+            if (std::adjacent_find(ids.begin(), ids.end()) != ids.end())
+                return fail_invalid("duplicate set_id in one batch");
         }
         Arena *arena = nullptr;
         char *d_base = nullptr;
@@ -987,6 +1014,8 @@ extern "C"
             return 0;
         if (!models || !score || !count || (n && !corr))
             return fail_invalid("null pointer");
+        if (!order_in_range(order, n))
+            return fail_invalid("order entry out of range");
         ThreadCtx &cx = t_ctx;
         int rc = cx.ensure();
         if (rc)
@@ -1064,6 +1093,8 @@ extern "C"
             return fail_invalid("n must fit in 32 bits");
         if (n && !corr)
             return fail_invalid("corr");
+        if (!order_in_range(order, n))
+            return fail_invalid("order entry out of range");
         ThreadCtx &cx = t_ctx;
         int rc = cx.ensure();
         if (rc)
@@ -1365,6 +1396,8 @@ extern "C"
         {
             if (sets[i].n >= 0xFFFFFFFFull || (sets[i].n && !sets[i].corr))
                 return fail_invalid("correspondence set");
+            if (!order_in_range(sets[i].order, sets[i].n))
+                return fail_invalid("order entry out of range");
             cx.batch_sets[i].n = sets[i].n;
             cx.batch_sets[i].has_order = sets[i].order != nullptr && sets[i].n > 0;
             cx.batch_sets[i].o_c7 = cv.take(sets[i].n * 7 * sizeof(double));

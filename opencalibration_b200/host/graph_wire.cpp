@@ -1048,6 +1048,10 @@ void read_node(Scanner &sc, GraphNode &node)
         sc.fail("image node " + std::to_string(node.id) + " lacks a member the reference reads");
     if (!has_sparse)
         node.num_sparse_features = node.features.size(); // deserialize :180-187
+    // The reference trusts the file (link_stage.cpp:63-65 then reads features[0 .. num_sparse) unchecked); a corrupt
+    // or crafted checkpoint must not become an out-of-bounds read of descriptor memory here.
+    if (node.num_sparse_features > node.features.size())
+        sc.fail("image node " + std::to_string(node.id) + ": num_sparse_features exceeds the number of features");
 }
 
 void read_edge(Scanner &sc, GraphEdge &edge)

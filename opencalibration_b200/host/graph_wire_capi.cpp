@@ -169,6 +169,8 @@ extern "C"
             return bad("ocbw_graph_add_node: null argument");
         if (!draw_id && g->doc.find_node(*id))
             return bad("ocbw_graph_add_node: node id already present");
+        if (num_sparse_features > n_features)
+            return bad("ocbw_graph_add_node: num_sparse_features exceeds n_features");
         return guarded([&] {
             w::GraphNode n;
             n.id = *id;

@@ -192,8 +192,16 @@ std::vector<camera_relations> link_pairs(const std::vector<LinkImage> &images, c
         if (p.image_1 >= n_img || p.image_2 >= n_img)
             throw std::invalid_argument("link_pairs: pair references an unknown image");
     for (const LinkImage &im : images)
+    {
         if (!im.features)
             throw std::invalid_argument("link_pairs: image without features");
+        // link_stage.cpp:63-65 reads features[0 .. num_sparse_features) unchecked; a count from a corrupt checkpoint
+        // must not become an out-of-bounds read of descriptor memory
+        if (im.num_sparse_features > im.features->size())
+            throw std::invalid_argument("link_pairs: num_sparse_features exceeds the number of features");
+    }
+    // the helper threads below work on the device the CALLER selected (ocb_set_device), not on the process default
+    const int device = ocb_current_device();
 
     // ---- per image, once: the subsample every closure of that image would compute (link_stage.cpp:63-65,80-81) and
     // the upload of those rows. Only images that occur in a pair are touched. The images are prepared in the order
@@ -224,8 +232,8 @@ std::vector<camera_relations> link_pairs(const std::vector<LinkImage> &images, c
     bool stop = false;       // set on the first error: everybody drains
     size_t prepared = 0;     // images of `order` that are subsampled and resident
     double prepare_seconds = 0;
-    // every worker (and the helper threads) runs on the process's default device: the one of its first ocb_init
     auto prepare = [&]() {
+        ocb_set_device(device);
         const size_t batch = (size_t)std::max(32, 4 * threads);
         for (size_t begin = 0; begin < order.size(); begin += batch)
         {
@@ -320,10 +328,14 @@ std::vector<camera_relations> link_pairs(const std::vector<LinkImage> &images, c
         std::vector<uint64_t> offsets;
         double gpu_seconds = 0;
         size_t chunk = 0; // which submission the records belong to
+        size_t next = 0;  // the submission this slot takes next: k, k + n_slots, ... strictly in that order, whichever
+                          // producer owns them (two producers on alternate chunks are not ordered against each other)
         bool full = false;
         bool busy = false; // claimed by a producer that is still matching into it
     };
     std::vector<Slot> slot(n_slots);
+    for (size_t k = 0; k < n_slots; k++)
+        slot[k].next = k;
     // page-locked result buffers are expensive to create (the driver maps them into every visible GPU), so they are
     // kept between calls and only grow
     ResultBuffers buffers = take_result_buffers(n_slots, max_rows * sizeof(ocb_top2));
@@ -336,12 +348,15 @@ std::vector<camera_relations> link_pairs(const std::vector<LinkImage> &images, c
         slot[k].top = static_cast<ocb_top2 *>(buffers.p[k]);
     st.seconds_setup = since(t_begin);
     auto produce = [&](size_t first) {
+        ocb_set_device(device);
         for (size_t c = first; c < n_chunks; c += n_producers)
         {
             Slot &sl = slot[c % n_slots];
             {
                 std::unique_lock<std::mutex> lk(mu);
-                cv.wait(lk, [&] { return (!sl.full && !sl.busy && prepared >= chunk_needs[c]) || stop; });
+                cv.wait(lk, [&] {
+                    return (!sl.full && !sl.busy && sl.next == c && prepared >= chunk_needs[c]) || stop;
+                });
                 if (stop)
                     return;
                 sl.busy = true;
@@ -387,6 +402,7 @@ std::vector<camera_relations> link_pairs(const std::vector<LinkImage> &images, c
         cv.notify_all();
     };
     auto consume = [&]() {
+        ocb_set_device(device);
         for (;;)
         {
             const size_t c = next_chunk.fetch_add(1);
@@ -436,6 +452,7 @@ std::vector<camera_relations> link_pairs(const std::vector<LinkImage> &images, c
                 // the K1 records have been consumed: the slot can take the next submission
                 std::lock_guard<std::mutex> lk(mu);
                 sl.full = false;
+                sl.next = c + n_slots;
                 cv.notify_all();
             }
             if (options.run_ransac && local_error.empty())

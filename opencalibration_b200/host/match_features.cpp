@@ -100,7 +100,9 @@ std::vector<size_t> spatially_subsample_feature_indices(const std::vector<featur
     // `spacing_pixels` (squared-distance comparison, strict). Sequential greedy => host; the nearest-neighbour
     // query is answered from a uniform grid of kept points (cell = spacing) instead of the reference's KD-tree,
     // which yields the same minimum-distance decision.
-    if (count == 0)
+    // count > features.size() is an out-of-bounds read in the reference (:17-23 index features[0 .. count)); here it
+    // means "all of them"
+    if (count == 0 || count > features.size())
         count = features.size();
     if (count == 0)
         return {};

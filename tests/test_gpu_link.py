@@ -91,3 +91,6 @@ def test_link_pairs_rejects_bad_input(gpu, hostlib):
     sets = [hostlib.FeatureSet(*survey.image(i)) for i in range(2)]
     with pytest.raises(hostlib.OcbError):
         hostlib.link_pairs(sets, [survey.camera8()] * 2, [(0, 5)])
+    # a sparse-feature count beyond the feature vector (a corrupt checkpoint) is rejected, not read out of bounds
+    with pytest.raises(hostlib.OcbError):
+        hostlib.link_pairs(sets, [survey.camera8()] * 2, [(0, 1)], num_sparse=[101, 0])

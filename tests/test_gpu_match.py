@@ -192,6 +192,17 @@ def test_batched_registration_shares_one_allocation(gpu, oracle):
         gpu.unregister_descriptors(sid)
 
 
+def test_batched_registration_rejects_duplicate_ids(gpu):
+    # the same id twice in one batch used to free the batch's shared allocation while it was being entered
+    a, _ = synthetic.config2_pair(64, 8, seed=3)
+    flat = a.view(np.uint8).reshape(-1)
+    with pytest.raises(gpu.OcbError, match="duplicate"):
+        gpu.register_descriptors_batch([(7101, flat, 64, None, 64), (7102, flat, 64, None, 64),
+                                        (7101, flat, 64, None, 32)])
+    with pytest.raises(gpu.OcbError):  # nothing of the rejected batch was entered
+        gpu.unregister_descriptors(7102)
+
+
 def test_config1_pair_through_the_mirror(gpu, hostlib, config1, golden):
     # BASELINE configs[0]: test_match's flow on the repo pair; golden = the reference's own match_features.cpp
     ia = hostlib.spatially_subsample_feature_indices(config1["a_xy"], config1["a_strength"], 40.0)

@@ -138,6 +138,18 @@ def test_threshold_is_strict(gpu, oracle):
                                                                                    np.nextafter(t, np.inf))[1][0]
 
 
+def test_evaluation_order_entries_are_validated(gpu, oracle):
+    # order[] indexes the correspondences on the device; an entry >= n must be an error, not a wild read
+    corr, _ = oracle.scene_homography(40, 10, 1)
+    M = np.zeros((2, 18))
+    M[:, [0, 4, 8, 9, 13, 17]] = 1.0
+    order = np.arange(len(corr), dtype=np.uint32)
+    gpu.score_models(0, M, corr, 0.005, order=order)
+    order[7] = len(corr)
+    with pytest.raises(gpu.OcbError, match="order"):
+        gpu.score_models(0, M, corr, 0.005, order=order)
+
+
 def test_many_hypotheses_ragged_groups(gpu, oracle):
     corr, _ = oracle.scene_homography(700, 300, 11)
     eo, _, models = stream_models(oracle, 0, corr, 61)  # 61 = 7 full groups of 8 + 5

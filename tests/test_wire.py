@@ -183,6 +183,31 @@ def test_truncated_and_corrupted_documents_fail_cleanly(golden_graph):
         wire.Graph(bad)
 
 
+def test_num_sparse_features_beyond_the_features_is_rejected(hostlib, golden_graph):
+    # the reference trusts this count (link_stage.cpp:63-65); here a crafted file must not reach the matcher
+    g = wire.Graph(golden_graph)
+    n = g.node(0)["n_features"]
+    g.close()
+    text = golden_graph.decode()
+    m = re.search(r'"num_sparse_features": (\d+)', text)
+    assert m
+    bad = text[:m.start(1)] + str(n + 1000000) + text[m.end(1):]
+    with pytest.raises(capi.OcbError, match="num_sparse_features"):
+        wire.Graph(bad.encode())
+    g = wire.Graph()
+    with pytest.raises(capi.OcbError, match="num_sparse_features"):
+        g.add_node(np.zeros(8), np.array([10, 10], np.uint64), np.zeros((3, 2)), np.zeros(3, np.float32),
+                   np.zeros((3, 8), np.uint64), num_sparse=4)
+    g.close()
+
+
+def test_subsample_count_beyond_the_features_means_all(hostlib, oracle):
+    rng = np.random.default_rng(4)
+    xy, st = rng.uniform(0, 500, (300, 2)), rng.uniform(0, 1, 300).astype(np.float32)
+    assert np.array_equal(hostlib.spatially_subsample_feature_indices(xy, st, 20.0, 100000),
+                          hostlib.spatially_subsample_feature_indices(xy, st, 20.0, 0))
+
+
 def _random_graph(rng, n_nodes, n_edges, builders):
     """Same addNode / addEdge sequence into every builder (the reference's MeasurementGraph and the product's)."""
     cam = np.array([3000.0, 2000.5, 1500.25, -0.1, 0.01, 1e-4, 1e-5, -2e-5])
