@@ -52,7 +52,10 @@ void match_top2(const uint64_t *q, size_t n1, const uint64_t *c, size_t n2, uint
 {
     // src/match/match_features.cpp:71-93 with integer distances: d*(1.0/486) is strictly monotone
     // in d on [0,486], so the double comparisons of the reference order exactly like these.
+    // Queries are independent (the reference's outer loop :71 carries no state from one query to the next), so the
+    // checker runs them on all host cores: full-size parity checks then take seconds.
     const int INF = 0xFFFF;
+#pragma omp parallel for schedule(static) if (n1 * n2 > (size_t)1 << 22)
     for (size_t i = 0; i < n1; i++)
     {
         int best = INF, second = INF;
@@ -127,6 +130,7 @@ bool guided_good_match(size_t list_length, double best_dist, double second_dist)
 
 void match_col_best(const uint64_t *q, size_t n1, const uint64_t *c, size_t n2, uint32_t *col_best_q)
 {
+#pragma omp parallel for schedule(static) if (n1 * n2 > (size_t)1 << 22)
     for (size_t k = 0; k < n2; k++)
     {
         int best = 0x7FFFFFFF;

@@ -94,3 +94,42 @@ def test_link_pairs_rejects_bad_input(gpu, hostlib):
     # a sparse-feature count beyond the feature vector (a corrupt checkpoint) is rejected, not read out of bounds
     with pytest.raises(hostlib.OcbError):
         hostlib.link_pairs(sets, [survey.camera8()] * 2, [(0, 1)], num_sparse=[101, 0])
+
+
+def test_c4_survey_slice_equals_the_reference_object_code(gpu, hostlib):
+    """BASELINE configs[3] at full image size: >= 200 directed pairs of the 25 x 40 survey, 8192 features per image,
+    through the batched runner; EVERY pair's match list (indices, distances, order) against the reference's own
+    compiled match_features.cpp (oracle/_ref, -mpopcnt build of the same translation unit), with the subsample
+    indices from the reference's own spatially_subsample_feature_indices."""
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+    if not O.Reference.available():
+        pytest.skip("oracle/_ref not built")
+    ref = O.Reference(popcnt=True)
+    survey = synthetic.PlanarSurvey(25, 40, 8192, seed=7)
+    pairs = survey.pairs[:225]
+    used = sorted({i for p in pairs for i in p})
+    local = {g: k for k, g in enumerate(used)}
+    with ThreadPoolExecutor(8) as ex:
+        imgs = list(ex.map(survey.image, used))
+    sets = [hostlib.FeatureSet(d, xy, s) for d, xy, s in imgs]
+    lp = [(local[a], local[b]) for a, b in pairs]
+    res = hostlib.link_pairs(sets, [survey.camera8()] * len(sets), lp, run_ransac=False, spacing=0.5,
+                             pairs_per_submission=64)
+    assert res.stats["comparisons"] > 200 * 8000 * 8000
+    idx = [ref.subsample(xy, s, 0.5) for _, xy, s in imgs]
+    assert all(len(i) > 8000 for i in idx)
+
+    def want(p):
+        a, b = lp[p]
+        return ref.match_features_subset(imgs[a][0], imgs[b][0], idx[a], idx[b])
+
+    with ThreadPoolExecutor(os.cpu_count() or 4) as ex:  # ctypes releases the GIL: one reference call per core
+        expected = list(ex.map(want, range(len(lp))))
+    total = 0
+    for p, w in enumerate(expected):
+        got = res.get(p)["matches"]
+        assert all(np.array_equal(x, y) for x, y in zip(got, w)), p
+        total += len(w[0])
+    assert total > 225 * 500  # neighbouring images share most of their footprint
+    res.close()

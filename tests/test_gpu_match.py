@@ -246,14 +246,14 @@ def test_cross_check_flags(gpu, hostlib, oracle):
 
 
 def test_full_size_properties_10k(gpu, oracle):
-    # BASELINE configs[1] at full size: size-independent properties + a sampled bit-exact check
+    # BASELINE configs[1] at full size: EVERY query and EVERY candidate column against the oracle (bit-exact), then
+    # size-independent properties
     n = 10000
     a, b = synthetic.config2_pair(n, n, seed=1)
     r, col = gpu.match_top2(a, b, cross_check=True)
-    sample = np.random.default_rng(0).permutation(n)[:256]
-    bk, bd, sd = oracle.match_top2(a[sample], b)
-    assert np.array_equal(r["best_k"][sample], bk) and np.array_equal(r["best_d"][sample], bd)
-    assert np.array_equal(r["second_d"][sample], sd)
+    bk, bd, sd = oracle.match_top2(a, b)
+    assert np.array_equal(r["best_k"], bk) and np.array_equal(r["best_d"], bd) and np.array_equal(r["second_d"], sd)
+    assert np.array_equal(col, oracle.match_col_best(a, b))
     assert np.all(r["best_d"] <= r["second_d"])
     # self match: every row finds itself at distance 0, at its first occurrence
     rs = gpu.match_top2(a, a)
@@ -271,6 +271,22 @@ def test_full_size_properties_10k(gpu, oracle):
     # checksum of the ratio-test survivors is reproducible across kernel variants
     keep = r["best_d"].astype(np.float64) * (1.0 / 486) < 0.8 * (r["second_d"].astype(np.float64) * (1.0 / 486))
     assert 4000 < keep.sum() < 6000
+
+
+def test_full_size_10k_through_the_mirror_equals_the_reference_object_code(gpu, hostlib):
+    # configs[1] through the reference-facing entry point against the reference's own compiled match_features.cpp
+    # (-mpopcnt build of the same translation unit), every emitted match: indices, distances and sort order
+    import oc_oracle
+    if not oc_oracle.Reference.available():
+        pytest.skip("oracle/_ref not built")
+    ref = oc_oracle.Reference(popcnt=True)
+    n = 10000
+    a, b = synthetic.config2_pair(n, n, seed=1)
+    idx = np.arange(n, dtype=np.uintp)
+    got = hostlib.match_features_subset(a, b, idx, idx)
+    want = ref.match_features_subset(a, b, idx, idx)
+    assert len(want[0]) > 4000
+    assert all(np.array_equal(x, y) for x, y in zip(got, want))
 
 
 def test_concurrent_callers(gpu, oracle):

@@ -160,14 +160,24 @@ def test_many_hypotheses_ragged_groups(gpu, oracle):
     assert np.array_equal(s2, s) and np.array_equal(c2, c)
 
 
-def test_config3_full_size_sampled(gpu, oracle):
-    # BASELINE configs[2]: 4k hypotheses x 20k correspondences from the reference's seeded stream
+def test_config3_full_size_every_hypothesis(gpu, oracle):
+    # BASELINE configs[2]: 4k hypotheses x 20k correspondences from the reference's seeded stream; ALL 4096 scores,
+    # counts and inlier bit masks (8.2e7 residuals) against the oracle, bit for bit
     corr, gt = oracle.scene_homography(14000, 6000, 42)
     eo, samples, models = stream_models(oracle, 0, corr, 4096)
-    s, c, _ = gpu.score_models(0, models, corr, 0.005, order=eo, want_bits=False)
-    pick = np.concatenate([np.arange(8), np.random.default_rng(0).permutation(4096)[:24], [4095]])
-    so, co, _ = oracle.score_hypotheses(0, models[pick], corr, order=eo, thr=0.005, want_bits=False)
-    assert np.array_equal(s[pick], so) and np.array_equal(c[pick], co)
+    s, c, bits = gpu.score_models(0, models, corr, 0.005, order=eo)
+    so, co, bo = oracle.score_hypotheses(0, models, corr, order=eo, thr=0.005)
+    assert np.array_equal(s, so) and np.array_equal(c, co) and np.array_equal(bits, bo)
+    assert (c > 10000).sum() > 500  # a good share of the stream's samples are all-inlier
+
+
+def test_config3_epipolar_full_size_every_hypothesis(gpu, oracle):
+    # the E/F residual on the same shape: SyntheticScene::fundamental(14000, 6000), threshold 0.01
+    corr, gt = oracle.scene_fundamental(14000, 6000, 0.0, 42)
+    eo, samples, models = stream_models(oracle, 2, corr, 4096)
+    s, c, bits = gpu.score_models(2, models, corr, 0.01, order=eo)
+    so, co, bo = oracle.score_hypotheses(2, models, corr, order=eo, thr=0.01)
+    assert np.array_equal(s, so) and np.array_equal(c, co) and np.array_equal(bits, bo)
     # size-independent properties: a sample drawn from inliers only scores >= 14000 * small, counts bound scores
     assert np.all(s <= c) and np.all(s >= 0) and c.max() >= 14000
     all_inlier_samples = np.all(samples < 14000, axis=1)
