@@ -169,6 +169,13 @@ def test_config3_full_size_every_hypothesis(gpu, oracle):
     so, co, bo = oracle.score_hypotheses(0, models, corr, order=eo, thr=0.005)
     assert np.array_equal(s, so) and np.array_equal(c, co) and np.array_equal(bits, bo)
     assert (c > 10000).sum() > 500  # a good share of the stream's samples are all-inlier
+    # size-independent properties: a sample drawn from inliers only scores >= 14000 * small, counts bound scores
+    assert np.all(s <= c) and np.all(s >= 0) and c.max() >= 14000
+    all_inlier_samples = np.all(samples < 14000, axis=1)
+    assert c[all_inlier_samples].min() >= 13990
+    # evaluation order changes neither counts nor (beyond rounding) scores
+    s_nat, c_nat, _ = gpu.score_models(0, models[:64], corr, 0.005, want_bits=False)
+    assert np.array_equal(c_nat, c[:64]) and np.allclose(s_nat, s[:64], rtol=1e-12)
 
 
 def test_config3_epipolar_full_size_every_hypothesis(gpu, oracle):
@@ -178,13 +185,6 @@ def test_config3_epipolar_full_size_every_hypothesis(gpu, oracle):
     s, c, bits = gpu.score_models(2, models, corr, 0.01, order=eo)
     so, co, bo = oracle.score_hypotheses(2, models, corr, order=eo, thr=0.01)
     assert np.array_equal(s, so) and np.array_equal(c, co) and np.array_equal(bits, bo)
-    # size-independent properties: a sample drawn from inliers only scores >= 14000 * small, counts bound scores
-    assert np.all(s <= c) and np.all(s >= 0) and c.max() >= 14000
-    all_inlier_samples = np.all(samples < 14000, axis=1)
-    assert c[all_inlier_samples].min() >= 13990
-    # evaluation order changes neither counts nor (beyond rounding) scores
-    s_nat, c_nat, _ = gpu.score_models(0, models[:64], corr, 0.005, want_bits=False)
-    assert np.array_equal(c_nat, c[:64]) and np.allclose(s_nat, s[:64], rtol=1e-12)
 
 
 def test_evaluate_through_the_mirror(gpu, hostlib, oracle):
