@@ -64,6 +64,29 @@ extern "C"
         uint64_t candidate_set;
     } ocb_pair;
 
+    /* One match that passed the ratio test, as the device emits it (ocb_match_pairs_ratio): the query POSITION in
+     * the query set, the candidate POSITION in the candidate set and the integer Hamming distance; the reference's
+     * feature_match (include/opencalibration/types/feature_match.hpp:10-21) is
+     * {indices_1[query_k], indices_2[best_k], best_d * (1.0 / 486)}. */
+    typedef struct ocb_match
+    {
+        uint32_t query_k;
+        uint32_t best_k;
+        uint32_t best_d;
+    } ocb_match;
+
+    /* The members of DifferentiableCameraModel<double> that image_to_3d reads
+     * (include/opencalibration/types/camera_model.hpp:22-37). */
+    typedef struct ocb_camera
+    {
+        double focal_length_pixels;
+        double principal_point[2];
+        double radial_distortion[3];
+        double tangential_distortion[2];
+        int32_t projection_planar; /* 1 = ProjectionType::PLANAR, 0 = UNKNOWN (the ray stays unset: NaN here) */
+        int32_t reserved;
+    } ocb_camera;
+
     enum ocb_model_kind
     {
         OCB_MODEL_HOMOGRAPHY = 0, /* include/opencalibration/model_inliers/homography_model.hpp:14-34 */
@@ -143,6 +166,21 @@ extern "C"
         size_t n;
     } ocb_set_source;
     int ocb_register_descriptors_batch(const ocb_set_source *sources, size_t count);
+    /* Like ocb_register_descriptors_batch, plus what the steps AFTER the match need on the device (K6): the keypoint
+     * location of every row (feature_2d::location, two doubles at xy + idx[k] * xy_stride; xy == NULL: the set has no
+     * keypoints and cannot be named by ocb_corr_bind_batch_matches) and the image's camera model. */
+    typedef struct ocb_image_source
+    {
+        uint64_t set_id;
+        const void *rows;
+        size_t stride;
+        const size_t *idx;
+        size_t n;
+        const void *xy;
+        size_t xy_stride;
+        ocb_camera camera;
+    } ocb_image_source;
+    int ocb_register_images_batch(const ocb_image_source *sources, size_t count);
     /* Page-locked host memory for callers that want results copied straight into their buffers (every host-buffer
      * entry point detects page-locked arguments and skips its staging copy). NULL on failure. */
     void *ocb_host_alloc(size_t bytes);
@@ -150,6 +188,16 @@ extern "C"
     /* Matches n_pairs pairs in one submission. out receives the ocb_top2 records of pair p at
      * out[out_offsets[p] .. out_offsets[p] + n_query_rows(p)); out_offsets has n_pairs entries. */
     int ocb_match_pairs(const ocb_pair *pairs, size_t n_pairs, ocb_top2 *out, const uint64_t *out_offsets);
+
+    /* ocb_match_pairs followed ON THE DEVICE by the ratio test of src/match/match_features.cpp:94 (best < 0.8 * second
+     * in IEEE double on distance = count * (1.0 / 486), :79 -- the reference's comparison bit for bit) and an
+     * order-preserving compaction (K5): the survivors of pair p, in query order (the emission order of :71-97), are
+     * out[out_offsets[p] .. out_offsets[p + 1]); out_offsets has n_pairs + 1 entries and out_offsets[n_pairs] is the
+     * total. Only the survivors cross PCIe (12 bytes each instead of 8 bytes per query row). out_capacity = records
+     * `out` can hold; a larger total gives OCB_E_INVALID (the sum of the pairs' query rows always suffices). The
+     * reference's std::sort (:100-101) is left to the caller. */
+    int ocb_match_pairs_ratio(const ocb_pair *pairs, size_t n_pairs, ocb_match *out, size_t out_capacity,
+                              uint64_t *out_offsets);
 
     /* ---- K4: Hamming top-2 over per-query candidate lists (guided matcher of the dense stage) ---------------
      * Replaces the inner loop of densifyMesh, src/dense/dense_stereo.cpp:251-273: list l compares query row
@@ -277,6 +325,24 @@ extern "C"
         const uint32_t *refit_bits; /* [ceil(n/32)] the inliers to refit to, index order */
     } ocb_score_request;
     int ocb_corr_bind_batch(const ocb_corr_set *sets, size_t count);
+    /* distort_keypoints on the device (K6) feeding the same binding: replaces src/distort/distort_keypoints.cpp:48-61
+     * (image_to_3d of both keypoints of every match, :62-103, quality = match distance) as LinkStage calls it
+     * (src/pipeline/link_stage.cpp:87-88) for a whole batch of pairs, and leaves the correspondences bound for
+     * ocb_score_requests exactly as ocb_corr_bind_batch would. matches[i] = {position in set_1, position in set_2,
+     * integer distance} IN THE ORDER OF THE SORTED MATCH LIST (match_features.cpp:100-101): correspondence i belongs to
+     * match i. Both sets must have been registered with keypoints (ocb_register_images_batch) on this thread's device.
+     * corr_out (nullable) receives the [n][7] rows, bit-identical to the host distort_keypoints of the C++ mirror. */
+    typedef struct ocb_match_set
+    {
+        uint64_t set_1, set_2;
+        const ocb_match *matches; /* [n] */
+        size_t n;
+        const uint32_t *order;    /* nullable [n] evaluation order, as in ocb_corr_set */
+        double *corr_out;         /* nullable [n][7] */
+    } ocb_match_set;
+    int ocb_corr_bind_batch_matches(const ocb_match_set *sets, size_t count);
+    /* image_to_3d (src/distort/distort_keypoints.cpp:62-103) for n keypoints of one camera: xy [n][2] -> rays [n][3]. */
+    int ocb_image_to_3d(const double *xy, size_t n, const ocb_camera *camera, double *rays);
     int ocb_score_requests(const ocb_score_request *requests, size_t count);
 
     /* Device-resident variant of ocb_score_models. d_corr4: [n][4] doubles (x1,y1,x2,y2) = measurement / z,

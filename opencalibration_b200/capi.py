@@ -56,6 +56,10 @@ def lib():
         "ocb_host_alloc": (vp, [sz]),
         "ocb_host_free": (None, [vp]),
         "ocb_match_pairs": (i32, [vp, sz, vp, vp]),
+        "ocb_match_pairs_ratio": (i32, [vp, sz, vp, sz, vp]),
+        "ocb_register_images_batch": (i32, [vp, sz]),
+        "ocb_corr_bind_batch_matches": (i32, [vp, sz]),
+        "ocb_image_to_3d": (i32, [vp, sz, vp, vp]),
         "ocb_match_lists": (i32, [vp, sz, vp, sz, vp, vp, vp, sz, vp]),
         "ocb_match_lists_device": (i32, [vp, vp, vp, vp, vp, sz, vp, vp]),
         "ocb_score_models": (i32, [i32, vp, sz, vp, sz, dbl, vp, vp, vp, vp]),
@@ -197,6 +201,81 @@ def match_pairs(pairs, n_query_rows, out=None):
         out = np.zeros(total, TOP2_DTYPE)
     check(lib().ocb_match_pairs(_ptr(pa), len(pa), _ptr(out), _ptr(offs)))
     return out, offs
+
+
+MATCH_DTYPE = np.dtype([("query_k", np.uint32), ("best_k", np.uint32), ("best_d", np.uint32)])
+CAMERA_DTYPE = np.dtype([("focal_length_pixels", "<f8"), ("principal_point", "<f8", 2), ("radial_distortion", "<f8", 3),
+                         ("tangential_distortion", "<f8", 2), ("projection_planar", "<i4"), ("reserved", "<i4")])
+IMAGE_SOURCE_DTYPE = np.dtype([("set_id", "<u8"), ("rows", "<u8"), ("stride", "<u8"), ("idx", "<u8"), ("n", "<u8"),
+                               ("xy", "<u8"), ("xy_stride", "<u8"), ("camera", CAMERA_DTYPE)])
+MATCH_SET_DTYPE = np.dtype([("set_1", "<u8"), ("set_2", "<u8"), ("matches", "<u8"), ("n", "<u8"), ("order", "<u8"),
+                            ("corr_out", "<u8")])
+
+
+def camera(cam8, planar=True):
+    """cam8 = (f, ppx, ppy, k1, k2, k3, p1, p2) -> ocb_camera record."""
+    c = np.zeros((), CAMERA_DTYPE)
+    cam8 = np.asarray(cam8, np.float64)
+    c["focal_length_pixels"] = cam8[0]
+    c["principal_point"] = cam8[1:3]
+    c["radial_distortion"] = cam8[3:6]
+    c["tangential_distortion"] = cam8[6:8]
+    c["projection_planar"] = 1 if planar else 0
+    return c
+
+
+def match_pairs_ratio(pairs, capacity):
+    """ocb_match_pairs + device ratio test + compaction -> (matches [total] MATCH_DTYPE, offsets [n_pairs + 1])."""
+    pa = np.zeros(len(pairs), PAIR_DTYPE)
+    for i, (a, b) in enumerate(pairs):
+        pa[i] = (a, b)
+    out = np.zeros(max(int(capacity), 1), MATCH_DTYPE)
+    offs = np.zeros(len(pairs) + 1, np.uint64)
+    check(lib().ocb_match_pairs_ratio(_ptr(pa), len(pa), _ptr(out), int(capacity), _ptr(offs)))
+    return out[:int(offs[-1])], offs
+
+
+def register_images_batch(images):
+    """images: [(set_id, rows [n][8] u64, xy [n][2] f64 or None, cam8 or None)]: rows, keypoints and camera model."""
+    src = np.zeros(len(images), IMAGE_SOURCE_DTYPE)
+    keep = []
+    for i, (sid, rows, xy, cam8) in enumerate(images):
+        rows = _rows(rows)
+        xy = None if xy is None else np.ascontiguousarray(xy, np.float64).reshape(-1, 2)
+        keep += [rows, xy]
+        src[i]["set_id"], src[i]["n"] = sid, len(rows)
+        src[i]["rows"], src[i]["stride"] = (rows.ctypes.data if len(rows) else 0), 64
+        if xy is not None:
+            assert len(xy) == len(rows)
+            src[i]["xy"], src[i]["xy_stride"] = (xy.ctypes.data if len(xy) else 0), 16
+        if cam8 is not None:
+            src[i]["camera"] = camera(cam8)
+    check(lib().ocb_register_images_batch(_ptr(src), len(src)))
+
+
+def corr_bind_batch_matches(sets):
+    """sets: [(set_1, set_2, matches MATCH_DTYPE [n], order uint32 [n] or None)] -> list of [n][7] correspondence rows
+    computed on the device (K6); the sets stay bound on this thread for ocb_score_requests."""
+    ms = np.zeros(len(sets), MATCH_SET_DTYPE)
+    keep, outs = [], []
+    for i, (s1, s2, matches, order) in enumerate(sets):
+        matches = np.ascontiguousarray(matches, MATCH_DTYPE)
+        order = None if order is None else np.ascontiguousarray(order, np.uint32)
+        out = np.full((len(matches), 7), np.nan)
+        keep += [matches, order]
+        outs.append(out)
+        ms[i] = (s1, s2, matches.ctypes.data if len(matches) else 0, len(matches),
+                 0 if order is None else order.ctypes.data, out.ctypes.data if len(matches) else 0)
+    check(lib().ocb_corr_bind_batch_matches(_ptr(ms), len(ms)))
+    return outs
+
+
+def image_to_3d(xy, cam8, planar=True):
+    xy = np.ascontiguousarray(xy, np.float64).reshape(-1, 2)
+    rays = np.zeros((len(xy), 3))
+    cam = camera(cam8, planar)
+    check(lib().ocb_image_to_3d(_ptr(xy), len(xy), cam.ctypes.data_as(C.c_void_p), _ptr(rays)))
+    return rays
 
 
 # ---- K4: candidate lists ----

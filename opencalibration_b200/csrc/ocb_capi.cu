@@ -291,6 +291,9 @@ struct DescSet
     size_t n = 0;
     int device = 0;
     Arena *arena = nullptr; // nullptr: d_rows is its own allocation
+    // keypoint locations + camera model (ocb_register_images_batch): what K6 needs after the match
+    void *d_xy = nullptr; // [n] double2, inside the same arena
+    ocb_camera camera{};
 };
 // caller holds g_sets_mu
 void free_set_storage(DescSet &s)
@@ -313,6 +316,7 @@ void free_set_storage(DescSet &s)
     }
     cudaSetDevice(cur);
     s.d_rows = nullptr;
+    s.d_xy = nullptr;
     s.arena = nullptr;
 }
 std::mutex g_sets_mu;
@@ -550,16 +554,17 @@ extern "C"
     }
 
     // Gathers rows base[idx[k] * stride .. +64) (idx == NULL: k * stride) into dst.
-    static void gather_rows(char *dst, const void *base, size_t stride, const size_t *idx, size_t n, size_t first = 0)
+    static void gather_rows(char *dst, const void *base, size_t stride, const size_t *idx, size_t n, size_t first = 0,
+                            size_t elem = OCB_ROW_BYTES)
     {
         const char *b = static_cast<const char *>(base) + first * stride;
-        if (!idx && stride == OCB_ROW_BYTES)
+        if (!idx && stride == elem)
         {
-            memcpy(dst, b, n * OCB_ROW_BYTES);
+            memcpy(dst, b, n * elem);
             return;
         }
         for (size_t k = 0; k < n; k++)
-            memcpy(dst + k * OCB_ROW_BYTES, b + (idx ? idx[k] : k) * stride, OCB_ROW_BYTES);
+            memcpy(dst + k * elem, b + (idx ? idx[k] : k) * stride, elem);
     }
 
     int ocb_match_top2_strided(const void *rows1, size_t stride1, const size_t *idx1, size_t n1, const void *rows2,
@@ -658,7 +663,7 @@ extern "C"
         return 0;
     }
 
-    int ocb_register_descriptors_batch(const ocb_set_source *sources, size_t count)
+    int ocb_register_images_batch(const ocb_image_source *sources, size_t count)
     {
         if (count == 0)
             return 0;
@@ -668,14 +673,18 @@ extern "C"
         int rc = cx.ensure();
         if (rc)
             return rc;
-        size_t total_rows = 0;
+        constexpr size_t XY_BYTES = 2 * sizeof(double);
+        size_t total_rows = 0, total_xy = 0;
         for (size_t i = 0; i < count; i++)
         {
             if (sources[i].n >= 0xFFFFFFFFull)
                 return fail_invalid("n must fit in 32 bits");
             if (sources[i].n && (!sources[i].rows || sources[i].stride < OCB_ROW_BYTES))
                 return fail_invalid("rows / stride");
+            if (sources[i].n && sources[i].xy && sources[i].xy_stride < XY_BYTES)
+                return fail_invalid("xy stride below 16 bytes");
             total_rows += sources[i].n;
+            total_xy += sources[i].xy ? sources[i].n : 0;
         }
         {
             // the same id twice in one batch would release the first entry's share of the arena while the batch is
@@ -689,18 +698,19 @@ extern "C"
         }
         Arena *arena = nullptr;
         char *d_base = nullptr;
+        const size_t xy_base = total_rows * OCB_ROW_BYTES; // keypoints follow the rows inside the allocation
         if (total_rows)
         {
             void *p = nullptr;
-            OCB_CUDA(set_storage_alloc(&p, total_rows * OCB_ROW_BYTES, cx.device));
+            OCB_CUDA(set_storage_alloc(&p, xy_base + total_xy * XY_BYTES, cx.device));
             arena = new Arena;
             arena->base = p, arena->device = cx.device, arena->live = 0;
             d_base = static_cast<char *>(p);
         }
         // gather -> page-locked staging -> device, double-buffered so that the copy engine works while the next
-        // block of rows is gathered
-        const size_t block_rows = (size_t)1 << 16; // 4 MiB
-        rc = cx.pinned_reserve(2 * block_rows * OCB_ROW_BYTES);
+        // block is gathered; first every set's rows, then every set's keypoints
+        const size_t block_bytes = (size_t)4 << 20;
+        rc = cx.pinned_reserve(2 * block_bytes);
         cudaEvent_t ev[2] = {nullptr, nullptr};
         if (!rc && total_rows)
         {
@@ -708,25 +718,36 @@ extern "C"
             cudaError_t e = cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming);
             if (e == cudaSuccess)
                 e = cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming);
-            size_t done = 0, blk = 0;
-            for (size_t i = 0; i < count && e == cudaSuccess; i++)
+            size_t blk = 0;
+            for (int pass = 0; pass < 2 && e == cudaSuccess; pass++)
             {
-                size_t k = 0;
-                while (k < sources[i].n && e == cudaSuccess)
+                const size_t elem = pass == 0 ? (size_t)OCB_ROW_BYTES : XY_BYTES;
+                const size_t block_elems = block_bytes / elem;
+                size_t done = 0;
+                char *d_dst = d_base + (pass == 0 ? 0 : xy_base);
+                for (size_t i = 0; i < count && e == cudaSuccess; i++)
                 {
-                    const size_t take = std::min(block_rows, sources[i].n - k);
-                    const int b = (int)(blk & 1);
-                    if (blk >= 2)
-                        e = cudaEventSynchronize(ev[b]);
-                    if (e != cudaSuccess)
-                        break;
-                    gather_rows(hp + (size_t)b * block_rows * OCB_ROW_BYTES, sources[i].rows, sources[i].stride,
-                                sources[i].idx ? sources[i].idx + k : nullptr, take, sources[i].idx ? 0 : k);
-                    e = cudaMemcpyAsync(d_base + done * OCB_ROW_BYTES, hp + (size_t)b * block_rows * OCB_ROW_BYTES,
-                                        take * OCB_ROW_BYTES, cudaMemcpyHostToDevice, cx.stream);
-                    if (e == cudaSuccess)
-                        e = cudaEventRecord(ev[b], cx.stream);
-                    k += take, done += take, blk++;
+                    const void *base = pass == 0 ? sources[i].rows : sources[i].xy;
+                    const size_t stride = pass == 0 ? sources[i].stride : sources[i].xy_stride;
+                    if (!base)
+                        continue;
+                    size_t k = 0;
+                    while (k < sources[i].n && e == cudaSuccess)
+                    {
+                        const size_t take = std::min(block_elems, sources[i].n - k);
+                        const int b = (int)(blk & 1);
+                        if (blk >= 2)
+                            e = cudaEventSynchronize(ev[b]);
+                        if (e != cudaSuccess)
+                            break;
+                        gather_rows(hp + (size_t)b * block_bytes, base, stride,
+                                    sources[i].idx ? sources[i].idx + k : nullptr, take, sources[i].idx ? 0 : k, elem);
+                        e = cudaMemcpyAsync(d_dst + done * elem, hp + (size_t)b * block_bytes, take * elem,
+                                            cudaMemcpyHostToDevice, cx.stream);
+                        if (e == cudaSuccess)
+                            e = cudaEventRecord(ev[b], cx.stream);
+                        k += take, done += take, blk++;
+                    }
                 }
             }
             if (e == cudaSuccess)
@@ -747,7 +768,7 @@ extern "C"
             return rc;
         }
         std::lock_guard<std::mutex> lk(g_sets_mu);
-        size_t off = 0;
+        size_t off = 0, off_xy = 0;
         for (size_t i = 0; i < count; i++)
         {
             auto it = g_sets.find(sources[i].set_id);
@@ -756,9 +777,15 @@ extern "C"
             DescSet s;
             s.n = sources[i].n;
             s.device = cx.device;
+            s.camera = sources[i].camera;
             if (sources[i].n)
             {
                 s.d_rows = d_base + off * OCB_ROW_BYTES;
+                if (sources[i].xy)
+                {
+                    s.d_xy = d_base + xy_base + off_xy * XY_BYTES;
+                    off_xy += sources[i].n;
+                }
                 s.arena = arena;
                 arena->live++;
             }
@@ -766,6 +793,22 @@ extern "C"
             g_sets[sources[i].set_id] = s;
         }
         return 0;
+    }
+
+    int ocb_register_descriptors_batch(const ocb_set_source *sources, size_t count)
+    {
+        if (count == 0)
+            return 0;
+        if (!sources)
+            return fail_invalid("sources");
+        std::vector<ocb_image_source> img(count);
+        for (size_t i = 0; i < count; i++)
+        {
+            memset(&img[i], 0, sizeof img[i]);
+            img[i].set_id = sources[i].set_id, img[i].rows = sources[i].rows, img[i].stride = sources[i].stride;
+            img[i].idx = sources[i].idx, img[i].n = sources[i].n;
+        }
+        return ocb_register_images_batch(img.data(), count);
     }
 
     void *ocb_host_alloc(size_t bytes)
@@ -881,6 +924,115 @@ extern "C"
         OCB_CUDA(cudaStreamSynchronize(bulk));
         if (out_end && !out_pinned)
             memcpy(out, hp + s_out, out_end * sizeof(ocb_top2));
+        return 0;
+    }
+
+    int ocb_match_pairs_ratio(const ocb_pair *pairs, size_t n_pairs, ocb_match *out, size_t out_capacity,
+                              uint64_t *out_offsets)
+    {
+        if (!out_offsets)
+            return fail_invalid("null pointer");
+        out_offsets[0] = 0;
+        if (n_pairs == 0)
+            return 0;
+        if (!pairs || (!out && out_capacity))
+            return fail_invalid("null pointer");
+        if (n_pairs >= (1ull << 31))
+            return fail_invalid("too many pairs");
+        ThreadCtx &cx = t_ctx;
+        int rc = cx.ensure();
+        if (rc)
+            return rc;
+        cudaStream_t bulk = cx.bulk;
+        std::vector<K1Problem> pr(n_pairs);
+        memset(pr.data(), 0, sizeof(K1Problem) * n_pairs);
+        std::vector<uint64_t> top_off(n_pairs + 1, 0);
+        {
+            std::lock_guard<std::mutex> lk(g_sets_mu);
+            for (size_t p = 0; p < n_pairs; p++)
+            {
+                auto a = g_sets.find(pairs[p].query_set), b = g_sets.find(pairs[p].candidate_set);
+                if (a == g_sets.end() || b == g_sets.end())
+                {
+                    set_last_error("unknown descriptor set in pair list");
+                    return OCB_E_NOT_FOUND;
+                }
+                if (a->second.device != cx.device || b->second.device != cx.device)
+                    return fail_invalid("descriptor set registered on another device");
+                pr[p].q = static_cast<const uint4 *>(a->second.d_rows), pr[p].n_q = (uint32_t)a->second.n;
+                pr[p].c = static_cast<const uint4 *>(b->second.d_rows), pr[p].n_c = (uint32_t)b->second.n;
+                top_off[p + 1] = top_off[p] + a->second.n;
+            }
+        }
+        const uint64_t rows_total = top_off[n_pairs];
+        K1Plan plan = k1_plan(pr.data(), n_pairs, sm_count(cx.device));
+        if ((uint64_t)plan.total_items >= 0x7FFFFFFFull)
+            return fail_invalid("too many work items for one submission");
+        const size_t table_bytes = sizeof(K1Problem) * n_pairs, k5_bytes = sizeof(K5Pair) * n_pairs;
+        size_t state_total = 0;
+        for (size_t p = 0; p < n_pairs; p++)
+            state_total += align_up(k1_state_bytes(pr[p]), 16);
+        // device block: [K1 table][K5 table][top-2 records of every query][K1 state][offsets][ticket][survivors]
+        Carver cv;
+        const size_t o_tab = cv.take(table_bytes), o_k5 = cv.take(k5_bytes), o_top = cv.take(rows_total * sizeof(ocb_top2));
+        const size_t o_state = cv.take(state_total), o_off = cv.take((n_pairs + 1) * sizeof(uint64_t));
+        const size_t o_ticket = cv.take(sizeof(uint32_t)), o_out = cv.take(rows_total * sizeof(ocb_match));
+        rc = cx.dev_reserve(cv.off);
+        if (rc)
+            return rc;
+        const bool out_pinned = out_capacity && is_pinned_host(out), off_pinned = is_pinned_host(out_offsets);
+        Carver sv;
+        const size_t s_tab = sv.take(table_bytes), s_k5 = sv.take(k5_bytes);
+        const size_t s_off = sv.take((n_pairs + 1) * sizeof(uint64_t));
+        const size_t s_out = sv.take(out_pinned ? 0 : rows_total * sizeof(ocb_match));
+        rc = cx.pinned_reserve(sv.off);
+        if (rc)
+            return rc;
+        char *d = static_cast<char *>(cx.dev.p);
+        char *hp = static_cast<char *>(cx.pinned.p);
+        K5Pair *k5 = reinterpret_cast<K5Pair *>(hp + s_k5);
+        size_t state_off = 0;
+        for (size_t p = 0; p < n_pairs; p++)
+        {
+            pr[p].out = reinterpret_cast<ocb_top2 *>(d + o_top) + top_off[p];
+            k1_bind_state(pr[p], d + o_state + state_off);
+            state_off += align_up(k1_state_bytes(pr[p]), 16);
+            k5[p].top = pr[p].out, k5[p].n_q = pr[p].n_q, k5[p].pad = 0;
+        }
+        if (state_total)
+            OCB_CUDA(cudaMemsetAsync(d + o_state, 0, state_total, bulk));
+        // both tables travel in one copy (they are adjacent in the staging image and on the device)
+        if (o_k5 - o_tab != s_k5 - s_tab)
+            return fail_invalid("internal: staging layout");
+        memcpy(hp + s_tab, pr.data(), table_bytes);
+        OCB_CUDA(cudaMemcpyAsync(d + o_tab, hp + s_tab, (s_k5 - s_tab) + k5_bytes, cudaMemcpyHostToDevice, bulk));
+        static_assert(sizeof(K1Problem) % 8 == 0, "tables are carved at the same relative offsets on both sides");
+        const K1Problem *d_tab = n_pairs > (size_t)K1_INLINE ? reinterpret_cast<const K1Problem *>(d + o_tab) : nullptr;
+        rc = k1_launch(d_tab, pr.data(), n_pairs, plan, bulk);
+        if (rc)
+            return rc;
+        rc = k5_ratio_compact(reinterpret_cast<const K5Pair *>(d + o_k5), n_pairs,
+                              reinterpret_cast<unsigned long long *>(d + o_off),
+                              reinterpret_cast<uint32_t *>(d + o_ticket), reinterpret_cast<ocb_match *>(d + o_out), bulk);
+        if (rc)
+            return rc;
+        // the offsets first (they say how many survivors there are), then exactly that many records
+        OCB_CUDA(cudaMemcpyAsync(off_pinned ? (void *)out_offsets : (void *)(hp + s_off), d + o_off,
+                                 (n_pairs + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, bulk));
+        OCB_CUDA(cudaStreamSynchronize(bulk));
+        if (!off_pinned)
+            memcpy(out_offsets, hp + s_off, (n_pairs + 1) * sizeof(uint64_t));
+        const uint64_t total = out_offsets[n_pairs];
+        if (total > out_capacity)
+            return fail_invalid("out_capacity is smaller than the number of surviving matches");
+        if (total)
+        {
+            OCB_CUDA(cudaMemcpyAsync(out_pinned ? (void *)out : (void *)(hp + s_out), d + o_out,
+                                     total * sizeof(ocb_match), cudaMemcpyDeviceToHost, bulk));
+            OCB_CUDA(cudaStreamSynchronize(bulk));
+            if (!out_pinned)
+                memcpy(out, hp + s_out, total * sizeof(ocb_match));
+        }
         return 0;
     }
 
@@ -1432,6 +1584,155 @@ extern "C"
             OCB_CUDA(cudaStreamSynchronize(cx.stream)); // the staging area is reused by the next call
         }
         cx.batch_valid = true;
+        return 0;
+    }
+
+    int ocb_corr_bind_batch_matches(const ocb_match_set *sets, size_t count)
+    {
+        ThreadCtx &cx = t_ctx;
+        int rc = cx.ensure();
+        if (rc)
+            return rc;
+        cx.batch_valid = false;
+        cx.batch_sets.clear();
+        if (count && !sets)
+            return fail_invalid("sets");
+        // batch block (stays bound): per set [n][7] rows + evaluation order, laid out like ocb_corr_bind_batch;
+        // per-call block: [K6 table][matches of every set]
+        Carver cv, in_cv;
+        cx.batch_sets.resize(count);
+        std::vector<K6Set> tab(count);
+        std::vector<size_t> o_match(count), o_order(count);
+        const size_t o_tab = in_cv.take(count * sizeof(K6Set));
+        uint32_t ctas = 0;
+        {
+            std::lock_guard<std::mutex> lk(g_sets_mu);
+            for (size_t i = 0; i < count; i++)
+            {
+                const ocb_match_set &ms = sets[i];
+                if (ms.n >= 0xFFFFFFFFull || (ms.n && !ms.matches))
+                    return fail_invalid("match set");
+                if (!order_in_range(ms.order, ms.n))
+                    return fail_invalid("order entry out of range");
+                K6Set &k = tab[i];
+                memset(&k, 0, sizeof k);
+                if (ms.n)
+                {
+                    auto a = g_sets.find(ms.set_1), b = g_sets.find(ms.set_2);
+                    if (a == g_sets.end() || b == g_sets.end())
+                    {
+                        set_last_error("unknown image set in match set");
+                        return OCB_E_NOT_FOUND;
+                    }
+                    if (a->second.device != cx.device || b->second.device != cx.device)
+                        return fail_invalid("image set registered on another device");
+                    if (!a->second.d_xy || !b->second.d_xy)
+                        return fail_invalid("image set was registered without keypoints (ocb_register_images_batch)");
+                    uint32_t worst_q = 0, worst_k = 0;
+                    for (size_t m = 0; m < ms.n; m++)
+                    {
+                        worst_q = std::max(worst_q, ms.matches[m].query_k);
+                        worst_k = std::max(worst_k, ms.matches[m].best_k);
+                    }
+                    if (worst_q >= a->second.n || worst_k >= b->second.n)
+                        return fail_invalid("match position out of range");
+                    k.xy1 = static_cast<const double2 *>(a->second.d_xy);
+                    k.xy2 = static_cast<const double2 *>(b->second.d_xy);
+                    k.cam1 = a->second.camera, k.cam2 = b->second.camera;
+                }
+                k.n = (uint32_t)ms.n;
+                k.cta_begin = ctas;
+                ctas += k6_set_ctas(k.n);
+                cx.batch_sets[i].n = ms.n;
+                cx.batch_sets[i].has_order = ms.order != nullptr && ms.n > 0;
+                cx.batch_sets[i].o_c7 = cv.take(ms.n * 7 * sizeof(double));
+                cx.batch_sets[i].o_ord = cv.take(cx.batch_sets[i].has_order ? ms.n * sizeof(uint32_t) : 0);
+                o_match[i] = in_cv.take(ms.n * sizeof(ocb_match));
+                o_order[i] = in_cv.take(cx.batch_sets[i].has_order ? ms.n * sizeof(uint32_t) : 0);
+            }
+        }
+        const size_t total = cv.off;
+        if (total > cx.batch.cap)
+        {
+            OCB_CUDA(cudaStreamSynchronize(cx.stream));
+            if (cx.batch.p)
+                OCB_CUDA(cudaFree(cx.batch.p));
+            cx.batch = Buf();
+            const size_t cap = std::max(total + total / 2, (size_t)1 << 20);
+            OCB_CUDA(cudaMalloc(&cx.batch.p, cap));
+            cx.batch.cap = cap;
+        }
+        if (total)
+        {
+            // staging image: [per-call block][image of the batch block]. Matches and evaluation orders go up in the
+            // per-call block (one copy); K6 writes the rows and moves the orders into the batch block, whose image
+            // comes back in one copy when the caller wants the rows
+            if ((rc = cx.dev_reserve(in_cv.off)) || (rc = cx.pinned_reserve(in_cv.off + total)))
+                return rc;
+            char *d = static_cast<char *>(cx.dev.p);
+            char *b = static_cast<char *>(cx.batch.p);
+            char *hp = static_cast<char *>(cx.pinned.p);
+            char *hb = hp + in_cv.off;
+            for (size_t i = 0; i < count; i++)
+            {
+                if (sets[i].n == 0)
+                    continue;
+                tab[i].matches = reinterpret_cast<const ocb_match *>(d + o_match[i]);
+                tab[i].c7 = reinterpret_cast<double *>(b + cx.batch_sets[i].o_c7);
+                memcpy(hp + o_match[i], sets[i].matches, sets[i].n * sizeof(ocb_match));
+                if (cx.batch_sets[i].has_order)
+                {
+                    memcpy(hp + o_order[i], sets[i].order, sets[i].n * sizeof(uint32_t));
+                    tab[i].order_src = reinterpret_cast<const uint32_t *>(d + o_order[i]);
+                    tab[i].order_dst = reinterpret_cast<uint32_t *>(b + cx.batch_sets[i].o_ord);
+                }
+            }
+            memcpy(hp + o_tab, tab.data(), count * sizeof(K6Set));
+            OCB_CUDA(cudaMemcpyAsync(d, hp, in_cv.off, cudaMemcpyHostToDevice, cx.stream));
+            if ((rc = k6_rays(reinterpret_cast<const K6Set *>(d + o_tab), count, ctas, cx.stream)))
+                return rc;
+            bool want_out = false;
+            for (size_t i = 0; i < count; i++)
+                want_out |= sets[i].n && sets[i].corr_out;
+            if (want_out)
+                OCB_CUDA(cudaMemcpyAsync(hb, b, total, cudaMemcpyDeviceToHost, cx.stream));
+            OCB_CUDA(cudaStreamSynchronize(cx.stream)); // the staging area is reused by the next call
+            if (want_out)
+                for (size_t i = 0; i < count; i++)
+                    if (sets[i].n && sets[i].corr_out)
+                        memcpy(sets[i].corr_out, hb + cx.batch_sets[i].o_c7, sets[i].n * 7 * sizeof(double));
+        }
+        cx.batch_valid = true;
+        return 0;
+    }
+
+    int ocb_image_to_3d(const double *xy, size_t n, const ocb_camera *camera, double *rays)
+    {
+        if (n >= 0xFFFFFFFFull)
+            return fail_invalid("n must fit in 32 bits");
+        if (n == 0)
+            return 0;
+        if (!xy || !camera || !rays)
+            return fail_invalid("null pointer");
+        ThreadCtx &cx = t_ctx;
+        int rc = cx.ensure();
+        if (rc)
+            return rc;
+        const size_t ib = n * 2 * sizeof(double), ob = n * 3 * sizeof(double);
+        Carver cv;
+        const size_t o_in = cv.take(ib), o_out = cv.take(ob);
+        if ((rc = cx.dev_reserve(cv.off)) || (rc = cx.pinned_reserve(cv.off)))
+            return rc;
+        char *d = static_cast<char *>(cx.dev.p);
+        char *hp = static_cast<char *>(cx.pinned.p);
+        if ((rc = upload(cx, d + o_in, xy, ib, o_in)))
+            return rc;
+        if ((rc = k6_points(reinterpret_cast<const double *>(d + o_in), n, *camera, reinterpret_cast<double *>(d + o_out),
+                            cx.stream)))
+            return rc;
+        OCB_CUDA(cudaMemcpyAsync(hp + o_out, d + o_out, ob, cudaMemcpyDeviceToHost, cx.stream));
+        OCB_CUDA(cudaStreamSynchronize(cx.stream));
+        memcpy(rays, hp + o_out, ob);
         return 0;
     }
 

@@ -86,6 +86,30 @@ int k1_launch(const K1Problem *d_problems, const K1Problem *h_problems, size_t n
               cudaStream_t stream);
 int k1_queries_per_cta();
 
+// ---- K5 / K6 launch interface (link_tail.cu) ----------------------------------------------------------------
+struct K5Pair
+{
+    const ocb_top2 *top; // [n_q] records of one pair (device)
+    uint32_t n_q, pad;
+};
+// counts the ratio-test survivors per pair, turns the counts into exclusive offsets (d_offsets [n_pairs + 1]) and writes
+// the survivors of pair p in query order at d_out + d_offsets[p]
+int k5_ratio_compact(const K5Pair *d_pairs, size_t n_pairs, unsigned long long *d_offsets, uint32_t *d_ticket,
+                     ocb_match *d_out, cudaStream_t stream);
+struct K6Set
+{
+    const double2 *xy1, *xy2; // keypoint locations of the two registered sets
+    const ocb_match *matches; // [n] sorted matches (device)
+    double *c7;               // [n][7] out
+    const uint32_t *order_src; // nullable: evaluation order as uploaded ...
+    uint32_t *order_dst;       // ... moved next to the rows (the layout ocb_score_requests reads)
+    ocb_camera cam1, cam2;
+    uint32_t n, cta_begin;
+};
+uint32_t k6_set_ctas(uint32_t n);
+int k6_rays(const K6Set *d_sets, size_t n_sets, uint32_t total_ctas, cudaStream_t stream);
+int k6_points(const double *d_xy, size_t n, const ocb_camera &cam, double *d_rays, cudaStream_t stream);
+
 // ---- K4 launch interface (hamming_lists.cu) ----------------------------------------------------------------
 int k4_launch(const void *d_q_rows, const void *d_c_rows, const uint32_t *d_list_query, const uint64_t *d_list_begin,
               const uint32_t *d_list_candidates, size_t n_lists, ocb_top2 *d_out, cudaStream_t stream);

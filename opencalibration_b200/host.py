@@ -74,8 +74,15 @@ def lib():
     L.ocbh_run_parallel_match.argtypes = [_u64p, _u64p, sz, sz, sz, i32, _szp, _f64p]
     L.ocbh_image_to_3d.argtypes = [_f64p, sz, _f64p, _f64p]
     L.ocbh_image_to_3d.restype = None
-    L.ocbh_link_pairs.argtypes = [C.c_void_p, _szp, _f64p, sz, _szp, sz, i32, sz, i32, dbl]
+    L.ocbh_link_pairs.argtypes = [C.c_void_p, _szp, _f64p, sz, _szp, sz, i32, sz, i32, dbl, i32, i32, vp]
     L.ocbh_link_pairs.restype = C.c_void_p
+    L.ocbh_link_pack_matches.argtypes = [C.c_void_p, vp, vp, i32]
+    L.ocbh_link_pack_matches.restype = sz
+    L.ocbh_partition_pairs.argtypes = [vp, sz, _szp, sz, sz, vp, vp, vp]
+    L.ocbh_hilbert_index.argtypes = [i32, i32, i32]
+    L.ocbh_hilbert_index.restype = C.c_uint32
+    L.ocbh_hilbert_order.argtypes = [_f64p, sz, _szp]
+    L.ocbh_hilbert_order.restype = None
     L.ocbh_link_free.argtypes = [C.c_void_p]
     L.ocbh_link_free.restype = None
     L.ocbh_link_stats.argtypes = [C.c_void_p, _f64p]
@@ -380,6 +387,19 @@ class LinkResults:
                     relation_type=rt.value, poses=poses.reshape(4, 8).copy(), inlier_pixels=px[:ni].copy(),
                     inlier_idx=ix[:ni].copy())
 
+    def pack_matches(self, out=None, threads=0):
+        """All match lists as flat records -> (counts [n_pairs] uint64, records [total][3] uint32 = feature_index_1,
+        feature_index_2, integer Hamming distance), pair after pair. `out`: optional preallocated uint32 buffer (e.g. a
+        view of shared memory) that receives the records."""
+        counts = np.zeros(max(self.n_pairs, 1), np.uint64)
+        total = int(lib().ocbh_link_pack_matches(self.handle, counts.ctypes.data_as(C.c_void_p), None, 0))
+        if out is None:
+            out = np.zeros(max(total, 1) * 3, np.uint32)
+        assert out.dtype == np.uint32 and out.size >= total * 3 and out.flags["C_CONTIGUOUS"]
+        lib().ocbh_link_pack_matches(self.handle, counts.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p),
+                                     int(threads))
+        return counts[:self.n_pairs], out[:total * 3].reshape(total, 3)
+
     def close(self):
         if self.handle:
             lib().ocbh_link_free(self.handle)
@@ -393,16 +413,20 @@ class LinkResults:
 
 
 def link_pairs(feature_sets, cameras8, pairs, num_sparse=None, threads=0, pairs_per_submission=0, run_ransac=True,
-               spacing=0.0):
+               spacing=0.0, device_tail=True, n_devices=1, positions=None):
     """What LinkStage's closures compute for every (image, neighbour) pair (src/pipeline/link_stage.cpp:75-112), for
-    the whole pair list: feature_sets = FeatureSet per image, cameras8 = camera8() per image, pairs = [(i, j)]."""
+    the whole pair list: feature_sets = FeatureSet per image, cameras8 = camera8() per image, pairs = [(i, j)].
+    device_tail=False keeps the ratio test and the rays on the host (A/B). n_devices > 1: the pair list is partitioned
+    over that many GPUs of this process along the Hilbert curve of `positions` ([n][2]; None: image index order)."""
     n = len(feature_sets)
     h = (C.c_void_p * n)(*[s.handle for s in feature_sets])
     ns = np.zeros(n, np.uintp) if num_sparse is None else np.ascontiguousarray(num_sparse, np.uintp)
     cams = np.ascontiguousarray(cameras8, np.float64).reshape(n, 8)
     pr = np.ascontiguousarray(pairs, np.uintp).reshape(-1, 2)
+    pos = None if positions is None else np.ascontiguousarray(positions, np.float64).reshape(n, 2)
     res = lib().ocbh_link_pairs(h, ns, cams, n, pr, len(pr), int(threads), int(pairs_per_submission), int(run_ransac),
-                               float(spacing))
+                               float(spacing), int(bool(device_tail)), int(n_devices),
+                               None if pos is None else pos.ctypes.data_as(C.c_void_p))
     if not res:
         raise OcbError("host mirror: " + lib().ocbh_last_error().decode())
     return LinkResults(res, len(pr))
@@ -422,3 +446,32 @@ def ransac_batch(kind, corr_list, threads=0):
     _check(lib().ocbh_ransac_batch(kind, np.ascontiguousarray(allc), offsets, n, int(threads), scores, M18, inl, st))
     return [(float(scores[j]), M18[j].copy(), inl[int(offsets[j]):int(offsets[j + 1])].astype(bool),
              dict(iterations=int(st[j, 0]), improvements=int(st[j, 1]))) for j in range(n)]
+
+
+# ---- overlap-graph partition (host/partition.hpp) ----
+def hilbert_index(order, x, y):
+    return int(lib().ocbh_hilbert_index(int(order), int(x), int(y)))
+
+
+def hilbert_order(positions):
+    pos = np.ascontiguousarray(positions, np.float64).reshape(-1, 2)
+    out = np.zeros(max(len(pos), 1), np.uintp)
+    if len(pos):
+        lib().ocbh_hilbert_order(pos, len(pos), out)
+    return out[:len(pos)].astype(np.int64)
+
+
+def partition_pairs(positions, pairs, world):
+    """-> (owner [n_images] part of every image, pair_part [n_pairs] part of every pair, halo [world][n_images] bool).
+    positions None: the images' index order stands in for the Hilbert curve."""
+    pr = np.ascontiguousarray(pairs, np.uintp).reshape(-1, 2)
+    if positions is None:
+        raise ValueError("positions are required (pass an [n][2] array)")
+    pos = np.ascontiguousarray(positions, np.float64).reshape(-1, 2)
+    n = len(pos)
+    owner, part = np.zeros(max(n, 1), np.uint32), np.zeros(max(len(pr), 1), np.uint32)
+    halo = np.zeros((world, max(n, 1)), np.uint8)
+    _check(lib().ocbh_partition_pairs(pos.ctypes.data_as(C.c_void_p), n, pr, len(pr), int(world),
+                                      owner.ctypes.data_as(C.c_void_p), part.ctypes.data_as(C.c_void_p),
+                                      halo.ctypes.data_as(C.c_void_p)))
+    return owner[:n], part[:len(pr)], halo[:, :n].astype(bool)

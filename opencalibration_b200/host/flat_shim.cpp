@@ -3,6 +3,7 @@
 // call the mirror exactly as src/pipeline/link_stage.cpp:80-93 would, and flatten the results.
 #include "guided_match.hpp"
 #include "link_batch.hpp"
+#include "partition.hpp"
 #include "models_detail.hpp"
 
 #include <chrono>
@@ -531,9 +532,11 @@ extern "C"
         std::vector<camera_relations> relations;
         ocb_host::LinkStats stats;
     };
+    // device_tail: 1 = ratio test, compaction and rays on the device (default), 0 = on the host. n_devices > 1: the pair
+    // list is partitioned over that many GPUs of this process (positions2: [n_images][2], nullable).
     void *ocbh_link_pairs(const void *const *image_handles, const size_t *num_sparse, const double *cam8, size_t n_images,
                           const size_t *pairs2, size_t n_pairs, int threads, size_t pairs_per_submission, int run_ransac,
-                          double spacing)
+                          double spacing, int device_tail, int n_devices, const double *positions2)
     {
         auto *res = new LinkResultHandle;
         const int rc = guarded([&] {
@@ -558,7 +561,11 @@ extern "C"
             opt.run_ransac = run_ransac != 0;
             if (spacing > 0)
                 opt.coarse_spacing_pixels = spacing;
-            res->relations = ocb_host::link_pairs(images, pairs, opt, &res->stats);
+            opt.device_tail = device_tail != 0;
+            if (n_devices > 1)
+                res->relations = ocb_host::link_pairs_multi(images, pairs, positions2, n_devices, opt, &res->stats);
+            else
+                res->relations = ocb_host::link_pairs(images, pairs, opt, &res->stats);
         });
         if (rc)
         {
@@ -610,6 +617,64 @@ extern "C"
             inl_idx3[3 * i] = m.feature_index_1, inl_idx3[3 * i + 1] = m.feature_index_2, inl_idx3[3 * i + 2] = m.match_index;
         }
     }
+    // All match lists of a link result as one flat array of 12-byte records {feature_index_1, feature_index_2, integer
+    // Hamming distance} (distance = d * (1.0 / 486) exactly), pair after pair in pair order; counts[p] = matches of pair
+    // p. records == nullptr: only the counts. This is what a rank contributes to the host gather of the match lists.
+    size_t ocbh_link_pack_matches(const void *h, uint64_t *counts, uint32_t *records, int threads)
+    {
+        const auto &rel = static_cast<const LinkResultHandle *>(h)->relations;
+        std::vector<size_t> off(rel.size() + 1, 0);
+        for (size_t p = 0; p < rel.size(); p++)
+        {
+            counts[p] = rel[p].matches.size();
+            off[p + 1] = off[p] + rel[p].matches.size();
+        }
+        if (records)
+        {
+#pragma omp parallel for schedule(dynamic, 16) num_threads(threads > 0 ? threads : omp_get_num_procs())
+            for (size_t p = 0; p < rel.size(); p++)
+            {
+                uint32_t *out = records + 3 * off[p];
+                for (const feature_match &m : rel[p].matches)
+                {
+                    out[0] = (uint32_t)m.feature_index_1, out[1] = (uint32_t)m.feature_index_2;
+                    out[2] = (uint32_t)std::lround(m.distance * feature_2d::DESCRIPTOR_BITS);
+                    out += 3;
+                }
+            }
+        }
+        return off[rel.size()];
+    }
+
+    // ---- overlap-graph partition (partition.hpp): owner[i] = part of image i, pair_part[k] = part of pair k,
+    // halo[part * n_images + i] = 1 when image i is a halo image of that part
+    int ocbh_partition_pairs(const double *positions2, size_t n_images, const size_t *pairs2, size_t n_pairs, size_t world,
+                             uint32_t *owner, uint32_t *pair_part, uint8_t *halo)
+    {
+        return guarded([&] {
+            std::vector<ocb_host::LinkPair> pairs(n_pairs);
+            for (size_t p = 0; p < n_pairs; p++)
+                pairs[p] = ocb_host::LinkPair{pairs2[2 * p], pairs2[2 * p + 1]};
+            const std::vector<ocb_host::PairShard> shards = ocb_host::partition_pairs(positions2, n_images, pairs, world);
+            std::memset(halo, 0, world * n_images);
+            for (size_t r = 0; r < world; r++)
+            {
+                for (size_t i : shards[r].owned_images)
+                    owner[i] = (uint32_t)r;
+                for (size_t i : shards[r].halo_images)
+                    halo[r * n_images + i] = 1;
+                for (size_t k : shards[r].pair_ids)
+                    pair_part[k] = (uint32_t)r;
+            }
+        });
+    }
+    uint32_t ocbh_hilbert_index(int order, int x, int y) { return ocb_host::hilbert_index(order, x, y); }
+    void ocbh_hilbert_order(const double *positions2, size_t n, size_t *order_out)
+    {
+        const std::vector<size_t> o = ocb_host::hilbert_order(positions2, n);
+        std::memcpy(order_out, o.data(), n * sizeof(size_t));
+    }
+
     int ocbh_ransac_batch(int kind, const double *corr, const size_t *offsets, size_t n_jobs, int threads, double *scores,
                           double *M18, uint8_t *inl, size_t *stats2)
     {

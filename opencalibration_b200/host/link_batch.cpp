@@ -13,6 +13,8 @@
 #include <deque>
 #include <functional>
 #include <future>
+#include <limits>
+#include <map>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -90,6 +92,25 @@ void give_back_result_buffers(ResultBuffers &b)
     b.p.clear();
 }
 
+inline double as_distance(uint32_t d)
+{
+    // distance = count * (1.0 / DESCRIPTOR_BITS)  (match_features.cpp:79)
+    return d == OCB_DIST_INF ? std::numeric_limits<double>::infinity() : d * (1.0 / feature_2d::DESCRIPTOR_BITS);
+}
+
+ocb_camera camera_of(const DifferentiableCameraModel<double> &m)
+{
+    ocb_camera c;
+    std::memset(&c, 0, sizeof c);
+    c.focal_length_pixels = m.focal_length_pixels;
+    c.principal_point[0] = m.principle_point[0], c.principal_point[1] = m.principle_point[1];
+    for (int i = 0; i < 3; i++)
+        c.radial_distortion[i] = m.radial_distortion[i];
+    c.tangential_distortion[0] = m.tangential_distortion[0], c.tangential_distortion[1] = m.tangential_distortion[1];
+    c.projection_planar = m.projection_type == ProjectionType::PLANAR ? 1 : 0;
+    return c;
+}
+
 // the end of one LinkStage closure, after ransac (link_stage.cpp:95-108)
 void finish_pair(const ocb_host::LinkImage &img, const ocb_host::LinkImage &near_image, camera_relations &relations,
                  std::vector<feature_match> &&coarse_matches, const std::vector<correspondence> &coarse_correspondences,
@@ -108,11 +129,12 @@ void finish_pair(const ocb_host::LinkImage &img, const ocb_host::LinkImage &near
     }
 }
 
-// Long-lived helper threads for link_pairs (the submission thread and the extra tail consumers). libocb keeps a
-// per-thread context (two streams, device and page-locked staging areas, bound correspondences); a std::thread per
-// call would build and tear that context down every time, which costs tens of milliseconds - far more when the
-// process holds contexts on several GPUs. The threads are created on demand, parked between calls and never joined
-// (the pool is leaked on purpose: they must not run destructors after the CUDA runtime has shut down).
+// Long-lived helper threads for link_pairs (the submission threads and the extra tail consumers), one pool per device.
+// libocb keeps a per-thread context (two streams, device and page-locked staging areas, bound correspondences); a
+// std::thread per call would build and tear that context down every time, which costs tens of milliseconds, and a
+// thread that alternates between devices would rebuild it on every switch. The threads are created on demand, parked
+// between calls and never joined (the pools are leaked on purpose: they must not run destructors after the CUDA
+// runtime has shut down).
 class HelperThreads
 {
   public:
@@ -129,10 +151,15 @@ class HelperThreads
         cv_.notify_one();
         return done;
     }
-    static HelperThreads &instance()
+    static HelperThreads &instance(int device)
     {
-        static HelperThreads *pool = new HelperThreads;
-        return *pool;
+        static std::mutex mu;
+        static std::map<int, HelperThreads *> *pools = new std::map<int, HelperThreads *>;
+        std::lock_guard<std::mutex> lk(mu);
+        HelperThreads *&p = (*pools)[device];
+        if (!p)
+            p = new HelperThreads;
+        return *p;
     }
 
   private:
@@ -202,19 +229,32 @@ std::vector<camera_relations> link_pairs(const std::vector<LinkImage> &images, c
     }
     // the helper threads below work on the device the CALLER selected (ocb_set_device), not on the process default
     const int device = ocb_current_device();
+    const bool device_tail = options.device_tail;
+
+    // ---- submissions. The first ones are small and grow geometrically up to pairs_per_submission: the GPU starts on
+    // the first pairs as soon as THEIR images are resident, and the first results reach the tail workers early; after
+    // the ramp every submission is large enough to fill the SMs for tens of milliseconds.
+    const size_t per = std::max<size_t>(1, options.pairs_per_submission);
+    std::vector<std::pair<size_t, size_t>> chunk; // [begin, end) into `pairs`
+    for (size_t begin = 0, size = std::min<size_t>(per, std::max<size_t>(1, options.first_submission)); begin < n_pairs;)
+    {
+        const size_t end = std::min(n_pairs, begin + size);
+        chunk.emplace_back(begin, end);
+        begin = end;
+        size = std::min(per, size * 2);
+    }
+    const size_t n_chunks = chunk.size();
 
     // ---- per image, once: the subsample every closure of that image would compute (link_stage.cpp:63-65,80-81) and
-    // the upload of those rows. Only images that occur in a pair are touched. The images are prepared in the order
-    // in which the submissions need them, by a helper thread that runs ahead of the matching: the first submission
-    // starts as soon as its own images are resident, and the rest of the preparation hides behind the GPU.
-    const size_t per = std::max<size_t>(1, options.pairs_per_submission);
-    const size_t n_chunks = (n_pairs + per - 1) / per;
-    std::vector<size_t> order;               // used images, by first use
+    // the upload of those rows (+ keypoints and camera model for the device-side rays). Only images that occur in a
+    // pair are touched. The images are prepared in the order in which the submissions need them, by a helper thread
+    // that runs ahead of the matching.
+    std::vector<size_t> order;                       // used images, by first use
     std::vector<size_t> position(n_img, ~(size_t)0); // image -> index in `order`
     std::vector<size_t> chunk_needs(n_chunks, 0);    // images of `order` that must be resident before chunk c starts
     for (size_t c = 0; c < n_chunks; c++)
     {
-        for (size_t p = c * per; p < std::min(n_pairs, (c + 1) * per); p++)
+        for (size_t p = chunk[c].first; p < chunk[c].second; p++)
             for (size_t i : {pairs[p].image_1, pairs[p].image_2})
                 if (position[i] == ~(size_t)0)
                 {
@@ -229,69 +269,86 @@ std::vector<camera_relations> link_pairs(const std::vector<LinkImage> &images, c
     std::vector<char> registered(n_img, 0);
     std::mutex mu;
     std::condition_variable cv;
-    bool stop = false;       // set on the first error: everybody drains
-    size_t prepared = 0;     // images of `order` that are subsampled and resident
+    bool stop = false;   // set on the first error: everybody drains
+    size_t prepared = 0; // images of `order` that are subsampled and resident
     double prepare_seconds = 0;
     auto prepare = [&]() {
         ocb_set_device(device);
         const size_t batch = (size_t)std::max(32, 4 * threads);
-        for (size_t begin = 0; begin < order.size(); begin += batch)
+        size_t begin = 0;
+        for (size_t c = 0; c < n_chunks; c++)
         {
+            // everything chunk c still needs, in batches (a batch is one device allocation and one pipelined upload)
+            while (begin < chunk_needs[c])
             {
-                std::lock_guard<std::mutex> lk(mu);
-                if (stop)
-                    return;
-            }
-            const auto t0 = clock_type::now();
-            const size_t end = std::min(order.size(), begin + batch);
-            std::string local_error;
+                {
+                    std::lock_guard<std::mutex> lk(mu);
+                    if (stop)
+                        return;
+                }
+                const auto t0 = clock_type::now();
+                const size_t end = std::min(chunk_needs[c], begin + batch);
+                std::string local_error;
 #pragma omp parallel for schedule(dynamic, 1) num_threads(threads)
-            for (size_t u = begin; u < end; u++)
-            {
-                const size_t i = order[u];
-                try
-                {
-                    indices[i] = spatially_subsample_feature_indices(*images[i].features, options.coarse_spacing_pixels,
-                                                                     images[i].num_sparse_features);
-                }
-                catch (const std::exception &e)
-                {
-#pragma omp critical(ocb_link_error)
-                    local_error = e.what();
-                }
-            }
-            // upload: one batched registration (one device allocation, pipelined gather + copy), rows taken straight
-            // from the feature vectors through the subsample indices
-            if (local_error.empty())
-            {
-                std::vector<ocb_set_source> src;
                 for (size_t u = begin; u < end; u++)
                 {
                     const size_t i = order[u];
-                    const std::vector<feature_2d> &f = *images[i].features;
-                    src.push_back(ocb_set_source{id_base + i,
-                                                 f.empty() ? nullptr : static_cast<const void *>(&f[0].descriptor),
-                                                 sizeof(feature_2d), indices[i].data(), indices[i].size()});
+                    try
+                    {
+                        indices[i] = spatially_subsample_feature_indices(
+                            *images[i].features, options.coarse_spacing_pixels, images[i].num_sparse_features);
+                    }
+                    catch (const std::exception &e)
+                    {
+#pragma omp critical(ocb_link_error)
+                        local_error = e.what();
+                    }
                 }
-                if (ocb_register_descriptors_batch(src.data(), src.size()))
-                    local_error = std::string("ocb_register_descriptors_batch: ") + ocb_last_error();
+                // upload: one batched registration, rows and keypoints taken straight from the feature vectors
+                // through the subsample indices
+                if (local_error.empty())
+                {
+                    std::vector<ocb_image_source> src;
+                    for (size_t u = begin; u < end; u++)
+                    {
+                        const size_t i = order[u];
+                        const std::vector<feature_2d> &f = *images[i].features;
+                        ocb_image_source s;
+                        std::memset(&s, 0, sizeof s);
+                        s.set_id = id_base + i;
+                        s.rows = f.empty() ? nullptr : static_cast<const void *>(&f[0].descriptor);
+                        s.stride = sizeof(feature_2d);
+                        s.idx = indices[i].data();
+                        s.n = indices[i].size();
+                        if (device_tail && options.run_ransac)
+                        {
+                            s.xy = f.empty() ? nullptr : static_cast<const void *>(&f[0].location);
+                            s.xy_stride = sizeof(feature_2d);
+                            s.camera = camera_of(images[i].model);
+                        }
+                        src.push_back(s);
+                    }
+                    if (ocb_register_images_batch(src.data(), src.size()))
+                        local_error = std::string("ocb_register_images_batch: ") + ocb_last_error();
+                    else
+                        for (const ocb_image_source &sset : src)
+                            registered[sset.set_id - id_base] = 1;
+                }
+                std::lock_guard<std::mutex> lk(mu);
+                prepare_seconds += since(t0);
+                if (!local_error.empty())
+                {
+                    if (error.empty())
+                        error = local_error;
+                    stop = true;
+                }
                 else
-                    for (const ocb_set_source &sset : src)
-                        registered[sset.set_id - id_base] = 1;
+                    prepared = end;
+                cv.notify_all();
+                if (stop)
+                    return;
+                begin = end;
             }
-            std::lock_guard<std::mutex> lk(mu);
-            prepare_seconds += since(t0);
-            if (!local_error.empty())
-            {
-                if (error.empty())
-                    error = local_error;
-                stop = true;
-            }
-            else
-                prepared = end;
-            cv.notify_all();
-            if (stop)
-                return;
         }
     };
     auto release_sets = [&]() {
@@ -301,18 +358,18 @@ std::vector<camera_relations> link_pairs(const std::vector<LinkImage> &images, c
     };
     LinkStats st;
 
-    // ---- submissions: producers (parked helper threads, see HelperThreads) keep the GPU matching the next
-    // chunks (into page-locked result buffers, one per slot) while `tail_workers` consumer threads, each with its own
-    // OpenMP team, finish the chunks already matched. Several consumers are needed because a chunk's RANSAC rounds
-    // are a serial chain of GPU round trips: with one consumer the chain's latency, not the host cores, bounds the tail.
+    // ---- producers (parked helper threads, see HelperThreads) keep the GPU matching the next submissions (into
+    // page-locked result buffers, one per slot) while `tail_workers` consumer threads, each with its own OpenMP team,
+    // finish the submissions already matched. Several consumers are needed because a submission's RANSAC rounds are a
+    // serial chain of GPU round trips: with one consumer the chain's latency, not the host cores, bounds the tail.
     size_t max_rows = 1; // upper bound: the subsample keeps at most the sparse features of an image
     for (size_t c = 0; c < n_chunks; c++)
     {
         size_t rows = 0;
-        for (size_t p = c * per; p < std::min(n_pairs, (c + 1) * per); p++)
+        for (size_t p = chunk[c].first; p < chunk[c].second; p++)
         {
             const LinkImage &im = images[pairs[p].image_1];
-            rows += im.num_sparse_features ? std::min(im.num_sparse_features, im.features->size()) : im.features->size();
+            rows += im.num_sparse_features ? im.num_sparse_features : im.features->size();
         }
         max_rows = std::max(max_rows, rows);
     }
@@ -324,8 +381,8 @@ std::vector<camera_relations> link_pairs(const std::vector<LinkImage> &images, c
     const size_t n_slots = (size_t)workers + n_producers;
     struct Slot
     {
-        ocb_top2 *top = nullptr;
-        std::vector<uint64_t> offsets;
+        void *records = nullptr;       // device_tail: ocb_match survivors (dense); else ocb_top2 per query row
+        std::vector<uint64_t> offsets; // device_tail: [pairs + 1] survivor offsets; else [pairs] row offsets
         double gpu_seconds = 0;
         size_t chunk = 0; // which submission the records belong to
         size_t next = 0;  // the submission this slot takes next: k, k + n_slots, ... strictly in that order, whichever
@@ -338,14 +395,15 @@ std::vector<camera_relations> link_pairs(const std::vector<LinkImage> &images, c
         slot[k].next = k;
     // page-locked result buffers are expensive to create (the driver maps them into every visible GPU), so they are
     // kept between calls and only grow
-    ResultBuffers buffers = take_result_buffers(n_slots, max_rows * sizeof(ocb_top2));
+    const size_t record_bytes = device_tail ? sizeof(ocb_match) : sizeof(ocb_top2);
+    ResultBuffers buffers = take_result_buffers(n_slots, max_rows * record_bytes);
     if (buffers.p.size() != n_slots)
     {
         give_back_result_buffers(buffers);
         throw std::runtime_error(std::string("ocb_host_alloc: ") + ocb_last_error());
     }
     for (size_t k = 0; k < n_slots; k++)
-        slot[k].top = static_cast<ocb_top2 *>(buffers.p[k]);
+        slot[k].records = buffers.p[k];
     st.seconds_setup = since(t_begin);
     auto produce = [&](size_t first) {
         ocb_set_device(device);
@@ -361,9 +419,9 @@ std::vector<camera_relations> link_pairs(const std::vector<LinkImage> &images, c
                     return;
                 sl.busy = true;
             }
-            const size_t begin = c * per, end = std::min(n_pairs, begin + per);
+            const size_t begin = chunk[c].first, end = chunk[c].second;
             std::vector<ocb_pair> sub(end - begin);
-            sl.offsets.resize(sub.size());
+            sl.offsets.assign(sub.size() + 1, 0);
             uint64_t total = 0;
             for (size_t p = begin; p < end; p++)
             {
@@ -372,13 +430,18 @@ std::vector<camera_relations> link_pairs(const std::vector<LinkImage> &images, c
                 total += indices[pairs[p].image_1].size();
             }
             const auto t0 = clock_type::now();
-            const int rc = ocb_match_pairs(sub.data(), sub.size(), sl.top, sl.offsets.data());
+            int rc;
+            if (device_tail) // K1 + ratio test + compaction on the device: only the survivors come back
+                rc = ocb_match_pairs_ratio(sub.data(), sub.size(), static_cast<ocb_match *>(sl.records), max_rows,
+                                           sl.offsets.data());
+            else
+                rc = ocb_match_pairs(sub.data(), sub.size(), static_cast<ocb_top2 *>(sl.records), sl.offsets.data());
             sl.gpu_seconds = since(t0);
             std::lock_guard<std::mutex> lk(mu);
             if (rc)
             {
                 if (error.empty())
-                    error = std::string("ocb_match_pairs: ") + ocb_last_error();
+                    error = std::string(device_tail ? "ocb_match_pairs_ratio: " : "ocb_match_pairs: ") + ocb_last_error();
                 stop = true;
             }
             sl.chunk = c;
@@ -393,7 +456,7 @@ std::vector<camera_relations> link_pairs(const std::vector<LinkImage> &images, c
     std::vector<camera_relations> relations(n_pairs);
     std::atomic<size_t> next_chunk{0}, total_matches{0}, total_inliers{0};
     double tail_seconds = 0, gpu_seconds = 0;
-    double phase_seconds[3] = {0, 0, 0}; // consumer wall time in (a) ratio test + rays, (b) RANSAC rounds, (c) finish
+    double phase_seconds[3] = {0, 0, 0}; // consumer wall time in (a) ratio test / sort / rays, (b) RANSAC, (c) finish
     auto fail = [&](const std::string &what) {
         std::lock_guard<std::mutex> lk(mu);
         if (error.empty())
@@ -415,29 +478,62 @@ std::vector<camera_relations> link_pairs(const std::vector<LinkImage> &images, c
                 if (stop)
                     return;
             }
-            const size_t begin = c * per, end = std::min(n_pairs, begin + per), cn = end - begin;
+            const size_t begin = chunk[c].first, end = chunk[c].second, cn = end - begin;
             const auto t0 = clock_type::now();
             std::string local_error;
             size_t n_matches = 0, n_inl = 0;
-            // (a) per pair: ratio test + sort -> match list, pixel -> ray (link_stage.cpp:83-88)
+            // (a) per pair: [ratio test +] the reference's std::sort -> match list (link_stage.cpp:83-85);
+            //     rays (:87-88) on the host, or left to the device (K6) when the RANSAC runs are bound
             std::vector<std::vector<feature_match>> coarse_matches(cn);
             std::vector<std::vector<correspondence>> coarse_correspondences(cn);
+            std::vector<std::vector<ocb_match>> sorted(device_tail && options.run_ransac ? cn : 0);
 #pragma omp parallel for schedule(dynamic, 1) num_threads(team) reduction(+ : n_matches)
             for (size_t p = begin; p < end; p++)
             {
                 try
                 {
+                    const size_t k = p - begin;
                     const LinkImage &img = images[pairs[p].image_1], &near_image = images[pairs[p].image_2];
-                    coarse_matches[p - begin] =
-                        detail::matches_from_top2(indices[pairs[p].image_1], indices[pairs[p].image_2],
-                                                  sl.top + sl.offsets[p - begin], nullptr, nullptr);
-                    n_matches += coarse_matches[p - begin].size();
-                    if (options.run_ransac)
-                        coarse_correspondences[p - begin] =
-                            distort_keypoints(*img.features, *near_image.features, coarse_matches[p - begin], img.model,
-                                              near_image.model);
+                    const std::vector<size_t> &idx1 = indices[pairs[p].image_1], &idx2 = indices[pairs[p].image_2];
+                    if (device_tail)
+                    {
+                        // Survivors arrive in query order, the order in which match_features.cpp:71-97 emits them.
+                        // std::sort's sequence of comparisons and moves depends only on the comparator's answers, and
+                        // a.d > b.d <=> a.d * (1.0 / 486) > b.d * (1.0 / 486) for these integers, so sorting the
+                        // 12-byte records yields the permutation the reference's sort (:100-101) produces.
+                        const ocb_match *first = static_cast<const ocb_match *>(sl.records) + sl.offsets[k];
+                        std::vector<ocb_match> recs(first, first + (sl.offsets[k + 1] - sl.offsets[k]));
+                        std::sort(recs.begin(), recs.end(),
+                                  [](const ocb_match &f1, const ocb_match &f2) -> bool { return f1.best_d > f2.best_d; });
+                        std::vector<feature_match> &out = coarse_matches[k];
+                        out.resize(recs.size());
+                        for (size_t i = 0; i < recs.size(); i++)
+                            out[i] = feature_match{idx1[recs[i].query_k], idx2[recs[i].best_k], as_distance(recs[i].best_d)};
+                        if (options.run_ransac)
+                        {
+                            // the rays are computed on the device when the runs are bound; the driver only needs the
+                            // qualities beforehand (PROSAC order, ransac.cpp:72-90)
+                            std::vector<correspondence> &corr = coarse_correspondences[k];
+                            corr.resize(recs.size());
+                            for (size_t i = 0; i < recs.size(); i++)
+                                corr[i].quality = out[i].distance;
+                            if (recs.size() < homography_model::MINIMUM_POINTS) // never bound (ransac.cpp:64-70)
+                                corr = distort_keypoints(*img.features, *near_image.features, out, img.model,
+                                                         near_image.model);
+                            sorted[k] = std::move(recs);
+                        }
+                    }
                     else
-                        relations[p].matches = std::move(coarse_matches[p - begin]);
+                    {
+                        coarse_matches[k] = detail::matches_from_top2(
+                            idx1, idx2, static_cast<const ocb_top2 *>(sl.records) + sl.offsets[k], nullptr, nullptr);
+                        if (options.run_ransac)
+                            coarse_correspondences[k] = distort_keypoints(*img.features, *near_image.features,
+                                                                          coarse_matches[k], img.model, near_image.model);
+                    }
+                    n_matches += coarse_matches[k].size();
+                    if (!options.run_ransac)
+                        relations[p].matches = std::move(coarse_matches[k]);
                 }
                 catch (const std::exception &e)
                 {
@@ -449,7 +545,7 @@ std::vector<camera_relations> link_pairs(const std::vector<LinkImage> &images, c
             const double t_a = since(t0);
             double t_b = t_a;
             {
-                // the K1 records have been consumed: the slot can take the next submission
+                // the records have been consumed: the slot can take the next submission
                 std::lock_guard<std::mutex> lk(mu);
                 sl.full = false;
                 sl.next = c + n_slots;
@@ -464,9 +560,25 @@ std::vector<camera_relations> link_pairs(const std::vector<LinkImage> &images, c
                 for (size_t k = 0; k < cn; k++)
                     jobs[k].matches = &coarse_correspondences[k], jobs[k].model = &models[k],
                     jobs[k].inliers = &coarse_inliers[k];
+                // device tail: bind the runs straight from the sorted match lists -- K6 computes both rays of every
+                // match (distort_keypoints, link_stage.cpp:87-88) into the bound rows and the rows come back for
+                // decompose(); 12 bytes per match go up instead of 56
+                const CorrBinder bind_from_matches = [&](const std::vector<ocb_corr_set> &sets) {
+                    std::vector<ocb_match_set> ms(sets.size());
+                    for (size_t k = 0; k < sets.size(); k++)
+                    {
+                        std::memset(&ms[k], 0, sizeof ms[k]);
+                        if (sets[k].n == 0)
+                            continue;
+                        ms[k].set_1 = id_base + pairs[begin + k].image_1, ms[k].set_2 = id_base + pairs[begin + k].image_2;
+                        ms[k].matches = sorted[k].data(), ms[k].n = sorted[k].size(), ms[k].order = sets[k].order;
+                        ms[k].corr_out = reinterpret_cast<double *>(coarse_correspondences[k].data());
+                    }
+                    detail::gpu_check(ocb_corr_bind_batch_matches(ms.data(), ms.size()), "ocb_corr_bind_batch_matches");
+                };
                 try
                 {
-                    ransac_batch(jobs, team);
+                    ransac_batch(jobs, team, device_tail ? &bind_from_matches : nullptr);
                 }
                 catch (const std::exception &e)
                 {
@@ -515,13 +627,14 @@ std::vector<camera_relations> link_pairs(const std::vector<LinkImage> &images, c
         // Everything the helper tasks touch is declared above; the guard is the innermost object, so whichever way
         // this scope is left it stops and joins the tasks before any of that state goes away.
         HelperGuard helpers{mu, cv, stop, {}};
+        HelperThreads &pool = HelperThreads::instance(device);
         helpers.tasks.reserve(2 + n_producers + (size_t)workers);
-        helpers.tasks.push_back(HelperThreads::instance().run(prepare));
+        helpers.tasks.push_back(pool.run(prepare));
         for (size_t k = 0; k < n_producers; k++)
-            helpers.tasks.push_back(HelperThreads::instance().run([&produce, k]() { produce(k); }));
+            helpers.tasks.push_back(pool.run([&produce, k]() { produce(k); }));
         const size_t first_consumer = helpers.tasks.size();
         for (int w = 1; w < workers; w++)
-            helpers.tasks.push_back(HelperThreads::instance().run(consume));
+            helpers.tasks.push_back(pool.run(consume));
         consume();
         for (size_t k = first_consumer; k < helpers.tasks.size(); k++)
             helpers.tasks[k].wait(); // every chunk is consumed (or an error stopped the run); the guard releases the rest
@@ -543,7 +656,7 @@ std::vector<camera_relations> link_pairs(const std::vector<LinkImage> &images, c
     if (std::getenv("OCB_LINK_TRACE"))
         std::fprintf(stderr,
                      "link_pairs: %zu pairs, %zu chunks, %d consumers x %d threads: upload %.3f s, match (GPU, summed) %.3f s, "
-                     "tail %.3f s = ratio/rays %.3f + ransac %.3f + finish %.3f, total %.3f s\n",
+                     "tail %.3f s = sort/rays %.3f + ransac %.3f + finish %.3f, total %.3f s\n",
                      n_pairs, n_chunks, workers, team, st.seconds_subsample_upload, gpu_seconds, tail_seconds,
                      phase_seconds[0], phase_seconds[1], phase_seconds[2], st.seconds_total);
     if (stats)

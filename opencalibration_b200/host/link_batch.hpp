@@ -4,9 +4,10 @@
 //              ransac<homography_model> -> decompose -> assembleInliers, all on that worker's core;
 //   here:      the packed descriptor rows of every image are uploaded ONCE (ocb_register_descriptors), in the order
 //              of first use and ahead of the matching; the pairs are matched in large submissions (ocb_match_pairs:
-//              one K1 launch per submission), and the per-pair tail (ratio test + sort, rays, RANSAC with device
-//              fits, refits and scoring, decomposition, inlier assembly) runs on OpenMP workers while the next
-//              submission is on the GPU.
+//              one K1 launch per submission, followed on the device by the ratio test and an order-preserving
+//              compaction, K5), and the per-pair tail (the reference's std::sort, rays on the device (K6), RANSAC
+//              with device fits, refits and scoring, decomposition, inlier assembly) runs on OpenMP workers while
+//              the next submission is on the GPU.
 // Results are returned in pair order (the order LinkStage::finalize restores, link_stage.cpp:119-131) and are
 // identical to running the reference-signature functions of opencalibration_api.hpp pair by pair.
 #pragma once
@@ -36,6 +37,12 @@ struct LinkOptions
     double coarse_spacing_pixels = 40.0; // link_stage.cpp:62
     bool run_ransac = true;             // false: stop after the match lists (relations.matches only)
     int tail_workers = 3;               // chunks whose tails (incl. the lock-step RANSAC rounds) run concurrently
+    size_t first_submission = 32;       // pairs of the first submission; later ones double up to pairs_per_submission
+    // true: ratio test + compaction (K5) and the pixel -> ray step (K6) run on the device, so that only the surviving
+    // matches cross PCIe and the host keeps the reference's std::sort, the RANSAC control flow, decompose and
+    // assembleInliers. false: the K1 records of every query come back and the host does the ratio test and the rays
+    // (the round-1 path, kept for A/B tests: both give identical relations).
+    bool device_tail = true;
 };
 struct LinkStats
 {

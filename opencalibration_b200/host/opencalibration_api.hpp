@@ -7,6 +7,9 @@
 #pragma once
 #include "reference_types.hpp"
 
+#include <ocb.h>
+
+#include <functional>
 #include <vector>
 
 namespace opencalibration
@@ -72,5 +75,11 @@ template <typename Model> struct RansacJob
     double result = 0; // what ransac() would have returned
     RansacStats stats;
 };
-template <typename Model> void ransac_batch(std::vector<RansacJob<Model>> &jobs, int threads = 0);
+// `binder` (optional) makes the jobs' correspondences resident instead of the default ocb_corr_bind_batch upload: it
+// receives one ocb_corr_set per job ({rows, n, evaluation order}; n == 0 for a job that is over before it starts) and
+// must leave them bound on the calling thread in that order (the batched LinkStage runner binds them straight from its
+// match lists with ocb_corr_bind_batch_matches, which also computes the rays on the device).
+using CorrBinder = std::function<void(const std::vector<ocb_corr_set> &)>;
+template <typename Model>
+void ransac_batch(std::vector<RansacJob<Model>> &jobs, int threads = 0, const CorrBinder *binder = nullptr);
 } // namespace ocb_host

@@ -577,7 +577,7 @@ namespace ocb_host
 // Many runs advanced in lock step: each round every unfinished run contributes one request, and ONE
 // ocb_score_requests call (one kernel launch, one copy each way) serves them all. The host-side logic of the runs
 // (sampling, fits, SPRT replay, local optimisation) executes on `threads` OpenMP workers between rounds.
-template <typename Model> void ransac_batch(std::vector<RansacJob<Model>> &jobs, int threads)
+template <typename Model> void ransac_batch(std::vector<RansacJob<Model>> &jobs, int threads, const CorrBinder *binder)
 {
     using namespace opencalibration;
     using Run = opencalibration::RansacRun<Model>;
@@ -605,7 +605,10 @@ template <typename Model> void ransac_batch(std::vector<RansacJob<Model>> &jobs,
         else
             jobs[j].result = 0;
     }
-    detail::gpu_check(ocb_corr_bind_batch(sets.data(), sets.size()), "ocb_corr_bind_batch");
+    if (binder)
+        (*binder)(sets);
+    else
+        detail::gpu_check(ocb_corr_bind_batch(sets.data(), sets.size()), "ocb_corr_bind_batch");
     std::vector<Need> need(n_jobs, Need::DONE);
     std::vector<ocb_score_request> requests;
     static const bool profile = std::getenv("OCB_RANSAC_PROFILE") != nullptr;
@@ -684,9 +687,9 @@ template <typename Model> void ransac_batch(std::vector<RansacJob<Model>> &jobs,
                      "evaluate %zu residuals %zu fit+score %zu refit+evaluate %zu\n",
                      n_jobs, threads, rounds, t_host * 1e3, t_gpu * 1e3, n_req[0], n_req[1], n_req[2], n_req[3], n_req[4]);
 }
-template void ransac_batch(std::vector<RansacJob<opencalibration::homography_model>> &, int);
-template void ransac_batch(std::vector<RansacJob<opencalibration::fundamental_matrix_model>> &, int);
-template void ransac_batch(std::vector<RansacJob<opencalibration::essential_matrix_model>> &, int);
+template void ransac_batch(std::vector<RansacJob<opencalibration::homography_model>> &, int, const CorrBinder *);
+template void ransac_batch(std::vector<RansacJob<opencalibration::fundamental_matrix_model>> &, int, const CorrBinder *);
+template void ransac_batch(std::vector<RansacJob<opencalibration::essential_matrix_model>> &, int, const CorrBinder *);
 } // namespace ocb_host
 
 namespace opencalibration

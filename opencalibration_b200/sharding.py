@@ -1,43 +1,33 @@
-"""Multi-GPU sharding of the pair list: one process per GPU, no data-path collective.
+"""Multi-GPU sharding of the pair list for the one-process-per-GPU harness.
 
-Directed image pairs are independent units (reference src/pipeline/link_stage.cpp:75-112). Images are ordered along a
-Hilbert curve over their positions and cut into `world` contiguous chunks (overlap-graph locality: most pairs have both
-images in one chunk); a pair belongs to the rank that owns its SOURCE image; every rank uploads its own images plus the
-"halo" images its pairs reference. The only cross-rank step is a host gather of the variable-length match lists back
-into the serial order the reference restores in LinkStage::finalize (link_stage.cpp:119-131).
+The partition itself is product code in C++ (opencalibration_b200/host/partition.cpp: Hilbert order of the image
+positions, same curve as the reference's include/opencalibration/types/hilbert.hpp:8-27, cut into `world` contiguous
+runs balanced by sourced pairs; a pair belongs to the part that owns its SOURCE image; halo images are resident too);
+this module only wraps it for bench.py / the tests, and implements the one cross-rank step of the path: the HOST GATHER
+of the variable-length match lists back into the serial pair order, which is what LinkStage::finalize does with its
+runners' results (reference src/pipeline/link_stage.cpp:119-131).
+
+Gather. All ranks of the job run on one box (north_star: "the 8 GPUs of one box"), so the gather goes through POSIX
+shared memory: rank 0 creates one segment, every rank packs its match lists (12-byte records: feature_index_1,
+feature_index_2, integer Hamming distance) straight into its own region of it, and a barrier later rank 0 holds every
+list without another copy; the serial order is restored as an index (pair -> offset, count), the way the reference
+moves vector handles rather than their contents. torch.distributed carries the region sizes (all_gather) and the
+barrier.
 """
 from dataclasses import dataclass, field
+from multiprocessing import shared_memory
 
 import numpy as np
 
 
 def hilbert_index(order, x, y):
-    """Position of integer cell (x, y) along a Hilbert curve over an order x order grid (order = power of two).
-    Same curve as the reference's xy2d helper (include/opencalibration/types/hilbert.hpp:8-27)."""
-    d = 0
-    s = order // 2
-    while s > 0:
-        rx = 1 if (x & s) else 0
-        ry = 1 if (y & s) else 0
-        d += s * s * ((3 * rx) ^ ry)
-        if ry == 0:
-            if rx == 1:
-                x, y = s - 1 - x, s - 1 - y
-            x, y = y, x
-        s //= 2
-    return d
+    from . import host
+    return host.hilbert_index(order, x, y)
 
 
-def hilbert_order(positions, order=1024):
-    """Permutation of image ids along the curve."""
-    pos = np.asarray(positions, np.float64).reshape(-1, 2)
-    if len(pos) == 0:
-        return np.zeros(0, np.int64)
-    lo, hi = pos.min(0), pos.max(0)
-    span = np.maximum(hi - lo, 1e-12)
-    cells = np.minimum(((pos - lo) / span * order).astype(np.int64), order - 1)
-    keys = np.array([hilbert_index(order, int(cx), int(cy)) for cx, cy in cells], np.int64)
-    return np.lexsort((np.arange(len(pos)), keys))
+def hilbert_order(positions):
+    from . import host
+    return host.hilbert_order(positions)
 
 
 @dataclass
@@ -54,24 +44,14 @@ class Shard:
 
 
 def partition(positions, pairs, world):
-    """-> list of Shard, one per rank. Chunks are balanced by the number of pairs each image sources."""
-    n_img = len(positions)
-    order = hilbert_order(positions)
-    load = np.zeros(n_img, np.int64)
-    for a, _ in pairs:
-        load[a] += 1
-    cum = np.cumsum(load[order])
-    total = int(cum[-1]) if n_img else 0
-    owner = np.zeros(n_img, np.int64)
-    for pos_in_curve, img in enumerate(order):
-        before = int(cum[pos_in_curve] - load[img])
-        owner[img] = min(world - 1, before * world // max(total, 1))
+    """-> list of Shard, one per rank (host/partition.cpp: partition_pairs)."""
+    from . import host
+    owner, part, halo = host.partition_pairs(positions, pairs, world)
     shards = []
     for r in range(world):
-        ids = np.array([i for i, (a, _) in enumerate(pairs) if owner[a] == r], np.int64)
-        owned = np.array(sorted(int(i) for i in np.nonzero(owner == r)[0]), np.int64)
-        halo = np.array(sorted({int(pairs[i][1]) for i in ids} - set(owned.tolist())), np.int64)
-        shards.append(Shard(r, owned, halo, ids, [pairs[i] for i in ids]))
+        ids = np.nonzero(part == r)[0].astype(np.int64)
+        shards.append(Shard(r, np.nonzero(owner == r)[0].astype(np.int64), np.nonzero(halo[r])[0].astype(np.int64), ids,
+                            [pairs[i] for i in ids]))
     return shards
 
 
@@ -86,34 +66,99 @@ def cut_statistics(shards, n_pairs):
     return {"cut_pair_fraction": cut / max(n_pairs, 1), "replication": resident / max(owned, 1)}
 
 
-def gather_results(local_pair_ids, local_results, n_pairs, dist=None, dst=0):
-    """Host gather of per-pair results (any picklable objects, e.g. match arrays) to rank `dst`, restored to the
-    global serial pair order. Without a process group (world 1) it just reorders."""
-    payload = (np.asarray(local_pair_ids, np.int64), list(local_results))
-    if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
-        gathered = [payload]
-        me = dst
-    else:
-        me = dist.get_rank()
-        gathered = [None] * dist.get_world_size() if me == dst else None
-        dist.gather_object(payload, gathered, dst=dst)
-    if me != dst:
-        return None
-    out = [None] * n_pairs
-    seen = 0
-    for ids, res in gathered:
-        for i, r in zip(ids.tolist(), res):
-            assert out[i] is None, f"pair {i} matched twice"
-            out[i] = r
-            seen += 1
-    assert seen == n_pairs, f"{n_pairs - seen} pairs were never matched"
-    return out
+RECORD_WORDS = 3  # uint32 words per match record: feature_index_1, feature_index_2, integer Hamming distance
 
 
-def run_sharded(positions, pairs, rank, world, upload, match_batch, dist=None):
-    """Drives one rank: upload(image_ids) makes the images resident; match_batch(pairs) -> list of per-pair results.
-    Returns the full serial-order result list on rank 0, None elsewhere."""
-    shard = partition(positions, pairs, world)[rank]
-    upload(shard.resident_images)
-    results = match_batch(shard.pairs) if len(shard.pairs) else []
-    return gather_results(shard.pair_ids, results, len(pairs), dist)
+class GatheredMatches:
+    """What rank 0 holds after the gather: every pair's match list, addressable in serial pair order."""
+
+    def __init__(self, records, offsets, counts):
+        self.records, self.offsets, self.counts = records, offsets, counts  # records [total][3] uint32
+
+    def __len__(self):
+        return len(self.counts)
+
+    def pair(self, p):
+        """-> (feature_index_1, feature_index_2, distance) of pair p; distance = d * (1.0 / 486) like the reference."""
+        r = self.records[int(self.offsets[p]):int(self.offsets[p]) + int(self.counts[p])]
+        return r[:, 0].astype(np.uintp), r[:, 1].astype(np.uintp), r[:, 2] * (1.0 / 486)
+
+    def total(self):
+        return int(self.counts.sum())
+
+
+class MatchGather:
+    """Host gather of per-pair match lists to rank 0 through one shared-memory segment (see the module docstring).
+
+    capacity_records = upper bound of the records any ONE rank contributes (e.g. its query rows); the segment holds
+    world * capacity_records records of 12 bytes, of which only the pages actually written are ever touched."""
+
+    def __init__(self, capacity_records, dist=None, name=None):
+        self.dist = dist if (dist is not None and dist.is_initialized() and dist.get_world_size() > 1) else None
+        self.rank = self.dist.get_rank() if self.dist else 0
+        self.world = self.dist.get_world_size() if self.dist else 1
+        self.capacity = int(capacity_records)
+        nbytes = max(1, self.world * self.capacity * RECORD_WORDS * 4)
+        if self.rank == 0:
+            self.shm = shared_memory.SharedMemory(create=True, size=nbytes, name=name)
+            names = [self.shm.name]
+        else:
+            names = [None]
+        if self.dist:
+            self.dist.broadcast_object_list(names, src=0)
+            if self.rank != 0:
+                self.shm = shared_memory.SharedMemory(name=names[0])
+                try:  # the creator unlinks it; an attaching process must not (Python < 3.13 registers it anyway)
+                    from multiprocessing import resource_tracker
+                    resource_tracker.unregister(self.shm._name, "shared_memory")
+                except Exception:  # noqa: BLE001
+                    pass
+        self.words = np.ndarray((self.world, self.capacity * RECORD_WORDS), np.uint32, buffer=self.shm.buf)
+
+    def region(self):
+        """This rank's region of the segment (flat uint32): pack the match records straight into it."""
+        return self.words[self.rank]
+
+    def gather(self, pair_ids, counts, n_pairs):
+        """Collective. pair_ids / counts: this rank's pairs (global ids, ascending) and their match counts, the records
+        already packed into region() pair after pair. Returns GatheredMatches on rank 0, None elsewhere."""
+        import torch
+        pair_ids = np.asarray(pair_ids, np.int64)
+        counts = np.asarray(counts, np.int64)
+        assert len(pair_ids) == len(counts) and int(counts.sum()) <= self.capacity
+        if self.dist:
+            # sizes first (so that every rank can post a matching receive), then ids and counts padded to the longest
+            dev = torch.device("cuda", torch.cuda.current_device()) if self.dist.get_backend() == "nccl" else "cpu"
+            sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(self.world)]
+            self.dist.all_gather(sizes, torch.tensor([len(pair_ids)], dtype=torch.int64, device=dev))
+            longest = max(int(s.item()) for s in sizes)
+            mine = torch.zeros(2, max(longest, 1), dtype=torch.int64)
+            mine[0, :len(pair_ids)] = torch.from_numpy(pair_ids)
+            mine[1, :len(counts)] = torch.from_numpy(counts)
+            mine = mine.to(dev)
+            every = [torch.zeros_like(mine) for _ in range(self.world)]
+            self.dist.all_gather(every, mine)  # also orders every rank's writes to the segment before rank 0's reads
+            self.dist.barrier()
+            if self.rank != 0:
+                return None
+            parts = [(e[0, :int(s.item())].cpu().numpy(), e[1, :int(s.item())].cpu().numpy()) for e, s in zip(every, sizes)]
+        else:
+            parts = [(pair_ids, counts)]
+        offsets = np.full(n_pairs, -1, np.int64)
+        all_counts = np.zeros(n_pairs, np.int64)
+        for r, (ids, cnt) in enumerate(parts):
+            assert np.all(offsets[ids] == -1), "a pair was matched twice"
+            start = np.concatenate([[0], np.cumsum(cnt)[:-1]]) if len(cnt) else np.zeros(0, np.int64)
+            offsets[ids] = r * self.capacity + start
+            all_counts[ids] = cnt
+        assert np.all(offsets >= 0), f"{int((offsets < 0).sum())} pairs were never matched"
+        return GatheredMatches(self.words.reshape(-1, RECORD_WORDS), offsets, all_counts)
+
+    def close(self):
+        self.words = None
+        try:
+            self.shm.close()
+            if self.rank == 0:
+                self.shm.unlink()
+        except Exception:  # noqa: BLE001
+            pass

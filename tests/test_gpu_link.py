@@ -133,3 +133,69 @@ def test_c4_survey_slice_equals_the_reference_object_code(gpu, hostlib):
         total += len(w[0])
     assert total > 225 * 500  # neighbouring images share most of their footprint
     res.close()
+
+
+def _relations_equal(a, b):
+    for k in ("H", "poses"):
+        if not np.array_equal(a[k], b[k], equal_nan=True):
+            return False
+    return (a["relation_type"] == b["relation_type"] and all(np.array_equal(x, y) for x, y in zip(a["matches"], b["matches"]))
+            and np.array_equal(a["inlier_idx"], b["inlier_idx"]) and np.array_equal(a["inlier_pixels"], b["inlier_pixels"]))
+
+
+@pytest.mark.parametrize("distorted", [False, True])
+def test_device_tail_equals_host_tail(gpu, hostlib, distorted):
+    """Ratio test + compaction (K5) and rays (K6) on the device give the relations of the host tail bit for bit -- also
+    with a distorted camera model, where every Levenberg-Marquardt iterate of the undistortion has to agree."""
+    survey = synthetic.PlanarSurvey(3, 4, 2500, seed=21)
+    imgs = [survey.image(i) for i in range(survey.n_images)]
+    imgs[5] = tuple(x[:3] for x in imgs[5])   # fewer matches than MINIMUM_POINTS: the run is over before it starts
+    imgs[7] = tuple(x[:0] for x in imgs[7])
+    cam = survey.camera8()
+    if distorted:
+        cam = hostlib.camera8(cam[0], cam[1:3], (0.02, -0.03, 0.01), (1e-3, -5e-4))
+    sets = [hostlib.FeatureSet(d, xy, s) for d, xy, s in imgs]
+    pairs = survey.pairs
+    kw = dict(threads=4, pairs_per_submission=16)
+    dev = hostlib.link_pairs(sets, [cam] * len(sets), pairs, device_tail=True, **kw)
+    ref = hostlib.link_pairs(sets, [cam] * len(sets), pairs, device_tail=False, **kw)
+    kept = 0
+    for p in range(len(pairs)):
+        a, b = dev.get(p), ref.get(p)
+        assert _relations_equal(a, b), (p, pairs[p])
+        kept += len(a["matches"][0]) > 0
+    assert kept >= 40
+    assert dev.stats["matches"] == ref.stats["matches"] and dev.stats["ransac_inliers"] == ref.stats["ransac_inliers"]
+    # matches only
+    dev2 = hostlib.link_pairs(sets, [cam] * len(sets), pairs, device_tail=True, run_ransac=False, **kw)
+    ref2 = hostlib.link_pairs(sets, [cam] * len(sets), pairs, device_tail=False, run_ransac=False, **kw)
+    for p in range(len(pairs)):
+        assert all(np.array_equal(x, y) for x, y in zip(dev2.get(p)["matches"], ref2.get(p)["matches"]))
+    # the flat form the ranks gather: counts and 12-byte records, pair after pair
+    counts, rec = dev2.pack_matches()
+    assert counts.sum() == len(rec) == dev2.stats["matches"]
+    o = 0
+    for p in range(len(pairs)):
+        i1, i2, d = dev2.get(p)["matches"]
+        r = rec[o:o + int(counts[p])]
+        assert np.array_equal(r[:, 0], i1) and np.array_equal(r[:, 1], i2) and np.array_equal(r[:, 2] * (1.0 / 486), d)
+        o += int(counts[p])
+
+
+def test_link_pairs_over_two_devices_equals_one(gpu, hostlib):
+    """In-process multi-GPU runner (host/partition.hpp: link_pairs_multi): the pair list partitioned over two GPUs of this
+    process gives the relations of the single-device run, in pair order."""
+    if gpu.lib().ocb_device_count() < 2:
+        pytest.skip("needs two GPUs (run with gpurun --gpus 2)")
+    survey = synthetic.PlanarSurvey(4, 6, 2000, seed=9)
+    imgs = [survey.image(i) for i in range(survey.n_images)]
+    sets = [hostlib.FeatureSet(d, xy, s) for d, xy, s in imgs]
+    cams = [survey.camera8()] * len(sets)
+    one = hostlib.link_pairs(sets, cams, survey.pairs, threads=8, pairs_per_submission=32)
+    two = hostlib.link_pairs(sets, cams, survey.pairs, threads=8, pairs_per_submission=32, n_devices=2,
+                             positions=survey.positions)
+    for p in range(len(survey.pairs)):
+        assert _relations_equal(one.get(p), two.get(p)), p
+    assert one.stats["matches"] == two.stats["matches"] and one.stats["comparisons"] == two.stats["comparisons"]
+    with pytest.raises(hostlib.OcbError):
+        hostlib.link_pairs(sets, cams, survey.pairs, n_devices=64, positions=survey.positions)
