@@ -82,37 +82,58 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(self.mhz)}
 
 
-# K1 instruction mix of the default variant WITH the fused cross-check, counted in the SASS of its
-# inner loop: per comparison 23 LOP3 + 3.4 VIMNMX + 2 integer adds + 0.2 compare on the ALU pipe (64 lanes/clk/SM),
-# 9 POPC on the XU pipe (16 lanes/clk/SM), 9.75 IMAD on the FMA pipe. (The plain sweep uses 27 LOP3 + 7 POPC.)
-K1_ALU_OPS, K1_XU_OPS = 28.6, 9.0
-# dram__bytes_read.sum + dram__bytes_write.sum of one K1 launch of this workload, from the committed
-# `ncu --set full` capture (profiles/r1s8_k1_ncu_full.csv); null would mean "not captured"
-K1_NCU_DRAM_BYTES = 1512192
-# pipe utilisation of the same capture (sm__inst_executed_pipe_{xu,alu}.avg.pct_of_peak_sustained_active)
-K1_NCU_PIPES = {"xu_pct_of_peak": 86.4, "alu_pct_of_peak": 69.2, "issue_slots_pct": 64.0,
-                "source": "profiles/r1s8_k1_ncu_full.csv"}
+def k1_profile(running_variant):
+    """The instruction mix, DRAM traffic and pipe utilisation of the headline kernel are NOT typed in here: they come
+    from profiles/k1_roofline.json, written by `tools/ncu_summary.py roofline` from an `ncu --set full` capture of this
+    same command plus the SASS of the built library, and carrying the kernel name, the variant and the hash of the
+    kernel source they belong to. A record that does not belong to the kernel that is running now is not used."""
+    import hashlib
+    path = os.path.join(ROOT, "profiles", "k1_roofline.json")
+    if not os.path.exists(path):
+        return None, "profiles/k1_roofline.json is missing"
+    rec = json.load(open(path))
+    if rec.get("k1_variant") != running_variant:
+        return None, f"profiles/k1_roofline.json describes k1_variant {rec.get('k1_variant')}, running {running_variant}"
+    for f, want in rec.get("source_sha256", {}).items():
+        got = hashlib.sha256(open(os.path.join(ROOT, "opencalibration_b200", "csrc", f), "rb").read()).hexdigest()
+        if got != want:
+            return None, f"profiles/k1_roofline.json was taken with another {f}"
+    if not rec.get("cross_check"):
+        return None, "profiles/k1_roofline.json describes the kernel without the fused cross-check"
+    return rec, None
 
 
-def roofline(achieved, sm_max, held, peak_src, ms_per_step, peaks):
+def roofline(achieved, sm_max, held, peak_src, ms_per_step, peaks, running_variant):
     """Bound = the integer pipes (north_star: XOR + POPC, not HBM, not tensor cores). `peak` is the PLAIN form's
     POPC-pipe roofline (16 XOR + 16 POPC per comparison) so that numbers stay comparable between
     variants; `mix_peak` is the tighter pipe bound of the instruction mix that actually runs."""
     popc_peak = 148 * 16 * sm_max * 1e6 / 16 / 1e9  # G comparisons/s: 16 POPC/clk/SM, 16 POPC per comparison
-    mix_clk = max(K1_ALU_OPS / 64.0, K1_XU_OPS / 16.0)  # SM clocks per comparison of the carry-save form
-    mix_peak = 148 * sm_max * 1e6 / mix_clk / 1e9
     algo_bytes = (N1 + N2) * 64 + N1 * 8 + N2 * 4
-    return {"bound": "int-pipe (popc/alu)", "achieved": achieved, "peak": popc_peak, "unit": UNIT,
-            "frac": achieved / popc_peak, "traffic": K1_NCU_DRAM_BYTES,
-            "peak_source": f"148 SMs x 16 POPC/clk/SM (probed on this pool: 16.0) x {sm_max:.0f} MHz "
-                           f"({peak_src} sm_max_mhz) / 16 POPC per comparison (plain XOR+POPC form)",
-            "frac_at_held_clock": achieved / (148 * 16 * held * 1e6 / 16 / 1e9),
-            "mix_peak": mix_peak, "mix_frac": achieved / mix_peak, "ncu_pipes": K1_NCU_PIPES,
-            "mix": {"alu_ops_per_cmp": K1_ALU_OPS, "xu_ops_per_cmp": K1_XU_OPS,
-                    "note": "prefix carry-save form trades POPCs for LOP3s, so it exceeds the plain-POPC roofline; "
-                            "mix_peak = 148 SMs x clock / max(alu/64, xu/16)"},
-            "hbm": {"achieved_gbs": algo_bytes / (ms_per_step * 1e-3) / 1e9, "peak_gbs": peaks.get("hbm_gbs"),
-                    "algorithmic_bytes_per_step": algo_bytes, "measured_dram_bytes_per_step": K1_NCU_DRAM_BYTES}}
+    prof, why_not = k1_profile(running_variant)
+    out = {"bound": "int-pipe (popc/alu)", "achieved": achieved, "peak": popc_peak, "unit": UNIT,
+           "frac": achieved / popc_peak, "traffic": prof["ncu"]["dram_bytes"] if prof else None,
+           "peak_source": f"148 SMs x 16 POPC/clk/SM (probed on this pool: 16.0) x {sm_max:.0f} MHz "
+                          f"({peak_src} sm_max_mhz) / 16 POPC per comparison (plain XOR+POPC form)",
+           "frac_at_held_clock": achieved / (148 * 16 * held * 1e6 / 16 / 1e9),
+           "hbm": {"achieved_gbs": algo_bytes / (ms_per_step * 1e-3) / 1e9, "peak_gbs": peaks.get("hbm_gbs"),
+                   "algorithmic_bytes_per_step": algo_bytes,
+                   "measured_dram_bytes_per_step": prof["ncu"]["dram_bytes"] if prof else None}}
+    if prof:
+        alu, xu = prof["sass"]["alu_ops_per_cmp"], prof["sass"]["xu_ops_per_cmp"]
+        mix_peak = 148 * sm_max * 1e6 / max(alu / 64.0, xu / 16.0) / 1e9  # SM clocks per comparison of the mix that runs
+        out.update({"mix_peak": mix_peak, "mix_frac": achieved / mix_peak,
+                    "mix": {"alu_ops_per_cmp": alu, "xu_ops_per_cmp": xu, "fma_ops_per_cmp": prof["sass"]["fma_ops_per_cmp"],
+                            "counted_in": f"SASS inner loop {prof['sass']['inner_loop']} of {prof['kernel']}",
+                            "note": "prefix carry-save form trades POPCs for LOP3s, so it exceeds the plain-POPC "
+                                    "roofline; mix_peak = 148 SMs x clock / max(alu/64, xu/16)"},
+                    "ncu_pipes": {k: prof["ncu"][k] for k in ("xu_pct_of_peak", "alu_pct_of_peak", "fma_pct_of_peak",
+                                                              "issue_slots_pct", "time_us")},
+                    "profile": {"file": "profiles/k1_roofline.json", "kernel": prof["kernel"],
+                                "k1_variant": prof["k1_variant"], "report": prof["report"],
+                                "git_rev": prof["git_rev_of_capture_summary"]}})
+    else:
+        out.update({"mix_peak": None, "mix_frac": None, "profile": None, "profile_unusable": why_not})
+    return out
 
 
 def _timed(torch, fn, reps):
@@ -209,9 +230,17 @@ def secondary_measurements(torch, capi, synthetic, stream):
 
 
 
-def cpu_reference_run(steps, warmup, threads=0, n2_sample=2500):
-    """The reference's CPU path: `threads` pairs per step (one pair per OpenMP worker, pipeline.cpp:42-49), each
-    N1 queries x n2_sample candidates of the same synthetic workload (bounded sample of the 10k x 10k pair)."""
+def c2_config(pairs_per_s, l2, k1_variant, parity_full, survivors, cross_check):
+    """The SAME keys in both arms (ours / --impl reference); values that only one arm has are null in the other."""
+    return {"workload": WORKLOAD, "n1": N1, "n2": N2, "comparisons_per_pair": N1 * N2, "cross_check": cross_check,
+            "pairs_per_s": pairs_per_s, "l2": l2, "k1_variant": k1_variant, "parity_full": parity_full,
+            "ratio_test_survivors": survivors}
+
+
+def cpu_reference_run(steps, warmup, threads=0):
+    """The reference's CPU path on the SAME configuration as the product arm: every step matches `threads` pairs (one
+    pair per OpenMP worker, src/pipeline/pipeline.cpp:42-49), each the full N1 x N2 rows of configs[1] (different
+    seeds per worker), through the reference's own match_features.cpp object code (oracle/_ref, -mpopcnt build)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oc_oracle as O
     from opencalibration_b200 import synthetic
@@ -223,22 +252,25 @@ def cpu_reference_run(steps, warmup, threads=0, n2_sample=2500):
     cores = ref.num_procs() if threads <= 0 else threads
     qs, cs = [], []
     for t in range(cores):
-        a, b = synthetic.config2_pair(N1, N2, seed=100 + t)
+        a, b = synthetic.config2_pair(N1, N2, seed=1 + t)  # worker 0 matches the product arm's rank-0 pair
         qs.append(a)
-        cs.append(b[:n2_sample])
+        cs.append(b)
     q, c = np.concatenate(qs), np.concatenate(cs)
-    cmp_per_step = cores * N1 * n2_sample
-    for _ in range(warmup):
+    cmp_per_step = cores * N1 * N2
+    for _ in range(max(1, warmup)):
         ref.bench_match_pairs(q[:cores * 500], c[:cores * 500], cores, 500, 500, cores)
-    secs = [ref.bench_match_pairs(q, c, cores, N1, n2_sample, cores)[0] for _ in range(steps)]
+    runs = [ref.bench_match_pairs(q, c, cores, N1, N2, cores) for _ in range(steps)]
+    secs = [r[0] for r in runs]
     value = cmp_per_step / (sum(secs) / len(secs)) / 1e9
     shipped = None
-    if ref_shipped is not None:
-        s = ref_shipped.bench_match_pairs(q[:cores * N1 // 4], c, cores, N1 // 4, n2_sample, cores)[0]
-        shipped = cores * (N1 // 4) * n2_sample / s / 1e9
+    if ref_shipped is not None:  # the flags the reference ships with (no -mpopcnt): a quarter of the queries is enough
+        s = ref_shipped.bench_match_pairs(q[:cores * N1 // 4], c, cores, N1 // 4, N2, cores)[0]
+        shipped = cores * (N1 // 4) * N2 / s / 1e9
     return dict(value=value, unit=UNIT, cores=cores, kind=kind,
-                sample=f"{cores} pairs/step (one per OpenMP thread) of {N1}x{n2_sample} rows of the workload, -mpopcnt build",
-                as_shipped_flags_value=shipped, ms_per_step=1e3 * sum(secs) / len(secs))
+                sample=f"{cores} pairs per step (one per OpenMP thread), each the full {N1}x{N2} rows of the workload, "
+                       f"{steps} steps, -mpopcnt build of the reference's own match_features.cpp",
+                as_shipped_flags_value=shipped, ms_per_step=1e3 * sum(secs) / len(secs),
+                pairs_per_s=cores / (sum(secs) / len(secs)), survivors_per_pair=runs[-1][1] / cores)
 
 
 def run_reference_survey(args):
@@ -290,11 +322,13 @@ def run_reference(args):
         return
     if args.workload != "c2":
         return run_reference_survey(args)
-    r = cpu_reference_run(args.steps, max(args.warmup, 1))
+    steps = max(1, min(args.steps, 40))  # a step is `cores` full pairs (~0.5 s): bounded so the arm ends in a minute
+    r = cpu_reference_run(steps, max(args.warmup, 1))
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+            "steps": steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "n1": N1, "n2": N2},
+            "config": c2_config(r["pairs_per_s"], "n/a (CPU arm)", None, None, int(r["survivors_per_pair"]),
+                                "not computed: src/match/match_features.cpp has no cross-check"),
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "as_shipped_flags_value")},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
@@ -396,21 +430,31 @@ def run_ours(args):
     secondary = None
     if rank == 0 and world == 1 and not args.no_secondary:
         secondary = secondary_measurements(torch, capi, synthetic, stream)
+    # ---- the sharded survey (BASELINE.json configs[3]) at THIS N: the overlap-graph partition north_star names, with the
+    # host gather of the match lists inside its timed region; every rank takes part
+    r_timed = dout.cpu().numpy().view(capi.TOP2_DTYPE).copy()
+    col_timed = dcol.cpu().numpy().copy()
+    del dq, dc, dout, dcol, ws, flush
+    torch.cuda.empty_cache()
+    survey_block = None
+    if not args.no_survey:
+        survey_block = measure_survey(torch, dist, rank, local_rank, world, "c4", steps=3, warmup=1, with_ransac=False,
+                                      verify=not args.no_verify)
 
     if rank != 0:
         if dist:
             dist.destroy_process_group()
         return
 
-    # ---- parity spot check of what was timed (sampled rows against the checker) + CPU baseline on this box
+    # ---- parity of what was timed: EVERY query and EVERY candidate column of the timed pair against the checker (all
+    # host cores, about a second) + CPU baseline on this box
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oc_oracle as O
     orc = O.Oracle()
-    r = dout.cpu().numpy().view(capi.TOP2_DTYPE)
-    pick = np.random.default_rng(0).permutation(N1)[:64]
-    bk, bd, sd = orc.match_top2(a[pick], b)
-    parity = bool(np.array_equal(r["best_k"][pick], bk) and np.array_equal(r["best_d"][pick], bd) and
-                  np.array_equal(r["second_d"][pick], sd))
+    bk, bd, sd = orc.match_top2(a, b)
+    parity = bool(np.array_equal(r_timed["best_k"], bk) and np.array_equal(r_timed["best_d"], bd) and
+                  np.array_equal(r_timed["second_d"], sd) and np.array_equal(col_timed, orc.match_col_best(a, b)))
+    assert parity, "the timed kernel's results differ from the oracle's"
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         cb = cpu_reference_run(steps=4, warmup=1)
@@ -423,11 +467,9 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD, "n1": N1, "n2": N2, "comparisons_per_step": cmp_per_step,
-                   "cross_check": "fused column-wise best query in the same sweep (no second pass)",
-                   "pairs_per_s": world / (ms_per_step * 1e-3), "l2": "flushed between timed steps (256 MiB write)",
-                   "k1_variant": capi.get_option("k1_variant"), "parity_spot_check": parity,
-                   "ratio_test_survivors": int(n_matches)},
+        "config": c2_config(world / (ms_per_step * 1e-3), "flushed between timed steps (256 MiB write)",
+                            capi.get_option("k1_variant"), parity, int(n_matches),
+                            "fused column-wise best query in the same sweep (no second pass)"),
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": (N1 + N2) * 64,
                 "d2h_bytes_per_step": N1 * 8 + N2 * 4, "ms_per_step": e2e_ms, "steps": conc_steps,
@@ -440,10 +482,13 @@ def run_ours(args):
                 "single_caller": {"value": world * cmp_per_step / (e2e_single_ms * 1e-3) / 1e9,
                                   "ms_per_step": e2e_single_ms, "steps": e2e_steps}},
         "gpu_launches": int(launches),
-        "roofline": roofline(achieved, sm_max, held, peak_src, ms_per_step, peaks),
+        "roofline": roofline(achieved, sm_max, held, peak_src, ms_per_step, peaks, capi.get_option("k1_variant")),
     }
     if cpu:
         line["cpu_baseline"] = cpu
+    if survey_block:
+        secondary = dict(secondary or {})
+        secondary["c4_survey"] = survey_block
     if secondary:
         line["secondary"] = secondary
     emit(line)
@@ -451,18 +496,182 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def run_survey(args):
-    """--workload c4 / c5 (BASELINE.json configs[3] / configs[4]): a synthetic aerial survey (PlanarSurvey: grid of
-    nadir cameras over a textured plane, 8192 features per image, directed pairs = 10 nearest cameras minus self)
-    through the batched LinkStage runner (host/link_batch.hpp = src/pipeline/link_stage.cpp:75-112 for a pair list):
-    subsample, descriptor upload, K1 matching in large submissions, ratio test + sort, rays, RANSAC (GPU scoring),
-    decomposition, inlier assembly. Pairs are sharded over the ranks by Hilbert-curve partition of the camera
-    positions (opencalibration_b200/sharding.py); no data-path collective; rank 0 gathers per-pair summaries.
-    One step = the whole survey once. value = pairs of all ranks / max-over-ranks wall time of the step (host code is
-    part of this path, so it is wall time, bracketed by device synchronisation + barrier)."""
-    import torch
+def measure_survey(torch, dist, rank, local_rank, world, workload, steps, warmup, with_ransac, spacing=0.5,
+                   pairs_per_submission=256, scale=1.0, verify=True, drop_in=False):
+    """BASELINE.json configs[3] / configs[4]: a synthetic aerial survey (PlanarSurvey: grid of nadir cameras over a
+    textured plane, 8192 features per image, directed pairs = 10 nearest cameras minus self) through the batched LinkStage
+    runner (host/link_batch.hpp = src/pipeline/link_stage.cpp:75-112 for a pair list): subsample, descriptor upload, K1
+    matching in large submissions, ratio test + compaction on the device (K5), the reference's std::sort [, rays on the
+    device (K6), RANSAC with GPU scoring, decomposition, inlier assembly]. Pairs are sharded over the ranks by the
+    Hilbert-curve partition of the camera positions (host/partition.cpp); no data-path collective. The ONE cross-rank
+    step is inside the timed region: the host gather of every pair's match list to rank 0, restored to the serial pair
+    order (link_stage.cpp:119-131), through shared memory (opencalibration_b200/sharding.py: MatchGather).
+    One step = the whole survey once, host vectors in, gathered lists on rank 0 out. value = pairs of all ranks /
+    max-over-ranks wall time of the step (host code is part of this path, so it is wall time, bracketed by device
+    synchronisation + barrier). Returns the block for the JSON line on rank 0, None elsewhere."""
     from concurrent.futures import ThreadPoolExecutor
     from opencalibration_b200 import capi, host, sharding, synthetic
+
+    rows, cols = (25, 40) if workload == "c4" else (50, 100)
+    if scale != 1.0:
+        rows, cols = max(2, int(rows * scale)), max(2, int(cols * scale))
+    survey = synthetic.PlanarSurvey(rows, cols, 8192, seed=7)
+    pairs = survey.pairs
+    if workload == "c5":
+        pairs = pairs[:40000]
+    shard = sharding.partition(survey.positions, pairs, world)[rank]
+    resident = shard.resident_images.tolist()
+    local_index = {g: i for i, g in enumerate(resident)}
+    cores = os.cpu_count() or 1
+    with ThreadPoolExecutor(max(1, min(8, cores // world))) as ex:
+        images = list(ex.map(survey.image, resident))
+    sets = [host.FeatureSet(d, xy, st) for d, xy, st in images]
+    cams = [survey.camera8()] * len(sets)
+    local_pairs = [(local_index[a], local_index[b]) for a, b in shard.pairs]
+    threads = max(1, cores // world - 1)  # one core per rank stays free for the submission threads
+    gather = sharding.MatchGather(capacity_records=max(1, len(local_pairs)) * 8192, dist=dist)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+
+    def step():
+        res = host.link_pairs(sets, cams, local_pairs, threads=threads, pairs_per_submission=pairs_per_submission,
+                              run_ransac=with_ransac, spacing=spacing)
+        counts, _ = res.pack_matches(out=gather.region(), threads=threads)  # this rank's lists, straight into the segment
+        return res, gather.gather(shard.pair_ids, counts, len(pairs))
+
+    # warm-up: whole untimed steps (they size the page-locked result buffers, the per-thread staging areas and the
+    # device memory pool the descriptor sets live in)
+    n_warm = max(1, min(warmup, 2))
+    for _ in range(n_warm):
+        step()[0].close()
+    steps = max(1, min(steps, 3))
+    launches0 = capi.kernel_launches()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    t0 = time.perf_counter()
+    res = gathered = None
+    for _ in range(steps):
+        if res is not None:
+            res.close()
+        res, gathered = step()
+    barrier()
+    secs = (time.perf_counter() - t0) / steps
+    stats = res.stats
+    clocks = sampler.result()
+    launches = capi.kernel_launches() - launches0
+    kept = sum(1 for p in range(res.n_pairs) if res.sizes(p)[0] > 0)
+    res.close()
+    t = torch.tensor([secs], dtype=torch.float64, device="cuda")
+    agg = torch.tensor([len(local_pairs), stats["comparisons"], stats["matches"], stats["ransac_inliers"], kept,
+                        len(resident)], dtype=torch.float64, device="cuda")
+    if dist:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(agg, op=dist.ReduceOp.SUM)
+    block = None
+    if rank == 0:
+        secs = float(t.item())
+        n_pairs, cmps, matches, inliers, kept_all, resident_all = [float(x) for x in agg.tolist()]
+        assert gathered is not None and len(gathered) == len(pairs) and gathered.total() == int(matches)
+        block = {
+            "workload": f"configs[{3 if workload == 'c4' else 4}]: {rows}x{cols} image survey, {int(n_pairs)} directed "
+                        f"pairs x 8192 features, batched LinkStage runner (match + ratio test + sort"
+                        f"{' + rays + RANSAC + decompose' if with_ransac else ''}), Hilbert partition over {world} "
+                        f"rank(s), match lists gathered to rank 0 inside the step",
+            "pairs_per_s": n_pairs / secs, "ms_per_step": secs * 1e3, "steps": steps, "warmup": n_warm,
+            "scaling": "strong", "images": survey.n_images, "pairs": int(n_pairs), "subsample_spacing_px": spacing,
+            "comparisons_per_step": cmps, "Gcmp_per_s": cmps / secs / 1e9, "matches": int(matches),
+            "ransac_inliers": int(inliers), "pairs_with_matches": int(kept_all),
+            "resident_images_all_ranks": int(resident_all), "host_threads_per_rank": threads, "host_cores": cores,
+            "rank0_breakdown_s": {k: v for k, v in stats.items() if k.startswith("seconds")},
+            "gather": {"what": "every pair's match list (12-byte records), all ranks -> rank 0, serial pair order",
+                       "transport": "POSIX shared memory on the box + torch.distributed all_gather of the index",
+                       "records": gathered.total(), "bytes": gathered.total() * 12},
+            "h2d_bytes_per_step": int(resident_all) * 8192 * (64 + (16 if with_ransac else 0)),
+            "d2h_bytes_per_step": int(matches) * 12, "gpu_launches": int(launches), "clocks": clocks,
+        }
+    # ---- after the clock: what was gathered against (a) rank 0 running the WHOLE survey alone in this same job and
+    # (b) the reference's own object code on a sample of pairs
+    if verify and world > 1:
+        if rank == 0:
+            missing = [g for g in range(survey.n_images) if g not in local_index]
+            with ThreadPoolExecutor(max(1, min(16, cores))) as ex:
+                extra = list(ex.map(survey.image, missing))
+            every = {g: sets[local_index[g]] for g in resident}
+            every.update({g: host.FeatureSet(d, xy, st) for g, (d, xy, st) in zip(missing, extra)})
+            all_sets = [every[g] for g in range(survey.n_images)]
+            all_cams = [survey.camera8()] * len(all_sets)
+            alone_threads = max(1, cores - 1)
+            host.link_pairs(all_sets, all_cams, pairs, threads=alone_threads, pairs_per_submission=pairs_per_submission,
+                            run_ransac=with_ransac, spacing=spacing).close()
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            alone = host.link_pairs(all_sets, all_cams, pairs, threads=alone_threads,
+                                    pairs_per_submission=pairs_per_submission, run_ransac=with_ransac, spacing=spacing)
+            alone_secs = time.perf_counter() - t1
+            counts1, rec1 = alone.pack_matches(threads=alone_threads)
+            alone.close()
+            same = bool(np.array_equal(counts1.astype(np.int64), gathered.counts))
+            o = 0
+            for p in range(len(pairs)):
+                if not same:
+                    break
+                n = int(counts1[p])
+                same = np.array_equal(rec1[o:o + n], gathered.records[int(gathered.offsets[p]):int(gathered.offsets[p]) + n])
+                o += n
+            assert same, "the gathered match lists differ from the single-GPU result"
+            block["gathered_equals_single_gpu_result"] = True
+            block["single_gpu_in_this_job"] = {"pairs_per_s": len(pairs) / alone_secs, "host_threads": alone_threads,
+                                               "note": "rank 0 alone on the whole survey while the other ranks wait"}
+            block["strong_scaling_efficiency_vs_single_gpu_in_this_job"] = \
+                block["pairs_per_s"] / (world * len(pairs) / alone_secs)
+        if dist:
+            dist.barrier()
+    if rank == 0 and verify:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import oc_oracle as O
+        try:
+            ref, kind = O.Reference(popcnt=True), "reference object code"
+        except (FileNotFoundError, OSError):
+            ref, kind = O.Oracle(), "oracle port"
+        if not with_ransac:  # with RANSAC only the pairs that keep a relation keep their matches (link_stage.cpp:103-107)
+            sample = [p for p in shard.pair_ids.tolist()][:: max(1, len(shard.pair_ids) // 16)][:16]
+
+            def want(p):
+                a, b = pairs[p]
+                (da, xa, sa), (db, xb, sb) = images[local_index[a]], images[local_index[b]]
+                return ref.match_features_subset(da, db, ref.subsample(xa, sa, spacing), ref.subsample(xb, sb, spacing))
+
+            with ThreadPoolExecutor(max(1, min(16, cores))) as ex:
+                wanted = list(ex.map(want, sample))
+            ok = all(all(np.array_equal(x, y) for x, y in zip(gathered.pair(p), w)) for p, w in zip(sample, wanted))
+            assert ok, "a gathered match list differs from the reference's"
+            block["parity_sample"] = {"pairs": len(sample), "against": kind, "equal": True}
+    if rank == 0 and drop_in and local_pairs:
+        # the same pairs through the DROP-IN entry point, the way the unmodified reference calls it: one
+        # match_features_subset(std::vector<feature_2d>...) closure per pair on OpenMP workers (pipeline.cpp:42-49),
+        # every call packing, uploading and matching its own two images (rank 0, a bounded sample of its pairs)
+        sample = local_pairs[:min(len(local_pairs), 768)]
+        sq, sc = [sets[a] for a, _ in sample], [sets[b] for _, b in sample]
+        host.run_parallel_handles(sq[:64], sc[:64], threads=threads)  # sizes the workers' staging areas
+        d_secs, d_matches = host.run_parallel_handles(sq, sc, threads=threads)
+        block["drop_in_per_pair_calls"] = {
+            "pairs_per_s": len(sample) / d_secs, "pairs": len(sample), "host_threads": threads, "matches": d_matches,
+            "api": "match_features_subset(std::vector<feature_2d>...) per pair, all features of both images, one "
+                   "closure per OpenMP worker like run_parallel (src/pipeline/pipeline.cpp:42-49)"}
+    gather.close()
+    for fs in sets:
+        fs.close()
+    return block
+
+
+def run_survey(args):
+    """--workload c4 / c5: the survey of measure_survey as the bench line of its own."""
+    import torch
+    from opencalibration_b200 import capi
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -475,100 +684,19 @@ def run_survey(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     capi.init(local_rank)
-    rows, cols = (25, 40) if args.workload == "c4" else (50, 100)
-    if args.survey_scale != 1.0:
-        rows, cols = max(2, int(rows * args.survey_scale)), max(2, int(cols * args.survey_scale))
-    survey = synthetic.PlanarSurvey(rows, cols, 8192, seed=7)
-    pairs = survey.pairs
-    if args.workload == "c5":
-        pairs = pairs[:40000]
-    shard = sharding.partition(survey.positions, pairs, world)[rank]
-    resident = shard.resident_images.tolist()
-    local_index = {g: i for i, g in enumerate(resident)}
-    with ThreadPoolExecutor(8) as ex:
-        images = list(ex.map(survey.image, resident))
-    sets = [host.FeatureSet(d, xy, st) for d, xy, st in images]
-    cams = [survey.camera8()] * len(sets)
-    local_pairs = [(local_index[a], local_index[b]) for a, b in shard.pairs]
-    threads = max(1, (os.cpu_count() or 1) // world - 1)  # one core per rank stays free for the submission thread
-    spacing = args.spacing
-
-    def barrier():
-        torch.cuda.synchronize()
-        if dist:
-            dist.barrier()
-
-    def step():
-        return host.link_pairs(sets, cams, local_pairs, threads=threads, pairs_per_submission=args.pairs_per_submission,
-                               run_ransac=args.with_ransac, spacing=spacing)
-
-    # warm-up: whole untimed steps (they size the page-locked result buffers, the per-thread staging areas and the
-    # device memory pool the descriptor sets live in)
-    for _ in range(max(1, min(args.warmup, 2))):
-        step().close()
-    steps = max(1, args.steps if args.steps < 50 else 1)
-    launches0 = capi.kernel_launches()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    barrier()
-    t0 = time.perf_counter()
-    stats = None
-    res = None
-    for _ in range(steps):
-        if res is not None:
-            res.close()
-        res = step()
-        stats = res.stats
-    barrier()
-    secs = (time.perf_counter() - t0) / steps
-    # a statistic for the JSON line, counted after the clock stopped (9000 Python-level accessor calls)
-    kept = sum(1 for p in range(res.n_pairs) if res.sizes(p)[0] > 0)
-    res.close()
-    clocks = sampler.result()
-    launches = capi.kernel_launches() - launches0
-    t = torch.tensor([secs], dtype=torch.float64, device="cuda")
-    agg = torch.tensor([len(local_pairs), stats["comparisons"], stats["matches"], stats["ransac_inliers"], kept,
-                        len(resident)], dtype=torch.float64, device="cuda")
-    if dist:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(agg, op=dist.ReduceOp.SUM)
-    summaries = sharding.gather_results(shard.pair_ids, [0] * len(shard.pair_ids), len(pairs), dist)
-    # the same pairs through the DROP-IN entry point, the way the unmodified reference calls it: one
-    # match_features_subset(std::vector<feature_2d>...) closure per pair on OpenMP workers (pipeline.cpp:42-49), every
-    # call packing, uploading and matching its own two images (rank 0, a bounded sample of its pairs)
-    drop_in = None
-    if rank == 0 and not args.no_secondary and local_pairs:
-        sample = local_pairs[:min(len(local_pairs), 768)]
-        sq, sc = [sets[a] for a, _ in sample], [sets[b] for _, b in sample]
-        host.run_parallel_handles(sq[:64], sc[:64], threads=threads)  # sizes the workers' staging areas
-        d_secs, d_matches = host.run_parallel_handles(sq, sc, threads=threads)
-        drop_in = {"pairs_per_s": len(sample) / d_secs, "pairs": len(sample), "host_threads": threads,
-                   "matches": d_matches,
-                   "api": "match_features_subset(std::vector<feature_2d>...) per pair, all features of both images, "
-                          "one closure per OpenMP worker like run_parallel (src/pipeline/pipeline.cpp:42-49)"}
+    b = measure_survey(torch, dist, rank, local_rank, world, args.workload, args.steps if args.steps < 50 else 1,
+                       args.warmup, args.with_ransac, args.spacing, args.pairs_per_submission, args.survey_scale,
+                       verify=not args.no_verify, drop_in=not args.no_secondary)
     if rank == 0:
-        assert summaries is not None and len(summaries) == len(pairs)
-        secs = float(t.item())
-        n_pairs, cmps, matches, inliers, kept_all, resident_all = [float(x) for x in agg.tolist()]
-        line = {
-            "metric": "image_pairs_matched_per_s", "value": n_pairs / secs, "unit": "pairs/s", "n_gpus": world,
-            "steps": steps, "warmup": max(1, min(args.warmup, 2)), "ms_per_step": secs * 1e3, "higher_is_better": True,
-            "scaling": "strong",
-            "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-            "config": {"workload": f"configs[{3 if args.workload == 'c4' else 4}]: {rows}x{cols} image survey, "
-                                   f"{int(n_pairs)} directed pairs x 8192 features, batched LinkStage runner "
-                                   f"(match + ratio test + sort{' + rays + RANSAC + decompose' if args.with_ransac else ''})",
-                       "images": survey.n_images, "pairs": int(n_pairs), "subsample_spacing_px": spacing,
-                       "comparisons_per_step": cmps, "Gcmp_per_s": cmps / secs / 1e9, "matches": int(matches),
-                       "ransac_inliers": int(inliers), "pairs_with_relation": int(kept_all),
-                       "resident_images_all_ranks": int(resident_all), "host_threads_per_rank": threads,
-                       "rank0_breakdown_s": {k: v for k, v in stats.items() if k.startswith("seconds")},
-                       "drop_in_per_pair_calls": drop_in},
-            "clocks": clocks, "gpu_launches": int(launches),
-            "e2e": {"value": n_pairs / secs, "unit": "pairs/s",
-                    "h2d_bytes_per_step": int(resident_all) * 8192 * 64, "d2h_bytes_per_step": int(n_pairs) * 8192 * 8,
-                    "note": "the step is end to end by construction: features start in host vectors, relations end there"},
-        }
+        line = {"metric": "image_pairs_matched_per_s", "value": b["pairs_per_s"], "unit": "pairs/s", "n_gpus": world,
+                "steps": b["steps"], "warmup": b["warmup"], "ms_per_step": b["ms_per_step"], "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+                "config": {k: v for k, v in b.items() if k not in ("clocks", "gpu_launches")},
+                "clocks": b["clocks"], "gpu_launches": b["gpu_launches"],
+                "e2e": {"value": b["pairs_per_s"], "unit": "pairs/s", "h2d_bytes_per_step": b["h2d_bytes_per_step"],
+                        "d2h_bytes_per_step": b["d2h_bytes_per_step"],
+                        "note": "the step is end to end by construction: features start in host vectors, the gathered "
+                                "match lists end in rank 0's host memory"}}
         emit(line)
     if dist:
         dist.destroy_process_group()
@@ -614,6 +742,8 @@ def main():
                          "(default: the metric's unit, pairs MATCHED: match lists after ratio test and sort)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true")
+    ap.add_argument("--no-survey", action="store_true", help="c2: skip the sharded configs[3] survey block")
+    ap.add_argument("--no-verify", action="store_true", help="skip the after-the-clock checks of the survey block")
     ap.add_argument("--callers", type=int, default=4, help="concurrent host callers of the e2e measurement")
     args = ap.parse_args()
     if args.impl == "reference":

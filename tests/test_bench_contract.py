@@ -79,4 +79,23 @@ def test_product_arm_line_has_every_contract_key():
     cb = d["cpu_baseline"]
     assert cb["kind"] == "reference" and cb["cores"] >= 1 and 0 < cb["value"] < d["value"]
     assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
-    assert d["config"]["parity_spot_check"] is True
+    assert d["config"]["parity_full"] is True  # every query and every column of the timed pair against the oracle
+    assert rf["profile"] and rf["profile"]["k1_variant"] == d["config"]["k1_variant"] and rf["mix_frac"] > 0.5
+    assert d["e2e"]["single_caller"]["value"] > 20
+    # the sharded survey (configs[3]) is part of the driver-run line at every N, gather inside its timed region
+    c4 = d["secondary"]["c4_survey"]
+    assert c4["pairs"] == 9000 and c4["pairs_per_s"] > 2000 and c4["gather"]["records"] == c4["matches"] > 9000 * 500
+    assert c4["parity_sample"]["equal"] is True and c4["parity_sample"]["pairs"] >= 8
+
+
+def test_reference_arm_uses_the_product_arms_configuration():
+    """Same workload, same config keys in both arms (the driver compares them): the full 10000 x 10000 pair per worker."""
+    r = run([sys.executable, "bench.py", "--impl", "reference", "--steps", "1", "--warmup", "1"])
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads([l for l in r.stdout.splitlines() if l.strip()][0])
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    assert src.count("c2_config(") == 3  # one definition, one call per arm: the keys cannot drift apart
+    assert {"workload", "n1", "n2", "comparisons_per_pair", "cross_check", "pairs_per_s", "l2", "k1_variant",
+            "parity_full", "ratio_test_survivors"} == set(d["config"])
+    assert d["config"]["n1"] == d["config"]["n2"] == 10000 and d["config"]["comparisons_per_pair"] == 10 ** 8
+    assert "full 10000x10000" in d["cpu_baseline"]["sample"] and d["config"]["ratio_test_survivors"] == 5000

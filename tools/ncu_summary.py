@@ -2,6 +2,10 @@
 
   python tools/ncu_summary.py full <rep.ncu-rep> <out.csv>       selected metrics of every captured launch
   python tools/ncu_summary.py launches <launches.csv> <out.csv>  per-kernel totals + share of the launch list
+  python tools/ncu_summary.py roofline <rep.ncu-rep> <out.json> [k1_variant] [comparisons per launch]
+        the self-describing roofline record bench.py reads (profiles/k1_roofline.json): kernel name of the capture,
+        variant index, hash of the kernel source and git revision it belongs to, DRAM bytes, pipe utilisation, and the
+        per-comparison instruction mix counted in the SASS of that kernel's inner loop (tools/sass_loops.py)
 """
 import csv
 import io
@@ -63,5 +67,77 @@ def launches(src, out):
     print(f"{out}: {len(rows)} launches, {total / 1e3:.2f} ms listed")
 
 
+def roofline(rep, out, variant="0", comparisons="100000000"):
+    import hashlib
+    import json
+    import os
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import sass_loops
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], check=True, capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    header, launches_ = rows[0], rows[2:]
+    col = {h: c for c, h in enumerate(header)}
+    k1 = [r for r in launches_ if "k1_top2_kernel" in r[col["Kernel Name"]]]
+    if not k1:
+        raise SystemExit("no k1_top2_kernel launch in " + rep)
+
+    def avg(metric, scale=1.0):
+        return sum(float(r[col[metric]].replace(",", "")) for r in k1) / len(k1) * scale
+
+    unit = rows[1][col["dram__bytes_read.sum"]]
+    to_bytes = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[unit]
+    wunit = rows[1][col["dram__bytes_write.sum"]]
+    kernel = k1[0][col["Kernel Name"]]
+    args = re.search(r"<([^>]*)>", kernel).group(1).replace(" ", "").split(",")  # Q, F, IMADACC, COL, MINB, PFX, BF
+    mangled = "k1_top2_kernelILi%sELi%sELb%sELb%sELi%sELb%sELb%sE" % tuple(args)
+    lib = os.path.join(root, "opencalibration_b200", "libocb.so")
+    name, dem, body = sass_loops.kernel_sass(lib, mangled)
+    ins = sass_loops.parse(body)
+    loops = []
+    for addr, op, text in ins:
+        if op.startswith("BRA"):
+            m = re.search(r"(0x[0-9a-f]+)\s*$", text)
+            if m and int(m.group(1), 16) <= addr:
+                loops.append((int(m.group(1), 16), addr))
+
+    def popc_density(l):
+        inside = [i for i in ins if l[0] <= i[0] <= l[1]]
+        k = sum(1 for i in inside if i[1].startswith("POPC"))
+        return k / len(inside) if k >= 8 else 0.0
+    lo, hi = max(loops, key=popc_density)
+    inside = [i for i in ins if lo <= i[0] <= hi]
+    q = int(args[0])
+    per_trip = (4 if q <= 2 else 2) * q  # hamming_top2.cu: #pragma unroll(Q <= 2 ? 4 : 2) over candidates, Q queries per thread
+    pipes = {}
+    for _, op, _t in inside:
+        pipes[sass_loops.pipe_of(op.split(".")[0])] = pipes.get(sass_loops.pipe_of(op.split(".")[0]), 0) + 1
+    sha = lambda f: hashlib.sha256(open(os.path.join(root, "opencalibration_b200", "csrc", f), "rb").read()).hexdigest()
+    git = subprocess.run(["git", "-C", root, "rev-parse", "HEAD"], capture_output=True, text=True).stdout.strip()
+    rec = {
+        "kernel": kernel.split("(")[0], "k1_variant": int(variant), "cross_check": args[3] in ("1", "true"),
+        "source_sha256": {f: sha(f) for f in ("hamming_top2.cu", "ocb_internal.cuh")}, "git_rev_of_capture_summary": git,
+        "comparisons_per_launch": int(comparisons), "launches_averaged": len(k1), "report": os.path.basename(rep),
+        "ncu": {"time_us": avg("gpu__time_duration.sum"),
+                "dram_bytes": avg("dram__bytes_read.sum", to_bytes) + avg("dram__bytes_write.sum",
+                                                                          {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[wunit]),
+                "xu_pct_of_peak": avg("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active"),
+                "alu_pct_of_peak": avg("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"),
+                "fma_pct_of_peak": avg("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"),
+                "issue_slots_pct": avg("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                "sm_cycles_active": avg("sm__cycles_active.avg"), "sm_ghz": avg("sm__cycles_elapsed.avg.per_second"),
+                "warp_instructions": avg("smsp__inst_executed.sum"),
+                "registers_per_thread": avg("launch__registers_per_thread")},
+        "sass": {"inner_loop": f"0x{lo:04x}..0x{hi:04x}", "instructions": len(inside), "comparisons_per_trip": per_trip,
+                 "alu_ops_per_cmp": pipes.get("alu", 0) / per_trip, "xu_ops_per_cmp": pipes.get("xu", 0) / per_trip,
+                 "fma_ops_per_cmp": pipes.get("fma", 0) / per_trip, "lsu_ops_per_cmp": pipes.get("lsu", 0) / per_trip},
+    }
+    # cross-check of the two sources: XU lane-operations per comparison as the counters saw them
+    n = rec["ncu"]
+    rec["ncu"]["xu_ops_per_cmp_from_counters"] = n["xu_pct_of_peak"] / 100 * 16 * 148 * n["sm_cycles_active"] / int(comparisons)
+    json.dump(rec, open(out, "w"), indent=1)
+    print(json.dumps(rec, indent=1))
+
+
 if __name__ == "__main__":
-    {"full": full, "launches": launches}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"full": full, "launches": launches, "roofline": roofline}[sys.argv[1]](*sys.argv[2:])
