@@ -536,11 +536,18 @@ def measure_survey(torch, dist, rank, local_rank, world, workload, steps, warmup
         if dist:
             dist.barrier()
 
+    phase = np.zeros(3)  # this rank's wall time in link_pairs / pack / gather, summed over the timed steps
+
     def step():
+        t_a = time.perf_counter()
         res = host.link_pairs(sets, cams, local_pairs, threads=threads, pairs_per_submission=pairs_per_submission,
                               run_ransac=with_ransac, spacing=spacing)
+        t_b = time.perf_counter()
         counts, _ = res.pack_matches(out=gather.region(), threads=threads)  # this rank's lists, straight into the segment
-        return res, gather.gather(shard.pair_ids, counts, len(pairs))
+        t_c = time.perf_counter()
+        out = gather.gather(shard.pair_ids, counts, len(pairs))
+        phase[:] += (t_b - t_a, t_c - t_b, time.perf_counter() - t_c)
+        return res, out
 
     # warm-up: whole untimed steps (they size the page-locked result buffers, the per-thread staging areas and the
     # device memory pool the descriptor sets live in)
@@ -551,6 +558,7 @@ def measure_survey(torch, dist, rank, local_rank, world, workload, steps, warmup
     launches0 = capi.kernel_launches()
     sampler = ClockSampler(local_rank)
     sampler.start()
+    phase[:] = 0
     barrier()
     t0 = time.perf_counter()
     res = gathered = None
@@ -568,9 +576,12 @@ def measure_survey(torch, dist, rank, local_rank, world, workload, steps, warmup
     t = torch.tensor([secs], dtype=torch.float64, device="cuda")
     agg = torch.tensor([len(local_pairs), stats["comparisons"], stats["matches"], stats["ransac_inliers"], kept,
                         len(resident)], dtype=torch.float64, device="cuda")
+    per_rank = torch.zeros(world, 5, dtype=torch.float64, device="cuda")
+    per_rank[rank] = torch.tensor([len(local_pairs), len(resident), *(phase / steps)], dtype=torch.float64)
     if dist:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(agg, op=dist.ReduceOp.SUM)
+        dist.all_reduce(per_rank, op=dist.ReduceOp.SUM)
     block = None
     if rank == 0:
         secs = float(t.item())
@@ -587,6 +598,8 @@ def measure_survey(torch, dist, rank, local_rank, world, workload, steps, warmup
             "ransac_inliers": int(inliers), "pairs_with_matches": int(kept_all),
             "resident_images_all_ranks": int(resident_all), "host_threads_per_rank": threads, "host_cores": cores,
             "rank0_breakdown_s": {k: v for k, v in stats.items() if k.startswith("seconds")},
+            "per_rank": [{"pairs": int(r[0]), "resident_images": int(r[1]), "link_pairs_s": r[2], "pack_s": r[3],
+                          "gather_s": r[4]} for r in per_rank.cpu().tolist()],
             "gather": {"what": "every pair's match list (12-byte records), all ranks -> rank 0, serial pair order",
                        "transport": "POSIX shared memory on the box + torch.distributed all_gather of the index",
                        "records": gathered.total(), "bytes": gathered.total() * 12},
