@@ -23,6 +23,11 @@ import sys
 import threading
 import time
 
+# The host side of the survey path runs OpenMP teams next to threads that wait for the GPU, with as few as four cores
+# per rank on an 8-GPU box: idle OpenMP workers must sleep, not spin, or they take the cores the working threads need.
+# (libgomp reads this when it is loaded, i.e. before the first import below that pulls it in.)
+os.environ.setdefault("OMP_WAIT_POLICY", "passive")
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))

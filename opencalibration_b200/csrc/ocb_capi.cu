@@ -73,6 +73,8 @@ struct ThreadCtx
     int device = -1; // -1: follow the process default
     bool ready = false;
     cudaStream_t stream = nullptr; // latency-sensitive per-call work: highest priority
+    cudaEvent_t bulk_done = nullptr; // blocking-sync event: a thread waiting for a large submission sleeps instead of
+                                     // spinning (the per-pair tail of the previous submission needs the core)
     cudaStream_t bulk = nullptr;   // large batched submissions (ocb_match_pairs): lowest priority, so that the small
                                    // kernels of other host threads (RANSAC scoring of the previous submission) are
                                    // dispatched ahead of the thousands of queued matching CTAs
@@ -118,8 +120,16 @@ struct ThreadCtx
         OCB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_low, &prio_high));
         OCB_CUDA(cudaStreamCreateWithPriority(&stream, cudaStreamNonBlocking, prio_high));
         OCB_CUDA(cudaStreamCreateWithPriority(&bulk, cudaStreamNonBlocking, prio_low));
+        OCB_CUDA(cudaEventCreateWithFlags(&bulk_done, cudaEventBlockingSync | cudaEventDisableTiming));
         ready = true;
         ready_device = device;
+        return 0;
+    }
+    // waits for everything enqueued on the bulk stream without spinning
+    int wait_bulk()
+    {
+        OCB_CUDA(cudaEventRecord(bulk_done, bulk));
+        OCB_CUDA(cudaEventSynchronize(bulk_done));
         return 0;
     }
     int dev_reserve(size_t bytes)
@@ -176,6 +186,8 @@ struct ThreadCtx
                 cudaStreamSynchronize(bulk);
                 cudaStreamDestroy(bulk);
             }
+            if (bulk_done)
+                cudaEventDestroy(bulk_done);
         }
         dev = Buf();
         pinned = Buf();
@@ -186,6 +198,7 @@ struct ThreadCtx
         batch_sets.clear();
         stream = nullptr;
         bulk = nullptr;
+        bulk_done = nullptr;
         ready = false;
         ready_device = -1;
     }
@@ -921,7 +934,8 @@ extern "C"
         if (out_end)
             OCB_CUDA(cudaMemcpyAsync(out_pinned ? (void *)out : (void *)(hp + s_out), d + o_out,
                                      out_end * sizeof(ocb_top2), cudaMemcpyDeviceToHost, bulk));
-        OCB_CUDA(cudaStreamSynchronize(bulk));
+        if ((rc = cx.wait_bulk()))
+            return rc;
         if (out_end && !out_pinned)
             memcpy(out, hp + s_out, out_end * sizeof(ocb_top2));
         return 0;
@@ -1019,7 +1033,8 @@ extern "C"
         // the offsets first (they say how many survivors there are), then exactly that many records
         OCB_CUDA(cudaMemcpyAsync(off_pinned ? (void *)out_offsets : (void *)(hp + s_off), d + o_off,
                                  (n_pairs + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, bulk));
-        OCB_CUDA(cudaStreamSynchronize(bulk));
+        if ((rc = cx.wait_bulk()))
+            return rc;
         if (!off_pinned)
             memcpy(out_offsets, hp + s_off, (n_pairs + 1) * sizeof(uint64_t));
         const uint64_t total = out_offsets[n_pairs];
@@ -1029,7 +1044,8 @@ extern "C"
         {
             OCB_CUDA(cudaMemcpyAsync(out_pinned ? (void *)out : (void *)(hp + s_out), d + o_out,
                                      total * sizeof(ocb_match), cudaMemcpyDeviceToHost, bulk));
-            OCB_CUDA(cudaStreamSynchronize(bulk));
+            if ((rc = cx.wait_bulk()))
+            return rc;
             if (!out_pinned)
                 memcpy(out, hp + s_out, total * sizeof(ocb_match));
         }

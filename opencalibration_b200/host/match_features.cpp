@@ -106,27 +106,53 @@ std::vector<size_t> spatially_subsample_feature_indices(const std::vector<featur
         count = features.size();
     if (count == 0)
         return {};
+    // :17-23: indices 0 .. count-1 sorted by strength, descending, with std::sort. The sort runs on compact (strength,
+    // index) records instead of indices compared through the 96-byte feature structs: std::sort's sequence of
+    // comparisons and moves depends only on the comparator's answers, which are the same, so the permutation is the
+    // reference's (ties included) -- and the records stay in cache.
+    struct Ranked
+    {
+        float strength;
+        uint32_t idx;
+    };
+    const bool compact = count <= 0xFFFFFFFFull;
     std::vector<size_t> by_strength(count);
-    for (size_t i = 0; i < count; i++)
-        by_strength[i] = i;
-    std::sort(by_strength.begin(), by_strength.end(),
-              [&features](size_t a, size_t b) { return features[a].strength > features[b].strength; });
+    if (compact)
+    {
+        std::vector<Ranked> ranked(count);
+        for (size_t i = 0; i < count; i++)
+            ranked[i] = Ranked{features[i].strength, (uint32_t)i};
+        std::sort(ranked.begin(), ranked.end(), [](const Ranked &a, const Ranked &b) { return a.strength > b.strength; });
+        for (size_t i = 0; i < count; i++)
+            by_strength[i] = ranked[i].idx;
+    }
+    else
+    {
+        for (size_t i = 0; i < count; i++)
+            by_strength[i] = i;
+        std::sort(by_strength.begin(), by_strength.end(),
+                  [&features](size_t a, size_t b) { return features[a].strength > features[b].strength; });
+    }
 
     std::vector<size_t> kept;
-    kept.reserve(features.size() / 4);
+    kept.reserve(count);
     const double limit = spacing_pixels * spacing_pixels;
     const bool gridded = spacing_pixels > 0 && std::isfinite(spacing_pixels);
-    // kept points bucketed by grid cell (cell = spacing) in a flat chained hash table: a point closer than `spacing`
-    // lies at most one cell away; two cells are searched so that a quotient rounded across a cell border cannot hide it
+    // kept points bucketed by grid cell in a flat chained hash table. The cell is a little LARGER than the spacing: two
+    // points no farther apart than `spacing` then differ by less than 0.999 cells per axis, so even with the quotient
+    // x / cell rounded (|x / cell| < 1e9: error below 2.3e-7 cells) their cell indices differ by at most one, and the
+    // 3 x 3 neighbourhood holds every kept point that can reject the candidate
+    const double cell = spacing_pixels * 1.001;
     size_t table_size = 64;
-    while (table_size < 4 * count)
+    while (table_size < 2 * count)
         table_size <<= 1;
     std::vector<int32_t> head(table_size, -1);
     struct Entry
     {
         uint64_t key;
         int32_t next;
-        size_t idx;
+        uint32_t pad;
+        double x, y;
     };
     std::vector<Entry> entries;
     entries.reserve(count);
@@ -148,24 +174,33 @@ std::vector<size_t> spatially_subsample_feature_indices(const std::vector<featur
     for (size_t idx : by_strength)
     {
         const double x = features[idx].location.x(), y = features[idx].location.y();
-        const bool finite = gridded && std::isfinite(x) && std::isfinite(y) && std::abs(x / spacing_pixels) < 1e9 &&
-                            std::abs(y / spacing_pixels) < 1e9;
+        const bool finite = gridded && std::isfinite(x) && std::isfinite(y) && std::abs(x / cell) < 1e9 &&
+                            std::abs(y / cell) < 1e9;
         bool keep = true;
+        int64_t cx = 0, cy = 0;
+        if (finite)
+            cx = (int64_t)std::floor(x / cell), cy = (int64_t)std::floor(y / cell);
         if (!kept.empty())
         {
             if (finite)
             {
-                const int64_t cx = (int64_t)std::floor(x / spacing_pixels), cy = (int64_t)std::floor(y / spacing_pixels);
-                for (int64_t gx = cx - 2; gx <= cx + 2 && keep; gx++)
-                    for (int64_t gy = cy - 2; gy <= cy + 2 && keep; gy++)
+                for (int64_t gx = cx - 1; gx <= cx + 1 && keep; gx++)
+                    for (int64_t gy = cy - 1; gy <= cy + 1 && keep; gy++)
                     {
                         const uint64_t key = cell_key(gx, gy);
                         for (int32_t e = head[slot_of(key)]; e >= 0; e = entries[e].next)
-                            if (entries[e].key == key && too_close(idx, entries[e].idx))
+                        {
+                            if (entries[e].key != key)
+                                continue;
+                            // the same subtraction, squares and sum as too_close(): (x - x') and (y - y') on the
+                            // coordinates kept next to the key (no trip to the feature structs)
+                            const double dx = x - entries[e].x, dy = y - entries[e].y;
+                            if (!(dx * dx + dy * dy > limit))
                             {
                                 keep = false;
                                 break;
                             }
+                        }
                     }
                 for (size_t other : unbucketed)
                     if (keep && too_close(idx, other))
@@ -185,9 +220,9 @@ std::vector<size_t> spatially_subsample_feature_indices(const std::vector<featur
             continue;
         if (finite)
         {
-            const uint64_t key = cell_key((int64_t)std::floor(x / spacing_pixels), (int64_t)std::floor(y / spacing_pixels));
+            const uint64_t key = cell_key(cx, cy);
             const size_t sl = slot_of(key);
-            entries.push_back(Entry{key, head[sl], idx});
+            entries.push_back(Entry{key, head[sl], 0u, x, y});
             head[sl] = (int32_t)(entries.size() - 1);
         }
         else

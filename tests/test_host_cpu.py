@@ -164,3 +164,20 @@ def test_synthetic_generators_are_seeded():
     imgs, pos, pairs = synthetic.grid_survey(3, 4, 128, seed=7)
     assert len(imgs) == 12 and all(i.shape == (128, 8) for i in imgs)
     assert all(a != b for a, b in pairs) and len(pairs) == 12 * 9
+
+
+def test_subsample_equals_the_reference_code_on_adversarial_layouts(hostlib, reference):
+    """spatially_subsample_feature_indices (match_features.cpp:8-52) answers the nearest-kept-neighbour query from a hash
+    grid and sorts compact records; the decisions and the order must be the reference's own (KD-tree, indirect sort)
+    also for points on cell borders, duplicates, strength ties, negative and huge coordinates."""
+    rng = np.random.default_rng(0)
+    for trial in range(150):
+        n = int(rng.integers(1, 400))
+        sp = float(rng.choice([0.5, 1.0, 7.3, 40.0, 1e-3, 1e4]))
+        xy = rng.integers(-50, 50, (n, 2)) * sp * rng.choice([1.0, 0.5, 1.001, 0.999]) + rng.choice([0, 1e7, -3e8])
+        if trial % 3 == 0:
+            xy = rng.normal(0, sp * 3, (n, 2))
+        st = rng.integers(0, 8, n).astype(np.float32) / 8 if trial % 2 else rng.random(n).astype(np.float32)
+        count = 0 if trial % 5 else int(rng.integers(1, n + 1))
+        got = hostlib.spatially_subsample_feature_indices(xy, st, sp, count)
+        assert np.array_equal(got, reference.subsample(xy, st, sp, count)), (trial, n, sp, count)
