@@ -524,7 +524,8 @@ def measure_survey(torch, dist, rank, local_rank, world, workload, steps, warmup
     pairs = survey.pairs
     if workload == "c5":
         pairs = pairs[:40000]
-    shard = sharding.partition(survey.positions, pairs, world)[rank]
+    shards = sharding.partition(survey.positions, pairs, world)
+    shard = shards[rank]
     resident = shard.resident_images.tolist()
     local_index = {g: i for i, g in enumerate(resident)}
     cores = os.cpu_count() or 1
@@ -534,7 +535,9 @@ def measure_survey(torch, dist, rank, local_rank, world, workload, steps, warmup
     cams = [survey.camera8()] * len(sets)
     local_pairs = [(local_index[a], local_index[b]) for a, b in shard.pairs]
     threads = max(1, cores // world - 1)  # one core per rank stays free for the submission threads
-    gather = sharding.MatchGather(capacity_records=max(1, len(local_pairs)) * 8192, dist=dist)
+    most = max(len(sh.pairs) for sh in shards)
+    gather = sharding.MatchGather(capacity_records=max(1, most) * 8192, max_pairs=most, dist=dist)
+    packed = gather.buffers()  # this rank's region of the segment: the runner's tail workers write into it directly
 
     def barrier():
         torch.cuda.synchronize()
@@ -546,12 +549,10 @@ def measure_survey(torch, dist, rank, local_rank, world, workload, steps, warmup
     def step():
         t_a = time.perf_counter()
         res = host.link_pairs(sets, cams, local_pairs, threads=threads, pairs_per_submission=pairs_per_submission,
-                              run_ransac=with_ransac, spacing=spacing)
+                              run_ransac=with_ransac, spacing=spacing, packed=packed)
         t_b = time.perf_counter()
-        counts, _ = res.pack_matches(out=gather.region(), threads=threads)  # this rank's lists, straight into the segment
-        t_c = time.perf_counter()
-        out = gather.gather(shard.pair_ids, counts, len(pairs))
-        phase[:] += (t_b - t_a, t_c - t_b, time.perf_counter() - t_c)
+        out = gather.gather([sh.pair_ids for sh in shards], len(pairs))
+        phase[:] += (t_b - t_a, 0.0, time.perf_counter() - t_b)
         return res, out
 
     # warm-up: whole untimed steps (they size the page-locked result buffers, the per-thread staging areas and the
@@ -603,10 +604,11 @@ def measure_survey(torch, dist, rank, local_rank, world, workload, steps, warmup
             "ransac_inliers": int(inliers), "pairs_with_matches": int(kept_all),
             "resident_images_all_ranks": int(resident_all), "host_threads_per_rank": threads, "host_cores": cores,
             "rank0_breakdown_s": {k: v for k, v in stats.items() if k.startswith("seconds")},
-            "per_rank": [{"pairs": int(r[0]), "resident_images": int(r[1]), "link_pairs_s": r[2], "pack_s": r[3],
-                          "gather_s": r[4]} for r in per_rank.cpu().tolist()],
+            "per_rank": [{"pairs": int(r[0]), "resident_images": int(r[1]), "link_pairs_s": r[2],
+                          "gather_wait_s": r[4]} for r in per_rank.cpu().tolist()],
             "gather": {"what": "every pair's match list (12-byte records), all ranks -> rank 0, serial pair order",
-                       "transport": "POSIX shared memory on the box + torch.distributed all_gather of the index",
+                       "transport": "POSIX shared memory on the box (records and index written by the tail workers while "
+                                    "the rank is still matching) + torch.distributed barrier",
                        "records": gathered.total(), "bytes": gathered.total() * 12},
             "h2d_bytes_per_step": int(resident_all) * 8192 * (64 + (16 if with_ransac else 0)),
             "d2h_bytes_per_step": int(matches) * 12, "gpu_launches": int(launches), "clocks": clocks,
@@ -638,7 +640,7 @@ def measure_survey(torch, dist, rank, local_rank, world, workload, steps, warmup
                 if not same:
                     break
                 n = int(counts1[p])
-                same = np.array_equal(rec1[o:o + n], gathered.records[int(gathered.offsets[p]):int(gathered.offsets[p]) + n])
+                same = np.array_equal(rec1[o:o + n], gathered.records(p))
                 o += n
             assert same, "the gathered match lists differ from the single-GPU result"
             block["gathered_equals_single_gpu_result"] = True
@@ -680,6 +682,7 @@ def measure_survey(torch, dist, rank, local_rank, world, workload, steps, warmup
             "pairs_per_s": len(sample) / d_secs, "pairs": len(sample), "host_threads": threads, "matches": d_matches,
             "api": "match_features_subset(std::vector<feature_2d>...) per pair, all features of both images, one "
                    "closure per OpenMP worker like run_parallel (src/pipeline/pipeline.cpp:42-49)"}
+    del gathered, packed
     gather.close()
     for fs in sets:
         fs.close()

@@ -74,7 +74,7 @@ def lib():
     L.ocbh_run_parallel_match.argtypes = [_u64p, _u64p, sz, sz, sz, i32, _szp, _f64p]
     L.ocbh_image_to_3d.argtypes = [_f64p, sz, _f64p, _f64p]
     L.ocbh_image_to_3d.restype = None
-    L.ocbh_link_pairs.argtypes = [C.c_void_p, _szp, _f64p, sz, _szp, sz, i32, sz, i32, dbl, i32, i32, vp]
+    L.ocbh_link_pairs.argtypes = [C.c_void_p, _szp, _f64p, sz, _szp, sz, i32, sz, i32, dbl, i32, i32, vp, vp, sz, vp, vp]
     L.ocbh_link_pairs.restype = C.c_void_p
     L.ocbh_link_pack_matches.argtypes = [C.c_void_p, vp, vp, i32]
     L.ocbh_link_pack_matches.restype = sz
@@ -413,11 +413,13 @@ class LinkResults:
 
 
 def link_pairs(feature_sets, cameras8, pairs, num_sparse=None, threads=0, pairs_per_submission=0, run_ransac=True,
-               spacing=0.0, device_tail=True, n_devices=1, positions=None):
+               spacing=0.0, device_tail=True, n_devices=1, positions=None, packed=None):
     """What LinkStage's closures compute for every (image, neighbour) pair (src/pipeline/link_stage.cpp:75-112), for
     the whole pair list: feature_sets = FeatureSet per image, cameras8 = camera8() per image, pairs = [(i, j)].
     device_tail=False keeps the ratio test and the rays on the host (A/B). n_devices > 1: the pair list is partitioned
-    over that many GPUs of this process along the Hilbert curve of `positions` ([n][2]; None: image index order)."""
+    over that many GPUs of this process along the Hilbert curve of `positions` ([n][2]; None: image index order).
+    packed = (records uint32 flat buffer, offsets uint64 [n_pairs], counts uint64 [n_pairs]): the tail workers also write
+    every pair's final match list as 12-byte records into `records` (LinkOptions::packed_out)."""
     n = len(feature_sets)
     h = (C.c_void_p * n)(*[s.handle for s in feature_sets])
     ns = np.zeros(n, np.uintp) if num_sparse is None else np.ascontiguousarray(num_sparse, np.uintp)
@@ -426,7 +428,10 @@ def link_pairs(feature_sets, cameras8, pairs, num_sparse=None, threads=0, pairs_
     pos = None if positions is None else np.ascontiguousarray(positions, np.float64).reshape(n, 2)
     res = lib().ocbh_link_pairs(h, ns, cams, n, pr, len(pr), int(threads), int(pairs_per_submission), int(run_ransac),
                                float(spacing), int(bool(device_tail)), int(n_devices),
-                               None if pos is None else pos.ctypes.data_as(C.c_void_p))
+                               None if pos is None else pos.ctypes.data_as(C.c_void_p),
+                               *((None, 0, None, None) if packed is None else
+                                 (packed[0].ctypes.data_as(C.c_void_p), packed[0].size // 3,
+                                  packed[1].ctypes.data_as(C.c_void_p), packed[2].ctypes.data_as(C.c_void_p))))
     if not res:
         raise OcbError("host mirror: " + lib().ocbh_last_error().decode())
     return LinkResults(res, len(pr))

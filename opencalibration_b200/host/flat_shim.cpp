@@ -533,10 +533,12 @@ extern "C"
         ocb_host::LinkStats stats;
     };
     // device_tail: 1 = ratio test, compaction and rays on the device (default), 0 = on the host. n_devices > 1: the pair
-    // list is partitioned over that many GPUs of this process (positions2: [n_images][2], nullable).
+    // list is partitioned over that many GPUs of this process (positions2: [n_images][2], nullable). packed_*: see
+    // LinkOptions (nullable; single-device runs only).
     void *ocbh_link_pairs(const void *const *image_handles, const size_t *num_sparse, const double *cam8, size_t n_images,
                           const size_t *pairs2, size_t n_pairs, int threads, size_t pairs_per_submission, int run_ransac,
-                          double spacing, int device_tail, int n_devices, const double *positions2)
+                          double spacing, int device_tail, int n_devices, const double *positions2, uint32_t *packed_out,
+                          size_t packed_capacity, uint64_t *packed_offsets, uint64_t *packed_counts)
     {
         auto *res = new LinkResultHandle;
         const int rc = guarded([&] {
@@ -562,6 +564,8 @@ extern "C"
             if (spacing > 0)
                 opt.coarse_spacing_pixels = spacing;
             opt.device_tail = device_tail != 0;
+            opt.packed_out = packed_out, opt.packed_capacity = packed_capacity;
+            opt.packed_offsets = packed_offsets, opt.packed_counts = packed_counts;
             if (n_devices > 1)
                 res->relations = ocb_host::link_pairs_multi(images, pairs, positions2, n_devices, opt, &res->stats);
             else

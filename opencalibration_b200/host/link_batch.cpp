@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <cmath>
 #include <cstring>
 #include <condition_variable>
 #include <deque>
@@ -138,17 +139,32 @@ void finish_pair(const ocb_host::LinkImage &img, const ocb_host::LinkImage &near
 class HelperThreads
 {
   public:
-    std::future<void> run(std::function<void()> fn)
+    // Role k of every call runs on the SAME thread (the subsample / upload thread, submission thread 0, submission
+    // thread 1, tail consumer 1, ...): that thread's libocb context -- streams, staging areas sized for exactly this
+    // role -- is warm from the previous call. (A shared queue let any parked thread take any role, and every thread
+    // then had to grow its own page-locked staging area once per role: tens of milliseconds on a box where such an
+    // allocation is mapped into eight GPUs, right at the start of a call, when nothing else can run.)
+    std::future<void> run(size_t role, std::function<void()> fn)
     {
         std::packaged_task<void()> task(std::move(fn));
         std::future<void> done = task.get_future();
+        Worker *w;
         {
             std::lock_guard<std::mutex> lk(mu_);
-            queue_.push_back(std::move(task));
-            if (idle_ < queue_.size())
-                std::thread(&HelperThreads::loop, this).detach();
+            while (workers_.size() <= role)
+                workers_.push_back(nullptr);
+            if (!workers_[role])
+            {
+                workers_[role] = new Worker;
+                std::thread(&HelperThreads::loop, workers_[role]).detach();
+            }
+            w = workers_[role];
         }
-        cv_.notify_one();
+        {
+            std::lock_guard<std::mutex> lk(w->mu);
+            w->queue.push_back(std::move(task));
+        }
+        w->cv.notify_one();
         return done;
     }
     static HelperThreads &instance(int device)
@@ -163,26 +179,28 @@ class HelperThreads
     }
 
   private:
-    void loop()
+    struct Worker
+    {
+        std::mutex mu;
+        std::condition_variable cv;
+        std::deque<std::packaged_task<void()>> queue;
+    };
+    static void loop(Worker *w)
     {
         for (;;)
         {
             std::packaged_task<void()> task;
             {
-                std::unique_lock<std::mutex> lk(mu_);
-                ++idle_;
-                cv_.wait(lk, [&] { return !queue_.empty(); });
-                --idle_;
-                task = std::move(queue_.front());
-                queue_.pop_front();
+                std::unique_lock<std::mutex> lk(w->mu);
+                w->cv.wait(lk, [&] { return !w->queue.empty(); });
+                task = std::move(w->queue.front());
+                w->queue.pop_front();
             }
             task();
         }
     }
     std::mutex mu_;
-    std::condition_variable cv_;
-    std::deque<std::packaged_task<void()>> queue_;
-    size_t idle_ = 0;
+    std::vector<Worker *> workers_;
 };
 
 // The helper threads of one link_pairs call work on that call's stack variables. Whatever way the call is left
@@ -232,16 +250,41 @@ std::vector<camera_relations> link_pairs(const std::vector<LinkImage> &images, c
     const bool device_tail = options.device_tail;
 
     // ---- submissions. The first ones are small and grow geometrically up to pairs_per_submission: the GPU starts on
-    // the first pairs as soon as THEIR images are resident, and the first results reach the tail workers early; after
-    // the ramp every submission is large enough to fill the SMs for tens of milliseconds.
+    // the first pairs as soon as THEIR images are resident, and the first results reach the tail workers early. The
+    // last ones shrink the same way: what is left to do after the GPU has finished is the tail of a small submission.
+    // In between every submission is large enough to fill the SMs for tens of milliseconds.
     const size_t per = std::max<size_t>(1, options.pairs_per_submission);
     std::vector<std::pair<size_t, size_t>> chunk; // [begin, end) into `pairs`
-    for (size_t begin = 0, size = std::min<size_t>(per, std::max<size_t>(1, options.first_submission)); begin < n_pairs;)
     {
-        const size_t end = std::min(n_pairs, begin + size);
-        chunk.emplace_back(begin, end);
-        begin = end;
-        size = std::min(per, size * 2);
+        std::vector<size_t> ramp; // 32, 64, 128, ... below `per`
+        for (size_t size = std::max<size_t>(1, options.first_submission); size < per; size *= 2)
+            ramp.push_back(size);
+        size_t ramp_total = 0;
+        for (size_t r : ramp)
+            ramp_total += r;
+        std::vector<size_t> sizes;
+        if (n_pairs > 2 * ramp_total + per)
+        {
+            sizes = ramp;
+            const size_t middle = n_pairs - 2 * ramp_total, k = (middle + per - 1) / per;
+            for (size_t i = 0; i < k; i++)
+                sizes.push_back(middle / k + (i < middle % k ? 1 : 0)); // equal middle submissions
+            sizes.insert(sizes.end(), ramp.rbegin(), ramp.rend());
+        }
+        else // short pair list: ramp up only
+            for (size_t left = n_pairs, size = ramp.empty() ? per : ramp.front(); left;)
+            {
+                const size_t take = std::min(left, size);
+                sizes.push_back(take);
+                left -= take;
+                size = std::min(per, size * 2);
+            }
+        size_t begin = 0;
+        for (size_t sz : sizes)
+        {
+            chunk.emplace_back(begin, begin + sz);
+            begin += sz;
+        }
     }
     const size_t n_chunks = chunk.size();
 
@@ -272,6 +315,12 @@ std::vector<camera_relations> link_pairs(const std::vector<LinkImage> &images, c
     bool stop = false;   // set on the first error: everybody drains
     size_t prepared = 0; // images of `order` that are subsampled and resident
     double prepare_seconds = 0;
+    // timeline of every submission, seconds since the call began (OCB_LINK_TRACE=2 prints it)
+    struct ChunkTimes
+    {
+        double ready = 0, launch = 0, matched = 0, tail_begin = 0, tail_end = 0;
+    };
+    std::vector<ChunkTimes> timeline(n_chunks);
     auto prepare = [&]() {
         ocb_set_device(device);
         const size_t batch = (size_t)std::max(32, 4 * threads);
@@ -343,7 +392,12 @@ std::vector<camera_relations> link_pairs(const std::vector<LinkImage> &images, c
                     stop = true;
                 }
                 else
+                {
                     prepared = end;
+                    for (size_t cc = 0; cc < n_chunks; cc++)
+                        if (timeline[cc].ready == 0 && chunk_needs[cc] <= prepared)
+                            timeline[cc].ready = since(t_begin);
+                }
                 cv.notify_all();
                 if (stop)
                     return;
@@ -430,6 +484,7 @@ std::vector<camera_relations> link_pairs(const std::vector<LinkImage> &images, c
                 total += indices[pairs[p].image_1].size();
             }
             const auto t0 = clock_type::now();
+            timeline[c].launch = since(t_begin);
             int rc;
             if (device_tail) // K1 + ratio test + compaction on the device: only the survivors come back
                 rc = ocb_match_pairs_ratio(sub.data(), sub.size(), static_cast<ocb_match *>(sl.records), max_rows,
@@ -437,6 +492,7 @@ std::vector<camera_relations> link_pairs(const std::vector<LinkImage> &images, c
             else
                 rc = ocb_match_pairs(sub.data(), sub.size(), static_cast<ocb_top2 *>(sl.records), sl.offsets.data());
             sl.gpu_seconds = since(t0);
+            timeline[c].matched = since(t_begin);
             std::lock_guard<std::mutex> lk(mu);
             if (rc)
             {
@@ -455,6 +511,7 @@ std::vector<camera_relations> link_pairs(const std::vector<LinkImage> &images, c
 
     std::vector<camera_relations> relations(n_pairs);
     std::atomic<size_t> next_chunk{0}, total_matches{0}, total_inliers{0};
+    std::atomic<uint64_t> packed_cursor{0};
     double tail_seconds = 0, gpu_seconds = 0;
     double phase_seconds[3] = {0, 0, 0}; // consumer wall time in (a) ratio test / sort / rays, (b) RANSAC, (c) finish
     auto fail = [&](const std::string &what) {
@@ -480,6 +537,7 @@ std::vector<camera_relations> link_pairs(const std::vector<LinkImage> &images, c
             }
             const size_t begin = chunk[c].first, end = chunk[c].second, cn = end - begin;
             const auto t0 = clock_type::now();
+            timeline[c].tail_begin = since(t_begin);
             std::string local_error;
             size_t n_matches = 0, n_inl = 0;
             // (a) per pair: [ratio test +] the reference's std::sort -> match list (link_stage.cpp:83-85);
@@ -607,8 +665,37 @@ std::vector<camera_relations> link_pairs(const std::vector<LinkImage> &images, c
                     }
                 }
             }
+            // (d) the flat copy of the final match lists, if the caller gathers them
+            if (options.packed_out && local_error.empty())
+            {
+                std::vector<uint64_t> at(cn + 1, 0);
+                for (size_t k = 0; k < cn; k++)
+                    at[k + 1] = at[k] + relations[begin + k].matches.size();
+                const uint64_t base = packed_cursor.fetch_add(at[cn]);
+                if (base + at[cn] > options.packed_capacity)
+                    local_error = "link_pairs: packed_capacity is smaller than the number of matches";
+                else
+                {
+#pragma omp parallel for schedule(dynamic, 4) num_threads(team)
+                    for (size_t k = 0; k < cn; k++)
+                    {
+                        uint32_t *out = options.packed_out + 3 * (base + at[k]);
+                        for (const feature_match &m : relations[begin + k].matches)
+                        {
+                            out[0] = (uint32_t)m.feature_index_1, out[1] = (uint32_t)m.feature_index_2;
+                            out[2] = (uint32_t)std::lround(m.distance * feature_2d::DESCRIPTOR_BITS);
+                            out += 3;
+                        }
+                        if (options.packed_offsets)
+                            options.packed_offsets[begin + k] = base + at[k];
+                        if (options.packed_counts)
+                            options.packed_counts[begin + k] = at[k + 1] - at[k];
+                    }
+                }
+            }
             total_matches += n_matches;
             total_inliers += n_inl;
+            timeline[c].tail_end = since(t_begin);
             {
                 std::lock_guard<std::mutex> lk(mu);
                 const double t_c = since(t0);
@@ -629,12 +716,12 @@ std::vector<camera_relations> link_pairs(const std::vector<LinkImage> &images, c
         HelperGuard helpers{mu, cv, stop, {}};
         HelperThreads &pool = HelperThreads::instance(device);
         helpers.tasks.reserve(2 + n_producers + (size_t)workers);
-        helpers.tasks.push_back(pool.run(prepare));
+        helpers.tasks.push_back(pool.run(0, prepare));
         for (size_t k = 0; k < n_producers; k++)
-            helpers.tasks.push_back(pool.run([&produce, k]() { produce(k); }));
+            helpers.tasks.push_back(pool.run(1 + k, [&produce, k]() { produce(k); }));
         const size_t first_consumer = helpers.tasks.size();
         for (int w = 1; w < workers; w++)
-            helpers.tasks.push_back(pool.run(consume));
+            helpers.tasks.push_back(pool.run(2 + (size_t)w, consume));
         consume();
         for (size_t k = first_consumer; k < helpers.tasks.size(); k++)
             helpers.tasks[k].wait(); // every chunk is consumed (or an error stopped the run); the guard releases the rest
@@ -659,6 +746,12 @@ std::vector<camera_relations> link_pairs(const std::vector<LinkImage> &images, c
                      "tail %.3f s = sort/rays %.3f + ransac %.3f + finish %.3f, total %.3f s\n",
                      n_pairs, n_chunks, workers, team, st.seconds_subsample_upload, gpu_seconds, tail_seconds,
                      phase_seconds[0], phase_seconds[1], phase_seconds[2], st.seconds_total);
+    if (const char *tr = std::getenv("OCB_LINK_TRACE"))
+        if (tr[0] == '2')
+            for (size_t c = 0; c < n_chunks; c++)
+                std::fprintf(stderr, "  chunk %2zu: %4zu pairs, images ready %.4f, launch %.4f, matched %.4f, tail %.4f .. %.4f\n", c,
+                             chunk[c].second - chunk[c].first, timeline[c].ready, timeline[c].launch, timeline[c].matched,
+                             timeline[c].tail_begin, timeline[c].tail_end);
     if (stats)
         *stats = st;
     return relations;

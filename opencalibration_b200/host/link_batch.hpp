@@ -43,6 +43,17 @@ struct LinkOptions
     // assembleInliers. false: the K1 records of every query come back and the host does the ratio test and the rays
     // (the round-1 path, kept for A/B tests: both give identical relations).
     bool device_tail = true;
+    // Optional flat copy of every pair's final match list, written by the tail workers as the submissions finish (what
+    // a rank contributes to the host gather of the match lists, link_stage.cpp:119-131): 12-byte records
+    // {feature_index_1, feature_index_2, integer Hamming distance} (distance = d * (1.0 / 486) exactly) into
+    // packed_out, which holds packed_capacity records (e.g. a region of shared memory); pair p's records are
+    // packed_out[3 * packed_offsets[p] ..) for packed_counts[p] records. The lists of one submission are contiguous; the
+    // submissions land in the order in which their tails finish. All three arrays are the caller's (offsets / counts:
+    // one entry per pair).
+    uint32_t *packed_out = nullptr;
+    size_t packed_capacity = 0;
+    uint64_t *packed_offsets = nullptr;
+    uint64_t *packed_counts = nullptr;
 };
 struct LinkStats
 {

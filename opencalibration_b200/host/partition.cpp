@@ -151,6 +151,7 @@ std::vector<opencalibration::camera_relations> link_pairs_multi(const std::vecto
                     part_pairs[k] = LinkPair{local[pairs[sh.pair_ids[k]].image_1], local[pairs[sh.pair_ids[k]].image_2]};
                 LinkOptions opt = options;
                 opt.threads = std::max(1, all_threads / n_devices);
+                opt.packed_out = nullptr, opt.packed_offsets = opt.packed_counts = nullptr; // per-part lists are not packed
                 std::vector<opencalibration::camera_relations> part =
                     link_pairs(part_images, part_pairs, opt, &part_stats[(size_t)d]);
                 for (size_t k = 0; k < sh.pair_ids.size(); k++)

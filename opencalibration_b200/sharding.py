@@ -8,11 +8,11 @@ of the variable-length match lists back into the serial pair order, which is wha
 runners' results (reference src/pipeline/link_stage.cpp:119-131).
 
 Gather. All ranks of the job run on one box (north_star: "the 8 GPUs of one box"), so the gather goes through POSIX
-shared memory: rank 0 creates one segment, every rank packs its match lists (12-byte records: feature_index_1,
-feature_index_2, integer Hamming distance) straight into its own region of it, and a barrier later rank 0 holds every
-list without another copy; the serial order is restored as an index (pair -> offset, count), the way the reference
-moves vector handles rather than their contents. torch.distributed carries the region sizes (all_gather) and the
-barrier.
+shared memory: rank 0 creates one segment, every rank's tail workers write its match lists (12-byte records:
+feature_index_1, feature_index_2, integer Hamming distance) and their index straight into its own region of it while
+the rank is still matching, and a barrier later rank 0 holds every list without another copy; the serial order is
+restored as an index (pair -> offset, count), the way the reference moves vector handles rather than their contents.
+torch.distributed carries the segment's name and the barrier.
 """
 from dataclasses import dataclass, field
 from multiprocessing import shared_memory
@@ -72,15 +72,21 @@ RECORD_WORDS = 3  # uint32 words per match record: feature_index_1, feature_inde
 class GatheredMatches:
     """What rank 0 holds after the gather: every pair's match list, addressable in serial pair order."""
 
-    def __init__(self, records, offsets, counts):
-        self.records, self.offsets, self.counts = records, offsets, counts  # records [total][3] uint32
+    def __init__(self, words, offsets, counts):
+        # words: the whole segment as uint32; offsets[p]: index of pair p's first word; counts[p]: its records
+        self.words, self.offsets, self.counts = words, offsets, counts
 
     def __len__(self):
         return len(self.counts)
 
+    def records(self, p):
+        """-> [n][3] uint32 view: feature_index_1, feature_index_2, integer Hamming distance."""
+        o, n = int(self.offsets[p]), int(self.counts[p])
+        return self.words[o:o + n * RECORD_WORDS].reshape(n, RECORD_WORDS)
+
     def pair(self, p):
         """-> (feature_index_1, feature_index_2, distance) of pair p; distance = d * (1.0 / 486) like the reference."""
-        r = self.records[int(self.offsets[p]):int(self.offsets[p]) + int(self.counts[p])]
+        r = self.records(p)
         return r[:, 0].astype(np.uintp), r[:, 1].astype(np.uintp), r[:, 2] * (1.0 / 486)
 
     def total(self):
@@ -90,15 +96,20 @@ class GatheredMatches:
 class MatchGather:
     """Host gather of per-pair match lists to rank 0 through one shared-memory segment (see the module docstring).
 
-    capacity_records = upper bound of the records any ONE rank contributes (e.g. its query rows); the segment holds
-    world * capacity_records records of 12 bytes, of which only the pages actually written are ever touched."""
+    capacity_records = upper bound of the records any ONE rank contributes (e.g. its query rows), max_pairs = upper bound
+    of the pairs of any one rank. Per rank the segment holds an index (offset and count of every pair of that rank, in
+    the rank's pair order) followed by the records; only the pages actually written are ever touched. A rank hands
+    buffers() to the runner (host.link_pairs(packed=...)), which writes both while it works; gather() is then a barrier
+    plus, on rank 0, building the serial-order index."""
 
-    def __init__(self, capacity_records, dist=None, name=None):
+    def __init__(self, capacity_records, max_pairs, dist=None, name=None):
         self.dist = dist if (dist is not None and dist.is_initialized() and dist.get_world_size() > 1) else None
         self.rank = self.dist.get_rank() if self.dist else 0
         self.world = self.dist.get_world_size() if self.dist else 1
-        self.capacity = int(capacity_records)
-        nbytes = max(1, self.world * self.capacity * RECORD_WORDS * 4)
+        self.capacity, self.max_pairs = int(capacity_records), max(1, int(max_pairs))
+        self.stride = 2 * 8 * self.max_pairs + self.capacity * RECORD_WORDS * 4  # bytes per rank
+        self.stride = (self.stride + 4095) // 4096 * 4096
+        nbytes = max(1, self.world * self.stride)
         if self.rank == 0:
             self.shm = shared_memory.SharedMemory(create=True, size=nbytes, name=name)
             names = [self.shm.name]
@@ -113,49 +124,44 @@ class MatchGather:
                     resource_tracker.unregister(self.shm._name, "shared_memory")
                 except Exception:  # noqa: BLE001
                     pass
-        self.words = np.ndarray((self.world, self.capacity * RECORD_WORDS), np.uint32, buffer=self.shm.buf)
 
-    def region(self):
-        """This rank's region of the segment (flat uint32): pack the match records straight into it."""
-        return self.words[self.rank]
+    def _views(self, r):
+        base = r * self.stride
+        index = np.ndarray((2, self.max_pairs), np.uint64, buffer=self.shm.buf, offset=base)
+        records = np.ndarray((self.capacity * RECORD_WORDS,), np.uint32, buffer=self.shm.buf,
+                             offset=base + 2 * 8 * self.max_pairs)
+        return records, index[0], index[1]
 
-    def gather(self, pair_ids, counts, n_pairs):
-        """Collective. pair_ids / counts: this rank's pairs (global ids, ascending) and their match counts, the records
-        already packed into region() pair after pair. Returns GatheredMatches on rank 0, None elsewhere."""
-        import torch
-        pair_ids = np.asarray(pair_ids, np.int64)
-        counts = np.asarray(counts, np.int64)
-        assert len(pair_ids) == len(counts) and int(counts.sum()) <= self.capacity
+    def buffers(self):
+        """This rank's (records flat uint32, offsets uint64 [max_pairs], counts uint64 [max_pairs])."""
+        return self._views(self.rank)
+
+    def gather(self, pair_ids_by_rank, n_pairs):
+        """Collective. pair_ids_by_rank[r] = the global ids of rank r's pairs in that rank's pair order (every rank can
+        compute all of them: the partition is deterministic). Returns GatheredMatches on rank 0, None elsewhere."""
         if self.dist:
-            # sizes first (so that every rank can post a matching receive), then ids and counts padded to the longest
-            dev = torch.device("cuda", torch.cuda.current_device()) if self.dist.get_backend() == "nccl" else "cpu"
-            sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(self.world)]
-            self.dist.all_gather(sizes, torch.tensor([len(pair_ids)], dtype=torch.int64, device=dev))
-            longest = max(int(s.item()) for s in sizes)
-            mine = torch.zeros(2, max(longest, 1), dtype=torch.int64)
-            mine[0, :len(pair_ids)] = torch.from_numpy(pair_ids)
-            mine[1, :len(counts)] = torch.from_numpy(counts)
-            mine = mine.to(dev)
-            every = [torch.zeros_like(mine) for _ in range(self.world)]
-            self.dist.all_gather(every, mine)  # also orders every rank's writes to the segment before rank 0's reads
-            self.dist.barrier()
+            self.dist.barrier()  # every rank's records and index are in the segment
             if self.rank != 0:
                 return None
-            parts = [(e[0, :int(s.item())].cpu().numpy(), e[1, :int(s.item())].cpu().numpy()) for e, s in zip(every, sizes)]
-        else:
-            parts = [(pair_ids, counts)]
         offsets = np.full(n_pairs, -1, np.int64)
-        all_counts = np.zeros(n_pairs, np.int64)
-        for r, (ids, cnt) in enumerate(parts):
-            assert np.all(offsets[ids] == -1), "a pair was matched twice"
-            start = np.concatenate([[0], np.cumsum(cnt)[:-1]]) if len(cnt) else np.zeros(0, np.int64)
-            offsets[ids] = r * self.capacity + start
-            all_counts[ids] = cnt
+        counts = np.zeros(n_pairs, np.int64)
+        rec_base = 2 * 8 * self.max_pairs // (RECORD_WORDS * 4)  # not a whole record in general: index in words instead
+        for r, ids in enumerate(pair_ids_by_rank):
+            ids = np.asarray(ids, np.int64)
+            assert len(ids) <= self.max_pairs
+            _, off, cnt = self._views(r)
+            seen = offsets[ids] != -1
+            assert not seen.any() and len(np.unique(ids)) == len(ids), "a pair was matched twice"
+            assert int((off[:len(ids)] + cnt[:len(ids)]).max(initial=0)) <= self.capacity
+            # word offset of the pair's first record in the whole segment
+            offsets[ids] = (r * self.stride + 2 * 8 * self.max_pairs) // 4 + off[:len(ids)].astype(np.int64) * RECORD_WORDS
+            counts[ids] = cnt[:len(ids)].astype(np.int64)
+        del rec_base
         assert np.all(offsets >= 0), f"{int((offsets < 0).sum())} pairs were never matched"
-        return GatheredMatches(self.words.reshape(-1, RECORD_WORDS), offsets, all_counts)
+        words = np.ndarray((len(self.shm.buf) // 4,), np.uint32, buffer=self.shm.buf)
+        return GatheredMatches(words, offsets, counts)
 
     def close(self):
-        self.words = None
         try:
             self.shm.close()
             if self.rank == 0:

@@ -171,6 +171,25 @@ def test_device_tail_equals_host_tail(gpu, hostlib, distorted):
     ref2 = hostlib.link_pairs(sets, [cam] * len(sets), pairs, device_tail=False, run_ransac=False, **kw)
     for p in range(len(pairs)):
         assert all(np.array_equal(x, y) for x, y in zip(dev2.get(p)["matches"], ref2.get(p)["matches"]))
+    # the flat copy the tail workers write while the call runs (LinkOptions::packed_out): per pair an offset and a count
+    rec = np.zeros(3 * dev2.stats["matches"], np.uint32)
+    off, cnt = np.zeros(len(pairs), np.uint64), np.zeros(len(pairs), np.uint64)
+    dev3 = hostlib.link_pairs(sets, [cam] * len(sets), pairs, run_ransac=False, packed=(rec, off, cnt), **kw)
+    spans = sorted((int(o), int(c)) for o, c in zip(off, cnt) if c)
+    assert all(a + n <= b for (a, n), (b, _) in zip(spans, spans[1:])) and int(cnt.sum()) == dev3.stats["matches"]
+    for p in range(len(pairs)):
+        i1, i2, d = dev3.get(p)["matches"]
+        r = rec.reshape(-1, 3)[int(off[p]):int(off[p]) + int(cnt[p])]
+        assert np.array_equal(r[:, 0], i1) and np.array_equal(r[:, 1], i2) and np.array_equal(r[:, 2] * (1.0 / 486), d)
+    with pytest.raises(hostlib.OcbError, match="packed_capacity"):
+        hostlib.link_pairs(sets, [cam] * len(sets), pairs, run_ransac=False, packed=(rec[:30], off, cnt), **kw)
+    # with RANSAC the packed lists are the FINAL ones: only pairs that keep a relation keep their matches (:103-107)
+    rec[:] = 0
+    dev4 = hostlib.link_pairs(sets, [cam] * len(sets), pairs, packed=(rec, off, cnt), **kw)
+    for p in range(len(pairs)):
+        i1, i2, d = dev4.get(p)["matches"]
+        r = rec.reshape(-1, 3)[int(off[p]):int(off[p]) + int(cnt[p])]
+        assert len(r) == len(i1) and np.array_equal(r[:, 0], i1) and np.array_equal(r[:, 1], i2)
     # the flat form the ranks gather: counts and 12-byte records, pair after pair
     counts, rec = dev2.pack_matches()
     assert counts.sum() == len(rec) == dev2.stats["matches"]

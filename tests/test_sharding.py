@@ -130,12 +130,17 @@ def _worker(rank, world, port, ret):
         resident = set(shard.resident_images.tolist())
         assert all(a in resident and b in resident for a, b in shard.pairs)
         lists = [_expected(a, b) for a, b in shard.pairs]  # a stand-in matcher: variable-length, deterministic per pair
-        g = sharding.MatchGather(capacity_records=13 * len(pairs), dist=dist)
-        counts = np.array([len(x) for x in lists], np.int64)
-        if len(lists):
-            flat = np.concatenate(lists).reshape(-1)
-            g.region()[:len(flat)] = flat
-        out = g.gather(shard.pair_ids, counts, len(pairs))
+        shards = sharding.partition(pos, pairs, world)
+        g = sharding.MatchGather(capacity_records=13 * len(pairs), max_pairs=len(pairs), dist=dist)
+        rec, off, cnt = g.buffers()
+        # written the way the runner's tail workers write them: in some order of completion, not in pair order
+        cursor = 0
+        for k in np.random.default_rng(rank).permutation(len(lists)):
+            n = len(lists[k])
+            rec[3 * cursor:3 * (cursor + n)] = lists[k].reshape(-1)
+            off[k], cnt[k] = cursor, n
+            cursor += n
+        out = g.gather([s.pair_ids for s in shards], len(pairs))
         if rank == 0:
             ok = len(out) == len(pairs)
             for p, (a, b) in enumerate(pairs):
@@ -169,17 +174,24 @@ def test_gather_over_gloo(hostlib, world):
 
 
 def test_gather_without_process_group():
-    g = sharding.MatchGather(capacity_records=40)
+    g = sharding.MatchGather(capacity_records=40, max_pairs=3)
     lists = [_expected(2, 1), _expected(0, 5), _expected(1, 1)]
-    flat = np.concatenate(lists).reshape(-1)
-    g.region()[:len(flat)] = flat
-    out = g.gather([2, 0, 1], [len(x) for x in lists], 3)
+    rec, off, cnt = g.buffers()
+    cursor = 0
+    for k, w in enumerate(lists):
+        rec[3 * cursor:3 * (cursor + len(w))] = w.reshape(-1)
+        off[k], cnt[k] = cursor, len(w)
+        cursor += len(w)
+    out = g.gather([[2, 0, 1]], 3)
     for p, w in zip([2, 0, 1], lists):
         assert np.array_equal(out.pair(p)[0], w[:, 0]) and np.array_equal(out.pair(p)[2], w[:, 2] * (1.0 / 486))
+        assert np.array_equal(out.records(p), w)
+    assert out.total() == sum(len(w) for w in lists)
     with pytest.raises(AssertionError):
-        g.gather([0, 0], [1, 1], 2)
+        g.gather([[0, 0, 1]], 2)
     with pytest.raises(AssertionError):
-        g.gather([0], [1], 2)
+        g.gather([[0]], 2)
+    del out
     g.close()
 
 
