@@ -534,7 +534,7 @@ def measure_survey(torch, dist, rank, local_rank, world, workload, steps, warmup
     sets = [host.FeatureSet(d, xy, st) for d, xy, st in images]
     cams = [survey.camera8()] * len(sets)
     local_pairs = [(local_index[a], local_index[b]) for a, b in shard.pairs]
-    threads = max(1, cores // world - 1)  # one core per rank stays free for the submission threads
+    threads = max(1, cores // world)  # the submission threads sleep while the GPU works (blocking waits)
     most = max(len(sh.pairs) for sh in shards)
     gather = sharding.MatchGather(capacity_records=max(1, most) * 8192, max_pairs=most, dist=dist)
     packed = gather.buffers()  # this rank's region of the segment: the runner's tail workers write into it directly

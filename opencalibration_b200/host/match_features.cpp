@@ -98,8 +98,8 @@ std::vector<size_t> spatially_subsample_feature_indices(const std::vector<featur
 {
     // match_features.cpp:8-52: strongest first; keep a feature iff its nearest kept neighbour is farther than
     // `spacing_pixels` (squared-distance comparison, strict). Sequential greedy => host; the nearest-neighbour
-    // query is answered from a uniform grid of kept points (cell = spacing) instead of the reference's KD-tree,
-    // which yields the same minimum-distance decision.
+    // query is answered from a uniform grid of kept points instead of the reference's KD-tree, which yields the
+    // same minimum-distance decision.
     // count > features.size() is an out-of-bounds read in the reference (:17-23 index features[0 .. count)); here it
     // means "all of them"
     if (count == 0 || count > features.size())
@@ -138,32 +138,28 @@ std::vector<size_t> spatially_subsample_feature_indices(const std::vector<featur
     kept.reserve(count);
     const double limit = spacing_pixels * spacing_pixels;
     const bool gridded = spacing_pixels > 0 && std::isfinite(spacing_pixels);
-    // kept points bucketed by grid cell in a flat chained hash table. The cell is a little LARGER than the spacing: two
-    // points no farther apart than `spacing` then differ by less than 0.999 cells per axis, so even with the quotient
-    // x / cell rounded (|x / cell| < 1e9: error below 2.3e-7 cells) their cell indices differ by at most one, and the
-    // 3 x 3 neighbourhood holds every kept point that can reject the candidate
-    const double cell = spacing_pixels * 1.001;
+    // kept points bucketed by grid cell in a flat chained hash table. The cell is a little more than TWICE the
+    // spacing (spacing = 0.4975 cells): the interval [x - spacing, x + spacing] then touches the point's own cell and
+    // at most one neighbour per axis -- the lower one when the point lies in the lower half of its cell, else the upper
+    // one -- with 0.0025 cells to spare on either side, far more than the rounding of the quotient x / cell
+    // (computed as x * (1 / cell); |x / cell| < 1e9: error below 3e-7 cells). Four cells hold every kept point that can reject the candidate.
+    const double cell = spacing_pixels * 2.01, inv_cell = 1.0 / cell;
     size_t table_size = 64;
     while (table_size < 2 * count)
         table_size <<= 1;
     std::vector<int32_t> head(table_size, -1);
     struct Entry
     {
-        uint64_t key;
+        int64_t cx, cy;
         int32_t next;
         uint32_t pad;
         double x, y;
     };
     std::vector<Entry> entries;
     entries.reserve(count);
-    auto cell_key = [](int64_t cx, int64_t cy) {
-        return (static_cast<uint64_t>(static_cast<uint32_t>(cx)) << 32) | static_cast<uint32_t>(cy);
-    };
-    auto slot_of = [table_size](uint64_t key) {
-        key ^= key >> 33;
-        key *= 0xff51afd7ed558ccdull;
-        key ^= key >> 33;
-        return static_cast<size_t>(key) & (table_size - 1);
+    auto slot_of = [table_size](int64_t cx, int64_t cy) {
+        return static_cast<size_t>((static_cast<uint64_t>(cx) * 0x9E3779B97F4A7C15ull) ^
+                                   (static_cast<uint64_t>(cy) * 0xC2B2AE3D27D4EB4Full)) >> 20 & (table_size - 1);
     };
     auto too_close = [&](size_t idx, size_t other) {
         const double dx = features[idx].location.x() - features[other].location.x();
@@ -174,55 +170,54 @@ std::vector<size_t> spatially_subsample_feature_indices(const std::vector<featur
     for (size_t idx : by_strength)
     {
         const double x = features[idx].location.x(), y = features[idx].location.y();
-        const bool finite = gridded && std::isfinite(x) && std::isfinite(y) && std::abs(x / cell) < 1e9 &&
-                            std::abs(y / cell) < 1e9;
+        const double qx = x * inv_cell, qy = y * inv_cell; // within 3e-7 cells of x / cell for |x / cell| < 1e9
+        const bool finite = gridded && std::isfinite(x) && std::isfinite(y) && std::abs(qx) < 1e9 && std::abs(qy) < 1e9;
         bool keep = true;
         int64_t cx = 0, cy = 0;
         if (finite)
-            cx = (int64_t)std::floor(x / cell), cy = (int64_t)std::floor(y / cell);
-        if (!kept.empty())
         {
-            if (finite)
+            const double fx = std::floor(qx), fy = std::floor(qy);
+            cx = (int64_t)fx, cy = (int64_t)fy;
+            if (!kept.empty())
             {
-                for (int64_t gx = cx - 1; gx <= cx + 1 && keep; gx++)
-                    for (int64_t gy = cy - 1; gy <= cy + 1 && keep; gy++)
-                    {
-                        const uint64_t key = cell_key(gx, gy);
-                        for (int32_t e = head[slot_of(key)]; e >= 0; e = entries[e].next)
+                const int64_t nx = qx - fx < 0.5 ? cx - 1 : cx + 1, ny = qy - fy < 0.5 ? cy - 1 : cy + 1;
+                const int64_t gxs[2] = {cx, nx}, gys[2] = {cy, ny};
+                for (int a = 0; a < 2 && keep; a++)
+                    for (int b = 0; b < 2 && keep; b++)
+                        for (int32_t e = head[slot_of(gxs[a], gys[b])]; e >= 0; e = entries[e].next)
                         {
-                            if (entries[e].key != key)
+                            const Entry &en = entries[e];
+                            if (en.cx != gxs[a] || en.cy != gys[b])
                                 continue;
                             // the same subtraction, squares and sum as too_close(): (x - x') and (y - y') on the
                             // coordinates kept next to the key (no trip to the feature structs)
-                            const double dx = x - entries[e].x, dy = y - entries[e].y;
+                            const double dx = x - en.x, dy = y - en.y;
                             if (!(dx * dx + dy * dy > limit))
                             {
                                 keep = false;
                                 break;
                             }
                         }
-                    }
                 for (size_t other : unbucketed)
                     if (keep && too_close(idx, other))
                         keep = false;
             }
-            else
-            {
-                for (size_t other : kept)
-                    if (too_close(idx, other))
-                    {
-                        keep = false;
-                        break;
-                    }
-            }
+        }
+        else
+        {
+            for (size_t other : kept)
+                if (too_close(idx, other))
+                {
+                    keep = false;
+                    break;
+                }
         }
         if (!keep)
             continue;
         if (finite)
         {
-            const uint64_t key = cell_key(cx, cy);
-            const size_t sl = slot_of(key);
-            entries.push_back(Entry{key, head[sl], 0u, x, y});
+            const size_t sl = slot_of(cx, cy);
+            entries.push_back(Entry{cx, cy, head[sl], 0u, x, y});
             head[sl] = (int32_t)(entries.size() - 1);
         }
         else
