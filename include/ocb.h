@@ -116,6 +116,11 @@ extern "C"
      *   "k2_variant"       0 = by size, 1 = one hypothesis group per CTA, 2 = four groups per CTA in lock-step
      *   "k2_hg"            hypotheses per group (1..8); 0 = balance the SMs */
     int ocb_set_option(const char *key, int64_t value);
+    /* Per-thread: 1 = the calling thread's host-buffer calls SLEEP while they wait for the device (an event with
+     * blocking synchronisation) instead of spinning on the stream; 0 (default) = spin, the lowest latency for a lone
+     * caller. A caller that runs more host threads than it has cores (the batched LinkStage runner on a box with four
+     * cores per GPU) wants the core for its other threads; results never depend on it. */
+    int ocb_set_thread_blocking_sync(int on);
     int64_t ocb_get_option(const char *key);
 
     /* ---- K1: Hamming top-2 --------------------------------------------------------------------------

@@ -40,6 +40,7 @@ def lib():
         "ocb_init": (i32, [i32]),
         "ocb_set_device": (i32, [i32]),
         "ocb_current_device": (i32, []),
+        "ocb_set_thread_blocking_sync": (i32, [i32]),
         "ocb_shutdown": (None, []),
         "ocb_last_error": (C.c_char_p, []),
         "ocb_version": (C.c_char_p, []),

@@ -125,6 +125,20 @@ struct ThreadCtx
         ready_device = device;
         return 0;
     }
+    bool blocking_sync = false; // ocb_set_thread_blocking_sync
+    // waits for everything enqueued on the per-call stream: spinning (lowest latency) or, when the thread asked for it,
+    // sleeping on the blocking-sync event
+    int wait_stream()
+    {
+        if (!blocking_sync)
+        {
+            OCB_CUDA(cudaStreamSynchronize(stream));
+            return 0;
+        }
+        OCB_CUDA(cudaEventRecord(bulk_done, stream));
+        OCB_CUDA(cudaEventSynchronize(bulk_done));
+        return 0;
+    }
     // waits for everything enqueued on the bulk stream without spinning
     int wait_bulk()
     {
@@ -383,6 +397,12 @@ extern "C"
     int ocb_set_device(int device)
     {
         t_ctx.device = device;
+        return 0;
+    }
+
+    int ocb_set_thread_blocking_sync(int on)
+    {
+        t_ctx.blocking_sync = on != 0;
         return 0;
     }
 
@@ -1670,7 +1690,8 @@ extern "C"
         const size_t total = cv.off;
         if (total > cx.batch.cap)
         {
-            OCB_CUDA(cudaStreamSynchronize(cx.stream));
+            if ((rc = cx.wait_stream()))
+                return rc;
             if (cx.batch.p)
                 OCB_CUDA(cudaFree(cx.batch.p));
             cx.batch = Buf();
@@ -1712,7 +1733,8 @@ extern "C"
                 want_out |= sets[i].n && sets[i].corr_out;
             if (want_out)
                 OCB_CUDA(cudaMemcpyAsync(hb, b, total, cudaMemcpyDeviceToHost, cx.stream));
-            OCB_CUDA(cudaStreamSynchronize(cx.stream)); // the staging area is reused by the next call
+            if ((rc = cx.wait_stream()))
+                return rc; // the staging area is reused by the next call
             if (want_out)
                 for (size_t i = 0; i < count; i++)
                     if (sets[i].n && sets[i].corr_out)
@@ -1747,7 +1769,8 @@ extern "C"
                             cx.stream)))
             return rc;
         OCB_CUDA(cudaMemcpyAsync(hp + o_out, d + o_out, ob, cudaMemcpyDeviceToHost, cx.stream));
-        OCB_CUDA(cudaStreamSynchronize(cx.stream));
+        if ((rc = cx.wait_stream()))
+                return rc;
         memcpy(rays, hp + o_out, ob);
         return 0;
     }
@@ -1908,7 +1931,8 @@ extern "C"
         char *hout = hp + in_bytes;
         if (out_bytes)
             OCB_CUDA(cudaMemcpyAsync(hout, d_out, out_bytes, cudaMemcpyDeviceToHost, cx.stream));
-        OCB_CUDA(cudaStreamSynchronize(cx.stream));
+        if ((rc = cx.wait_stream()))
+                return rc;
         for (size_t i = 0; i < count; i++)
         {
             const ocb_score_request &r = req[i];

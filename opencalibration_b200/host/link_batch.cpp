@@ -523,6 +523,9 @@ std::vector<camera_relations> link_pairs(const std::vector<LinkImage> &images, c
     };
     auto consume = [&]() {
         ocb_set_device(device);
+        // a tail worker that waits for a RANSAC round gives its core to the other workers instead of spinning on it
+        // (the caller's own setting is restored when the call returns)
+        ocb_set_thread_blocking_sync(threads < omp_get_num_procs() || options.tail_workers > 1 ? 1 : 0);
         for (;;)
         {
             const size_t c = next_chunk.fetch_add(1);
@@ -723,6 +726,7 @@ std::vector<camera_relations> link_pairs(const std::vector<LinkImage> &images, c
         for (int w = 1; w < workers; w++)
             helpers.tasks.push_back(pool.run(2 + (size_t)w, consume));
         consume();
+        ocb_set_thread_blocking_sync(0);
         for (size_t k = first_consumer; k < helpers.tasks.size(); k++)
             helpers.tasks[k].wait(); // every chunk is consumed (or an error stopped the run); the guard releases the rest
     }

@@ -62,10 +62,22 @@ template <size_t K> struct HypothesisStream
             }
         if (has_quality)
         {
+            // ransac.cpp:83-90: indices sorted by quality, ascending, with std::sort. Sorted as compact (quality, index)
+            // records: the comparator's answers, hence the permutation (ties included), are the reference's, without a
+            // trip through the 56-byte correspondences for every comparison.
+            struct Ranked
+            {
+                double quality;
+                size_t idx;
+            };
+            std::vector<Ranked> ranked(matches.size());
+            for (size_t i = 0; i < ranked.size(); i++)
+                ranked[i] = Ranked{matches[i].quality, i};
+            std::sort(ranked.begin(), ranked.end(),
+                      [](const Ranked &a, const Ranked &b) { return a.quality < b.quality; });
             sorted_idx.resize(matches.size());
-            std::iota(sorted_idx.begin(), sorted_idx.end(), 0);
-            std::sort(sorted_idx.begin(), sorted_idx.end(),
-                      [this](size_t a, size_t b) { return matches[a].quality < matches[b].quality; });
+            for (size_t i = 0; i < ranked.size(); i++)
+                sorted_idx[i] = ranked[i].idx;
         }
         eval_order.resize(matches.size());
         std::iota(eval_order.begin(), eval_order.end(), 0);
@@ -707,8 +719,14 @@ void assembleInliers(const std::vector<feature_match> &matches, const std::vecto
 {
     // ransac.cpp:263-282
     inlier_list.reserve(std::count(inliers.begin(), inliers.end(), true));
+    constexpr size_t AHEAD = 12; // the two feature records of a match are random 96-byte reads: ask for them early
     for (size_t i = 0; i < matches.size(); i++)
     {
+        if (i + AHEAD < matches.size())
+        {
+            __builtin_prefetch(&source_features[matches[i + AHEAD].feature_index_1]);
+            __builtin_prefetch(&dest_features[matches[i + AHEAD].feature_index_2]);
+        }
         if (!inliers[i])
             continue;
         feature_match_denormalized d;
