@@ -253,7 +253,17 @@ std::vector<camera_relations> link_pairs(const std::vector<LinkImage> &images, c
     // the first pairs as soon as THEIR images are resident, and the first results reach the tail workers early. The
     // last ones shrink the same way: what is left to do after the GPU has finished is the tail of a small submission.
     // In between every submission is large enough to fill the SMs for tens of milliseconds.
-    const size_t per = std::max<size_t>(1, options.pairs_per_submission);
+    int tail_workers = options.tail_workers;
+    if (const char *e = std::getenv("OCB_LINK_TAIL_WORKERS")) // experiments
+        tail_workers = std::max(1, std::atoi(e));
+    const int workers = options.run_ransac ? std::max(1, std::min(tail_workers, threads)) : 1;
+    const int team = std::max(1, threads / workers);
+    // With RANSAC a submission's tail is a chain of lock-step rounds on ONE tail worker's team; when that team is a
+    // single thread (few cores per GPU) a large submission would keep its worker busy long after the GPU has moved on,
+    // so the submissions are kept small enough for the workers to share the load evenly.
+    size_t per = std::max<size_t>(1, options.pairs_per_submission);
+    if (options.run_ransac && team < 2)
+        per = std::min<size_t>(per, 64);
     std::vector<std::pair<size_t, size_t>> chunk; // [begin, end) into `pairs`
     {
         std::vector<size_t> ramp; // 32, 64, 128, ... below `per`
@@ -427,8 +437,6 @@ std::vector<camera_relations> link_pairs(const std::vector<LinkImage> &images, c
         }
         max_rows = std::max(max_rows, rows);
     }
-    const int workers = options.run_ransac ? std::max(1, std::min(options.tail_workers, threads)) : 1;
-    const int team = std::max(1, threads / workers);
     // two submissions in flight (two producers on alternate chunks, each with its own stream): while one submission
     // drains its last CTAs, returns its records and the next problem table is built, the other one fills the SMs
     const size_t n_producers = std::min<size_t>(2, std::max<size_t>(n_chunks, 1));

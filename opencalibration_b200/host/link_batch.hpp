@@ -36,7 +36,7 @@ struct LinkOptions
     size_t pairs_per_submission = 256;  // pairs per ocb_match_pairs call
     double coarse_spacing_pixels = 40.0; // link_stage.cpp:62
     bool run_ransac = true;             // false: stop after the match lists (relations.matches only)
-    int tail_workers = 3;               // chunks whose tails (incl. the lock-step RANSAC rounds) run concurrently
+    int tail_workers = 4;               // chunks whose tails (incl. the lock-step RANSAC rounds) run concurrently
     size_t first_submission = 32;       // pairs of the first submission; later ones double up to pairs_per_submission
     // true: ratio test + compaction (K5) and the pixel -> ray step (K6) run on the device, so that only the surviving
     // matches cross PCIe and the host keeps the reference's std::sort, the RANSAC control flow, decompose and
