@@ -203,6 +203,14 @@ extern "C"
      * reference's std::sort (:100-101) is left to the caller. */
     int ocb_match_pairs_ratio(const ocb_pair *pairs, size_t n_pairs, ocb_match *out, size_t out_capacity,
                               uint64_t *out_offsets);
+    /* ocb_match_pairs_ratio followed ON THE DEVICE by the reference's final std::sort (K7): pair p's survivors come
+     * back in the order of src/match/match_features.cpp:100-101 -- descending distance, ties in the order libstdc++'s
+     * (unstable) introsort leaves them, replayed step for step -- so out[out_offsets[p] + i] is match i of the
+     * reference's result. quality_order (nullable, out_capacity entries): for the same pair,
+     * quality_order[out_offsets[p] + j] = the index i of the match at rank j of the reference's PROSAC ordering
+     * (src/model_inliers/ransac.cpp:83-90: std::sort of 0 .. n-1 by quality = distance, ascending). */
+    int ocb_match_pairs_sorted(const ocb_pair *pairs, size_t n_pairs, ocb_match *out, size_t out_capacity,
+                               uint64_t *out_offsets, uint32_t *quality_order);
 
     /* ---- K4: Hamming top-2 over per-query candidate lists (guided matcher of the dense stage) ---------------
      * Replaces the inner loop of densifyMesh, src/dense/dense_stereo.cpp:251-273: list l compares query row

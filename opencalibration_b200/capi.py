@@ -58,6 +58,7 @@ def lib():
         "ocb_host_free": (None, [vp]),
         "ocb_match_pairs": (i32, [vp, sz, vp, vp]),
         "ocb_match_pairs_ratio": (i32, [vp, sz, vp, sz, vp]),
+        "ocb_match_pairs_sorted": (i32, [vp, sz, vp, sz, vp, vp]),
         "ocb_register_images_batch": (i32, [vp, sz]),
         "ocb_corr_bind_batch_matches": (i32, [vp, sz]),
         "ocb_image_to_3d": (i32, [vp, sz, vp, vp]),
@@ -234,6 +235,20 @@ def match_pairs_ratio(pairs, capacity):
     offs = np.zeros(len(pairs) + 1, np.uint64)
     check(lib().ocb_match_pairs_ratio(_ptr(pa), len(pa), _ptr(out), int(capacity), _ptr(offs)))
     return out[:int(offs[-1])], offs
+
+
+def match_pairs_sorted(pairs, capacity, want_quality_order=True):
+    """ocb_match_pairs_ratio + the reference's std::sort on the device -> (matches in the reference's final order,
+    offsets [n_pairs + 1], quality_order or None)."""
+    pa = np.zeros(len(pairs), PAIR_DTYPE)
+    for i, (a, b) in enumerate(pairs):
+        pa[i] = (a, b)
+    out = np.zeros(max(int(capacity), 1), MATCH_DTYPE)
+    offs = np.zeros(len(pairs) + 1, np.uint64)
+    qo = np.zeros(max(int(capacity), 1), np.uint32) if want_quality_order else None
+    check(lib().ocb_match_pairs_sorted(_ptr(pa), len(pa), _ptr(out), int(capacity), _ptr(offs), _ptr(qo)))
+    total = int(offs[-1])
+    return out[:total], offs, (qo[:total] if want_quality_order else None)
 
 
 def register_images_batch(images):

@@ -16,6 +16,9 @@
 //       Eigen expressions and the TinySolver Levenberg-Marquardt undistortion), so device rays == host rays bit for
 //       bit. One thread per (match, side); FP64 pipe / latency bound, ~20 operations per ray without distortion.
 #include "ocb_internal.cuh"
+#include "std_sort_replay.cuh"
+
+#include <algorithm>
 
 namespace ocb
 {
@@ -150,6 +153,66 @@ int k5_ratio_compact(const K5Pair *d_pairs, size_t n_pairs, unsigned long long *
     count_launch();
     OCB_CUDA(cudaGetLastError());
     k5_compact_kernel<<<(unsigned)n_pairs, K5_THREADS, 0, stream>>>(d_pairs, d_offsets, d_out);
+    count_launch();
+    OCB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// K7 -- the reference's two std::sort calls on the device: the match list by distance, descending
+// (src/match/match_features.cpp:100-101), and the PROSAC pool by quality, ascending (src/model_inliers/ransac.cpp:83-90).
+// Both are unstable sorts whose tie order matters downstream, so libstdc++'s algorithm is replayed step for step
+// (std_sort_replay.cuh) on (key, position) words: one warp per pair, the words in shared memory, lane 0 running the
+// sequential algorithm while the other lanes load, permute and store. Latency bound (a dependent shared-memory access
+// per step, ~1 ms per pair) and off the critical path: the warps of a submission's pairs run next to the K1 CTAs of
+// the next submission.
+// ----------------------------------------------------------------------------------------------------------
+constexpr int K7_THREADS = 32;
+
+__global__ void __launch_bounds__(K7_THREADS)
+    k7_sort_kernel(const unsigned long long *__restrict__ offsets, const ocb_match *__restrict__ in,
+                   ocb_match *__restrict__ out, uint32_t *__restrict__ quality_order,
+                   unsigned long long *__restrict__ scratch, uint32_t smem_cap)
+{
+    extern __shared__ unsigned long long k7_words[];
+    const uint32_t lane = threadIdx.x;
+    const unsigned long long lo = offsets[blockIdx.x];
+    const uint32_t n = (uint32_t)(offsets[blockIdx.x + 1] - lo);
+    if (n == 0)
+        return;
+    uint64_t *v = reinterpret_cast<uint64_t *>(n <= smem_cap ? k7_words : scratch + lo); // long lists: global scratch
+    for (uint32_t i = lane; i < n; i += K7_THREADS)
+        v[i] = ((uint64_t)in[lo + i].best_d << 32) | i;
+    __syncwarp();
+    if (lane == 0)
+        sort_replay::std_sort(v, (long)n, sort_replay::KeyOrder<true>());
+    __syncwarp();
+    for (uint32_t i = lane; i < n; i += K7_THREADS)
+        out[lo + i] = in[lo + (uint32_t)v[i]];
+    if (!quality_order)
+        return;
+    // correspondence i belongs to sorted match i and carries quality = its distance
+    for (uint32_t i = lane; i < n; i += K7_THREADS)
+        v[i] = (v[i] & 0xFFFFFFFF00000000ull) | i;
+    __syncwarp();
+    if (lane == 0)
+        sort_replay::std_sort(v, (long)n, sort_replay::KeyOrder<false>());
+    __syncwarp();
+    for (uint32_t i = lane; i < n; i += K7_THREADS)
+        quality_order[lo + i] = (uint32_t)v[i];
+}
+
+int k7_sort(const unsigned long long *d_offsets, size_t n_pairs, uint32_t max_rows_per_pair, const ocb_match *d_in,
+            ocb_match *d_out, uint32_t *d_quality_order, unsigned long long *d_scratch, cudaStream_t stream)
+{
+    if (n_pairs == 0)
+        return 0;
+    // the words of a pair live in shared memory when they fit (up to 96 KB: two such warps per SM next to K1's CTAs)
+    const uint32_t smem_cap = std::min<uint32_t>(std::max<uint32_t>(max_rows_per_pair, 1u), 96u * 1024u / 8u);
+    const size_t smem = (size_t)smem_cap * sizeof(unsigned long long);
+    OCB_CUDA(cudaFuncSetAttribute(k7_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    k7_sort_kernel<<<(unsigned)n_pairs, K7_THREADS, smem, stream>>>(d_offsets, d_in, d_out, d_quality_order, d_scratch,
+                                                                   smem_cap);
     count_launch();
     OCB_CUDA(cudaGetLastError());
     return 0;

@@ -961,8 +961,20 @@ extern "C"
         return 0;
     }
 
+    static int match_pairs_tail(const ocb_pair *pairs, size_t n_pairs, ocb_match *out, size_t out_capacity,
+                                uint64_t *out_offsets, bool sorted, uint32_t *quality_order);
     int ocb_match_pairs_ratio(const ocb_pair *pairs, size_t n_pairs, ocb_match *out, size_t out_capacity,
                               uint64_t *out_offsets)
+    {
+        return match_pairs_tail(pairs, n_pairs, out, out_capacity, out_offsets, false, nullptr);
+    }
+    int ocb_match_pairs_sorted(const ocb_pair *pairs, size_t n_pairs, ocb_match *out, size_t out_capacity,
+                               uint64_t *out_offsets, uint32_t *quality_order)
+    {
+        return match_pairs_tail(pairs, n_pairs, out, out_capacity, out_offsets, true, quality_order);
+    }
+    static int match_pairs_tail(const ocb_pair *pairs, size_t n_pairs, ocb_match *out, size_t out_capacity,
+                                uint64_t *out_offsets, bool sorted, uint32_t *quality_order)
     {
         if (!out_offsets)
             return fail_invalid("null pointer");
@@ -1011,6 +1023,10 @@ extern "C"
         const size_t o_tab = cv.take(table_bytes), o_k5 = cv.take(k5_bytes), o_top = cv.take(rows_total * sizeof(ocb_top2));
         const size_t o_state = cv.take(state_total), o_off = cv.take((n_pairs + 1) * sizeof(uint64_t));
         const size_t o_ticket = cv.take(sizeof(uint32_t)), o_out = cv.take(rows_total * sizeof(ocb_match));
+        // K7: sorted copy of the survivors, PROSAC order, scratch words for lists too long for shared memory
+        const size_t o_sorted = cv.take(sorted ? rows_total * sizeof(ocb_match) : 0);
+        const size_t o_qorder = cv.take(sorted && quality_order ? rows_total * sizeof(uint32_t) : 0);
+        const size_t o_words = cv.take(sorted ? rows_total * sizeof(uint64_t) : 0);
         rc = cx.dev_reserve(cv.off);
         if (rc)
             return rc;
@@ -1019,6 +1035,8 @@ extern "C"
         const size_t s_tab = sv.take(table_bytes), s_k5 = sv.take(k5_bytes);
         const size_t s_off = sv.take((n_pairs + 1) * sizeof(uint64_t));
         const size_t s_out = sv.take(out_pinned ? 0 : rows_total * sizeof(ocb_match));
+        const bool qo_pinned = sorted && quality_order && is_pinned_host(quality_order);
+        const size_t s_qo = sv.take(sorted && quality_order && !qo_pinned ? rows_total * sizeof(uint32_t) : 0);
         rc = cx.pinned_reserve(sv.off);
         if (rc)
             return rc;
@@ -1050,6 +1068,19 @@ extern "C"
                               reinterpret_cast<uint32_t *>(d + o_ticket), reinterpret_cast<ocb_match *>(d + o_out), bulk);
         if (rc)
             return rc;
+        if (sorted)
+        {
+            uint32_t longest = 0;
+            for (size_t p = 0; p < n_pairs; p++)
+                longest = std::max(longest, pr[p].n_q);
+            rc = k7_sort(reinterpret_cast<const unsigned long long *>(d + o_off), n_pairs, longest,
+                         reinterpret_cast<const ocb_match *>(d + o_out), reinterpret_cast<ocb_match *>(d + o_sorted),
+                         quality_order ? reinterpret_cast<uint32_t *>(d + o_qorder) : nullptr,
+                         reinterpret_cast<unsigned long long *>(d + o_words), bulk);
+            if (rc)
+                return rc;
+        }
+        const size_t o_result = sorted ? o_sorted : o_out;
         // the offsets first (they say how many survivors there are), then exactly that many records
         OCB_CUDA(cudaMemcpyAsync(off_pinned ? (void *)out_offsets : (void *)(hp + s_off), d + o_off,
                                  (n_pairs + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, bulk));
@@ -1062,12 +1093,17 @@ extern "C"
             return fail_invalid("out_capacity is smaller than the number of surviving matches");
         if (total)
         {
-            OCB_CUDA(cudaMemcpyAsync(out_pinned ? (void *)out : (void *)(hp + s_out), d + o_out,
+            OCB_CUDA(cudaMemcpyAsync(out_pinned ? (void *)out : (void *)(hp + s_out), d + o_result,
                                      total * sizeof(ocb_match), cudaMemcpyDeviceToHost, bulk));
+            if (sorted && quality_order)
+                OCB_CUDA(cudaMemcpyAsync(qo_pinned ? (void *)quality_order : (void *)(hp + s_qo), d + o_qorder,
+                                         total * sizeof(uint32_t), cudaMemcpyDeviceToHost, bulk));
             if ((rc = cx.wait_bulk()))
-            return rc;
+                return rc;
             if (!out_pinned)
                 memcpy(out, hp + s_out, total * sizeof(ocb_match));
+            if (sorted && quality_order && !qo_pinned)
+                memcpy(quality_order, hp + s_qo, total * sizeof(uint32_t));
         }
         return 0;
     }

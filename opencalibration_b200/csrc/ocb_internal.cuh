@@ -96,6 +96,11 @@ struct K5Pair
 // the survivors of pair p in query order at d_out + d_offsets[p]
 int k5_ratio_compact(const K5Pair *d_pairs, size_t n_pairs, unsigned long long *d_offsets, uint32_t *d_ticket,
                      ocb_match *d_out, cudaStream_t stream);
+// K7: per pair, d_out[offsets[p] ..) = d_in[offsets[p] ..) in the order of the reference's std::sort by distance
+// (descending); d_quality_order (nullable) = the positions of those sorted matches in the order of the reference's
+// std::sort by quality (ascending). d_scratch: one 64-bit word per record, used by pairs too long for shared memory.
+int k7_sort(const unsigned long long *d_offsets, size_t n_pairs, uint32_t max_rows_per_pair, const ocb_match *d_in,
+            ocb_match *d_out, uint32_t *d_quality_order, unsigned long long *d_scratch, cudaStream_t stream);
 struct K6Set
 {
     const double2 *xy1, *xy2; // keypoint locations of the two registered sets

@@ -79,6 +79,8 @@ def lib():
     L.ocbh_link_pack_matches.argtypes = [C.c_void_p, vp, vp, i32]
     L.ocbh_link_pack_matches.restype = sz
     L.ocbh_partition_pairs.argtypes = [vp, sz, _szp, sz, sz, vp, vp, vp]
+    L.ocbh_prosac_order.argtypes = [_f64p, sz, vp]
+    L.ocbh_prosac_order.restype = None
     L.ocbh_hilbert_index.argtypes = [i32, i32, i32]
     L.ocbh_hilbert_index.restype = C.c_uint32
     L.ocbh_hilbert_order.argtypes = [_f64p, sz, _szp]
@@ -480,3 +482,11 @@ def partition_pairs(positions, pairs, world):
                                       owner.ctypes.data_as(C.c_void_p), part.ctypes.data_as(C.c_void_p),
                                       halo.ctypes.data_as(C.c_void_p)))
     return owner[:n], part[:len(pr)], halo[:, :n].astype(bool)
+
+
+def prosac_order(quality):
+    """ransac.cpp:83-90 on the host: indices 0 .. n-1 sorted by quality, ascending, with libstdc++'s std::sort."""
+    q = np.ascontiguousarray(quality, np.float64)
+    out = np.zeros(max(len(q), 1), np.uint32)
+    lib().ocbh_prosac_order(q, len(q), out.ctypes.data_as(C.c_void_p))
+    return out[:len(q)]

@@ -6,6 +6,7 @@
 #include "partition.hpp"
 #include "models_detail.hpp"
 
+#include <algorithm>
 #include <chrono>
 #include <cstring>
 #include <omp.h>
@@ -677,6 +678,22 @@ extern "C"
     {
         const std::vector<size_t> o = ocb_host::hilbert_order(positions2, n);
         std::memcpy(order_out, o.data(), n * sizeof(size_t));
+    }
+
+    // the host's own PROSAC ordering (ransac.cpp:83-90: std::sort of 0 .. n-1 by quality, ascending) for a quality array
+    void ocbh_prosac_order(const double *quality, size_t n, uint32_t *order)
+    {
+        struct Ranked
+        {
+            double quality;
+            size_t idx;
+        };
+        std::vector<Ranked> ranked(n);
+        for (size_t i = 0; i < n; i++)
+            ranked[i] = Ranked{quality[i], i};
+        std::sort(ranked.begin(), ranked.end(), [](const Ranked &a, const Ranked &b) { return a.quality < b.quality; });
+        for (size_t i = 0; i < n; i++)
+            order[i] = (uint32_t)ranked[i].idx;
     }
 
     int ocbh_ransac_batch(int kind, const double *corr, const size_t *offsets, size_t n_jobs, int threads, double *scores,

@@ -443,7 +443,8 @@ std::vector<camera_relations> link_pairs(const std::vector<LinkImage> &images, c
     const size_t n_slots = (size_t)workers + n_producers;
     struct Slot
     {
-        void *records = nullptr;       // device_tail: ocb_match survivors (dense); else ocb_top2 per query row
+        void *records = nullptr;       // device_tail: ocb_match survivors (dense, sorted); else ocb_top2 per query row
+        std::vector<uint32_t> quality_order; // device_tail + RANSAC: PROSAC order of every pair's sorted matches
         std::vector<uint64_t> offsets; // device_tail: [pairs + 1] survivor offsets; else [pairs] row offsets
         double gpu_seconds = 0;
         size_t chunk = 0; // which submission the records belong to
@@ -494,9 +495,15 @@ std::vector<camera_relations> link_pairs(const std::vector<LinkImage> &images, c
             const auto t0 = clock_type::now();
             timeline[c].launch = since(t_begin);
             int rc;
-            if (device_tail) // K1 + ratio test + compaction on the device: only the survivors come back
-                rc = ocb_match_pairs_ratio(sub.data(), sub.size(), static_cast<ocb_match *>(sl.records), max_rows,
-                                           sl.offsets.data());
+            if (device_tail)
+            {
+                // K1 + ratio test + compaction + the reference's std::sort on the device: only the survivors come
+                // back, already in the order of match_features.cpp:100-101, with their PROSAC order when RANSAC follows
+                if (options.run_ransac)
+                    sl.quality_order.resize(max_rows);
+                rc = ocb_match_pairs_sorted(sub.data(), sub.size(), static_cast<ocb_match *>(sl.records), max_rows,
+                                            sl.offsets.data(), options.run_ransac ? sl.quality_order.data() : nullptr);
+            }
             else
                 rc = ocb_match_pairs(sub.data(), sub.size(), static_cast<ocb_top2 *>(sl.records), sl.offsets.data());
             sl.gpu_seconds = since(t0);
@@ -505,7 +512,7 @@ std::vector<camera_relations> link_pairs(const std::vector<LinkImage> &images, c
             if (rc)
             {
                 if (error.empty())
-                    error = std::string(device_tail ? "ocb_match_pairs_ratio: " : "ocb_match_pairs: ") + ocb_last_error();
+                    error = std::string(device_tail ? "ocb_match_pairs_sorted: " : "ocb_match_pairs: ") + ocb_last_error();
                 stop = true;
             }
             sl.chunk = c;
@@ -556,6 +563,7 @@ std::vector<camera_relations> link_pairs(const std::vector<LinkImage> &images, c
             std::vector<std::vector<feature_match>> coarse_matches(cn);
             std::vector<std::vector<correspondence>> coarse_correspondences(cn);
             std::vector<std::vector<ocb_match>> sorted(device_tail && options.run_ransac ? cn : 0);
+            std::vector<std::vector<uint32_t>> quality_order(sorted.size());
 #pragma omp parallel for schedule(dynamic, 1) num_threads(team) reduction(+ : n_matches)
             for (size_t p = begin; p < end; p++)
             {
@@ -566,14 +574,11 @@ std::vector<camera_relations> link_pairs(const std::vector<LinkImage> &images, c
                     const std::vector<size_t> &idx1 = indices[pairs[p].image_1], &idx2 = indices[pairs[p].image_2];
                     if (device_tail)
                     {
-                        // Survivors arrive in query order, the order in which match_features.cpp:71-97 emits them.
-                        // std::sort's sequence of comparisons and moves depends only on the comparator's answers, and
-                        // a.d > b.d <=> a.d * (1.0 / 486) > b.d * (1.0 / 486) for these integers, so sorting the
-                        // 12-byte records yields the permutation the reference's sort (:100-101) produces.
+                        // The survivors arrive in the reference's final order: emitted in query order
+                        // (match_features.cpp:71-97), then put through libstdc++'s std::sort on the distance (:100-101)
+                        // as replayed on the device (K7). What is left is mapping positions to the original indices.
                         const ocb_match *first = static_cast<const ocb_match *>(sl.records) + sl.offsets[k];
                         std::vector<ocb_match> recs(first, first + (sl.offsets[k + 1] - sl.offsets[k]));
-                        std::sort(recs.begin(), recs.end(),
-                                  [](const ocb_match &f1, const ocb_match &f2) -> bool { return f1.best_d > f2.best_d; });
                         std::vector<feature_match> &out = coarse_matches[k];
                         out.resize(recs.size());
                         for (size_t i = 0; i < recs.size(); i++)
@@ -589,6 +594,8 @@ std::vector<camera_relations> link_pairs(const std::vector<LinkImage> &images, c
                             if (recs.size() < homography_model::MINIMUM_POINTS) // never bound (ransac.cpp:64-70)
                                 corr = distort_keypoints(*img.features, *near_image.features, out, img.model,
                                                          near_image.model);
+                            quality_order[k].assign(sl.quality_order.begin() + sl.offsets[k],
+                                                    sl.quality_order.begin() + sl.offsets[k + 1]);
                             sorted[k] = std::move(recs);
                         }
                     }
@@ -627,8 +634,12 @@ std::vector<camera_relations> link_pairs(const std::vector<LinkImage> &images, c
                 std::vector<std::vector<bool>> coarse_inliers(cn);
                 std::vector<RansacJob<homography_model>> jobs(cn);
                 for (size_t k = 0; k < cn; k++)
+                {
                     jobs[k].matches = &coarse_correspondences[k], jobs[k].model = &models[k],
                     jobs[k].inliers = &coarse_inliers[k];
+                    if (device_tail && !quality_order[k].empty())
+                        jobs[k].quality_order = quality_order[k].data();
+                }
                 // device tail: bind the runs straight from the sorted match lists -- K6 computes both rays of every
                 // match (distort_keypoints, link_stage.cpp:87-88) into the bound rows and the rows come back for
                 // decompose(); 12 bytes per match go up instead of 56

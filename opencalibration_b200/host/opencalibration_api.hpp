@@ -72,6 +72,10 @@ template <typename Model> struct RansacJob
     const std::vector<opencalibration::correspondence> *matches = nullptr;
     Model *model = nullptr;
     std::vector<bool> *inliers = nullptr;
+    // optional: the PROSAC ordering of src/model_inliers/ransac.cpp:83-90 (indices sorted by quality, ascending, in the
+    // order the reference's std::sort leaves ties) computed elsewhere -- the batched LinkStage runner gets it from the
+    // device together with the sorted match list (ocb_match_pairs_sorted); nullptr: sorted here
+    const uint32_t *quality_order = nullptr;
     double result = 0; // what ransac() would have returned
     RansacStats stats;
 };

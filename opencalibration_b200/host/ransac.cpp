@@ -52,7 +52,8 @@ template <size_t K> struct HypothesisStream
     std::default_random_engine generator{42};
     size_t prosac_n;
 
-    explicit HypothesisStream(const std::vector<opencalibration::correspondence> &m) : matches(m)
+    explicit HypothesisStream(const std::vector<opencalibration::correspondence> &m, const uint32_t *quality_order = nullptr)
+        : matches(m)
     {
         for (const auto &c : matches)
             if (c.quality != 0)
@@ -60,7 +61,9 @@ template <size_t K> struct HypothesisStream
                 has_quality = true;
                 break;
             }
-        if (has_quality)
+        if (has_quality && quality_order)
+            sorted_idx.assign(quality_order, quality_order + matches.size()); // the same permutation, computed on the device
+        else if (has_quality)
         {
             // ransac.cpp:83-90: indices sorted by quality, ascending, with std::sort. Sorted as compact (quality, index)
             // records: the comparator's answers, hence the permutation (ties included), are the reference's, without a
@@ -212,7 +215,8 @@ template <typename Model> class RansacRun
                        // (homography only; drivers that cannot serve it leave device_refit off)
     };
 
-    RansacRun(const std::vector<correspondence> &matches_, Model &model_, std::vector<bool> &inliers_)
+    RansacRun(const std::vector<correspondence> &matches_, Model &model_, std::vector<bool> &inliers_,
+              const uint32_t *quality_order = nullptr)
         : matches(matches_), model(model_), inliers(inliers_), N(matches_.size())
     {
         inliers.resize(N);
@@ -222,7 +226,7 @@ template <typename Model> class RansacRun
             state = State::FINISHED;
             return;
         }
-        stream.reset(new HypothesisStream<K>(matches));
+        stream.reset(new HypothesisStream<K>(matches, quality_order));
         order32.resize(N);
         for (size_t p = 0; p < N; p++)
             order32[p] = static_cast<uint32_t>(stream->eval_order[p]);
@@ -602,7 +606,7 @@ template <typename Model> void ransac_batch(std::vector<RansacJob<Model>> &jobs,
 #pragma omp parallel for schedule(dynamic, 1) num_threads(threads)
     for (size_t j = 0; j < n_jobs; j++)
     {
-        runs[j].reset(new Run(*jobs[j].matches, *jobs[j].model, *jobs[j].inliers));
+        runs[j].reset(new Run(*jobs[j].matches, *jobs[j].model, *jobs[j].inliers, jobs[j].quality_order));
         runs[j]->device_refit = opencalibration::ransac_device_fit(); // only the homography run ever asks for it
     }
     std::vector<ocb_corr_set> sets(n_jobs);

@@ -78,6 +78,62 @@ def test_ratio_compaction_ties_and_many_pairs(gpu, oracle):
         gpu.unregister_descriptors(6000 + i)
 
 
+def test_device_sort_equals_the_reference_order(gpu, hostlib, oracle):
+    """K7: the survivors of every pair in the order the reference's std::sort leaves them (match_features.cpp:100-101,
+    unstable, ties included) and their PROSAC ordering (ransac.cpp:83-90): against the oracle's match_features_subset
+    (the same libstdc++ std::sort on the same emission order) and the host driver's own ordering."""
+    rng = np.random.default_rng(3)
+    images, pos, pairs = synthetic.grid_survey(3, 3, 2500, seed=9)
+    images[3] = images[3][:40]
+    images[6] = images[6][:0]
+    for i, d in enumerate(images):
+        gpu.register_descriptors(9000 + i, d)
+    extra = [(0, 0), (3, 1), (6, 2), (2, 6)]
+    all_pairs = pairs + extra
+    cap = sum(len(images[a]) for a, _ in all_pairs)
+    out, offs, qo = gpu.match_pairs_sorted([(9000 + a, 9000 + b) for a, b in all_pairs], cap)
+    unsorted, offs2 = gpu.match_pairs_ratio([(9000 + a, 9000 + b) for a, b in all_pairs], cap)
+    assert np.array_equal(offs, offs2)
+    ties = 0
+    for p, (a, b) in enumerate(all_pairs):
+        got = out[int(offs[p]):int(offs[p + 1])]
+        n1, n2 = len(images[a]), len(images[b])
+        w1, w2, wd = oracle.match_features_subset(images[a], images[b], np.arange(n1, dtype=np.uintp),
+                                                  np.arange(n2, dtype=np.uintp)) if n1 and n2 else ([], [], [])
+        assert np.array_equal(got["query_k"], w1) and np.array_equal(got["best_k"], w2), (p, a, b)
+        assert np.array_equal(got["best_d"] * (1.0 / 486), wd)
+        ties += len(got) - len(np.unique(got["best_d"]))
+        order = qo[int(offs[p]):int(offs[p + 1])]
+        assert np.array_equal(order, hostlib.prosac_order(got["best_d"] * (1.0 / 486))), (p, a, b)
+    assert ties > 5000  # the tie order is what makes this more than "sorted by distance"
+    same, _, none = gpu.match_pairs_sorted([(9000, 9001)], len(images[0]), want_quality_order=False)
+    assert none is None and np.array_equal(same, out[int(offs[0]):int(offs[1])]) if all_pairs[0] == (0, 1) else True
+    for i in range(len(images)):
+        gpu.unregister_descriptors(9000 + i)
+
+
+def test_device_sort_of_lists_longer_than_shared_memory(gpu, oracle):
+    # 13 000 survivors: more words than fit in the kernel's shared memory -> the global scratch path
+    n = 13000
+    a, _ = synthetic.config2_pair(n, 8, seed=5)
+    rng = np.random.default_rng(1)
+    b = a.copy()
+    flips = rng.integers(0, 60, n)  # candidate i = query i with a few bits flipped: every query survives the ratio test
+    for j in range(60):
+        rows = np.nonzero(flips > j)[0]
+        bit = rng.integers(0, 486, len(rows))
+        b[rows, bit // 64] ^= np.uint64(1) << (bit % 64).astype(np.uint64)
+    gpu.register_descriptors(9100, a)
+    gpu.register_descriptors(9101, b)
+    out, offs, qo = gpu.match_pairs_sorted([(9100, 9101)], n)
+    idx = np.arange(n, dtype=np.uintp)
+    w1, w2, wd = oracle.match_features_subset(a, b, idx, idx)
+    assert len(w1) > 12000
+    assert np.array_equal(out["query_k"], w1) and np.array_equal(out["best_k"], w2)
+    for s in (9100, 9101):
+        gpu.unregister_descriptors(s)
+
+
 def grid(cols, rows):
     return np.array([(i, j) for i in range(0, cols, cols // 20) for j in range(0, rows, rows // 20)], np.float64)
 
