@@ -705,6 +705,8 @@ def run_survey(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     capi.init(local_rank)
+    if os.environ.get("OCB_K1_ITEMS"):  # experiments: work items per SM of the K1 planner
+        capi.set_option("k1_items_per_sm", int(os.environ["OCB_K1_ITEMS"]))
     b = measure_survey(torch, dist, rank, local_rank, world, args.workload, args.steps if args.steps < 50 else 1,
                        args.warmup, args.with_ransac, args.spacing, args.pairs_per_submission, args.survey_scale,
                        verify=not args.no_verify, drop_in=not args.no_secondary)

@@ -248,6 +248,9 @@ std::vector<camera_relations> link_pairs(const std::vector<LinkImage> &images, c
     // the helper threads below work on the device the CALLER selected (ocb_set_device), not on the process default
     const int device = ocb_current_device();
     const bool device_tail = options.device_tail;
+    bool device_sort = device_tail && options.device_sort;
+    if (const char *e = std::getenv("OCB_LINK_DEVICE_SORT")) // experiments / tests
+        device_sort = device_tail && e[0] == '1';
 
     // ---- submissions. The first ones are small and grow geometrically up to pairs_per_submission: the GPU starts on
     // the first pairs as soon as THEIR images are resident, and the first results reach the tail workers early. The
@@ -439,7 +442,12 @@ std::vector<camera_relations> link_pairs(const std::vector<LinkImage> &images, c
     }
     // two submissions in flight (two producers on alternate chunks, each with its own stream): while one submission
     // drains its last CTAs, returns its records and the next problem table is built, the other one fills the SMs
-    const size_t n_producers = std::min<size_t>(2, std::max<size_t>(n_chunks, 1));
+    // (three with the device sort: a submission then ends with the sequential sort replay K7, about three milliseconds
+    // during which its stream has little for the SMs; the submission threads sleep while they wait)
+    size_t want_producers = device_sort ? 3 : 2;
+    if (const char *e = std::getenv("OCB_LINK_PRODUCERS")) // experiments
+        want_producers = (size_t)std::max(1, std::atoi(e));
+    const size_t n_producers = std::min<size_t>(want_producers, std::max<size_t>(n_chunks, 1));
     const size_t n_slots = (size_t)workers + n_producers;
     struct Slot
     {
@@ -497,12 +505,18 @@ std::vector<camera_relations> link_pairs(const std::vector<LinkImage> &images, c
             int rc;
             if (device_tail)
             {
-                // K1 + ratio test + compaction + the reference's std::sort on the device: only the survivors come
-                // back, already in the order of match_features.cpp:100-101, with their PROSAC order when RANSAC follows
-                if (options.run_ransac)
-                    sl.quality_order.resize(max_rows);
-                rc = ocb_match_pairs_sorted(sub.data(), sub.size(), static_cast<ocb_match *>(sl.records), max_rows,
-                                            sl.offsets.data(), options.run_ransac ? sl.quality_order.data() : nullptr);
+                // K1 + ratio test + compaction on the device: only the survivors come back; with device_sort already in
+                // the order of match_features.cpp:100-101 and with their PROSAC order when RANSAC follows
+                if (device_sort)
+                {
+                    if (options.run_ransac)
+                        sl.quality_order.resize(max_rows);
+                    rc = ocb_match_pairs_sorted(sub.data(), sub.size(), static_cast<ocb_match *>(sl.records), max_rows,
+                                                sl.offsets.data(), options.run_ransac ? sl.quality_order.data() : nullptr);
+                }
+                else
+                    rc = ocb_match_pairs_ratio(sub.data(), sub.size(), static_cast<ocb_match *>(sl.records), max_rows,
+                                               sl.offsets.data());
             }
             else
                 rc = ocb_match_pairs(sub.data(), sub.size(), static_cast<ocb_top2 *>(sl.records), sl.offsets.data());
@@ -574,11 +588,16 @@ std::vector<camera_relations> link_pairs(const std::vector<LinkImage> &images, c
                     const std::vector<size_t> &idx1 = indices[pairs[p].image_1], &idx2 = indices[pairs[p].image_2];
                     if (device_tail)
                     {
-                        // The survivors arrive in the reference's final order: emitted in query order
-                        // (match_features.cpp:71-97), then put through libstdc++'s std::sort on the distance (:100-101)
-                        // as replayed on the device (K7). What is left is mapping positions to the original indices.
+                        // Survivors are emitted in query order (match_features.cpp:71-97) and then put through
+                        // libstdc++'s std::sort on the distance (:100-101) -- here, or already on the device (K7).
+                        // std::sort's sequence of comparisons and moves depends only on the comparator's answers, and
+                        // a.d > b.d <=> a.d * (1.0 / 486) > b.d * (1.0 / 486) for these integers, so sorting the
+                        // 12-byte records yields the permutation the reference's sort produces on its 24-byte ones.
                         const ocb_match *first = static_cast<const ocb_match *>(sl.records) + sl.offsets[k];
                         std::vector<ocb_match> recs(first, first + (sl.offsets[k + 1] - sl.offsets[k]));
+                        if (!device_sort)
+                            std::sort(recs.begin(), recs.end(),
+                                      [](const ocb_match &f1, const ocb_match &f2) -> bool { return f1.best_d > f2.best_d; });
                         std::vector<feature_match> &out = coarse_matches[k];
                         out.resize(recs.size());
                         for (size_t i = 0; i < recs.size(); i++)
@@ -594,8 +613,9 @@ std::vector<camera_relations> link_pairs(const std::vector<LinkImage> &images, c
                             if (recs.size() < homography_model::MINIMUM_POINTS) // never bound (ransac.cpp:64-70)
                                 corr = distort_keypoints(*img.features, *near_image.features, out, img.model,
                                                          near_image.model);
-                            quality_order[k].assign(sl.quality_order.begin() + sl.offsets[k],
-                                                    sl.quality_order.begin() + sl.offsets[k + 1]);
+                            if (device_sort)
+                                quality_order[k].assign(sl.quality_order.begin() + sl.offsets[k],
+                                                        sl.quality_order.begin() + sl.offsets[k + 1]);
                             sorted[k] = std::move(recs);
                         }
                     }
@@ -743,7 +763,7 @@ std::vector<camera_relations> link_pairs(const std::vector<LinkImage> &images, c
             helpers.tasks.push_back(pool.run(1 + k, [&produce, k]() { produce(k); }));
         const size_t first_consumer = helpers.tasks.size();
         for (int w = 1; w < workers; w++)
-            helpers.tasks.push_back(pool.run(2 + (size_t)w, consume));
+            helpers.tasks.push_back(pool.run(8 + (size_t)w, consume)); // roles 1..8: submission threads
         consume();
         ocb_set_thread_blocking_sync(0);
         for (size_t k = first_consumer; k < helpers.tasks.size(); k++)

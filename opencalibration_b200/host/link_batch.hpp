@@ -43,6 +43,12 @@ struct LinkOptions
     // assembleInliers. false: the K1 records of every query come back and the host does the ratio test and the rays
     // (the round-1 path, kept for A/B tests: both give identical relations).
     bool device_tail = true;
+    // With the device tail: also run the reference's two std::sort calls on the device (K7, libstdc++'s introsort
+    // replayed step for step: match list by distance, PROSAC pool by quality) instead of on the tail workers. Exact
+    // either way (tests/test_sort_replay.py, tests/test_gpu_link_tail.py). Off by default: the replay is sequential per
+    // pair (~3 ms per submission on one warp per pair) and measured SLOWER end to end than sorting on the host, on one
+    // GPU (-3 .. -9 % pairs/s) and on eight.
+    bool device_sort = false;
     // Optional flat copy of every pair's final match list, written by the tail workers as the submissions finish (what
     // a rank contributes to the host gather of the match lists, link_stage.cpp:119-131): 12-byte records
     // {feature_index_1, feature_index_2, integer Hamming distance} (distance = d * (1.0 / 486) exactly) into

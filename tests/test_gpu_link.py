@@ -166,6 +166,15 @@ def test_device_tail_equals_host_tail(gpu, hostlib, distorted):
         kept += len(a["matches"][0]) > 0
     assert kept >= 40
     assert dev.stats["matches"] == ref.stats["matches"] and dev.stats["ransac_inliers"] == ref.stats["ransac_inliers"]
+    # ... and with the two std::sort calls replayed on the device as well (K7: match order and PROSAC order)
+    import os
+    os.environ["OCB_LINK_DEVICE_SORT"] = "1"
+    try:
+        srt = hostlib.link_pairs(sets, [cam] * len(sets), pairs, device_tail=True, **kw)
+    finally:
+        del os.environ["OCB_LINK_DEVICE_SORT"]
+    for p in range(len(pairs)):
+        assert _relations_equal(srt.get(p), ref.get(p)), (p, pairs[p])
     # matches only
     dev2 = hostlib.link_pairs(sets, [cam] * len(sets), pairs, device_tail=True, run_ransac=False, **kw)
     ref2 = hostlib.link_pairs(sets, [cam] * len(sets), pairs, device_tail=False, run_ransac=False, **kw)
