@@ -494,6 +494,24 @@ def run_ours(args):
     if survey_block:
         secondary = dict(secondary or {})
         secondary["c4_survey"] = survey_block
+    if world == 1 and not args.no_secondary:
+        # LAST (a failed probe leaves the CUDA context unusable): the tensor-core formulation of the same search
+        # (include/ocb_probe.h, csrc/tc_probe.cu) on the headline pair -- evidence for / against north_star's choice of
+        # the integer pipes, not a product path
+        secondary = dict(secondary or {})
+        try:
+            got, ms_expand, ms_mma, ranges = capi.probe_tensor_top2(a, b, reps=20)
+            same = bool(np.array_equal(got["best_k"], bk) and np.array_equal(got["best_d"], bd) and
+                        np.array_equal(got["second_d"], sd))
+            secondary["tensor_core_probe"] = {
+                "what": "top-2 of the headline pair as an exact s8 contraction: tcgen05.mma.kind::i8 (+-1 operands, "
+                        "dot = 512 - 2 x hamming), TMEM accumulators, top-2 epilogue from tcgen05.ld; no cross-check",
+                "bit_exact_vs_oracle": same, "ms_mma_top2": ms_mma, "ms_expand_bits_to_s8": ms_expand,
+                "candidate_ranges": ranges, "Gcmp_per_s_mma_only": cmp_per_step / (ms_mma * 1e-3) / 1e9,
+                "Gcmp_per_s_with_expansion": cmp_per_step / ((ms_mma + ms_expand) * 1e-3) / 1e9,
+                "k1_ms_same_pair_with_cross_check": ms_per_step}
+        except Exception as e:  # noqa: BLE001
+            secondary["tensor_core_probe"] = {"error": str(e)[:300]}
     if secondary:
         line["secondary"] = secondary
     emit(line)

@@ -289,6 +289,20 @@ def test_full_size_10k_through_the_mirror_equals_the_reference_object_code(gpu, 
     assert all(np.array_equal(x, y) for x, y in zip(got, want))
 
 
+@pytest.mark.parametrize("n1,n2", [(128, 128), (300, 1000), (1000, 257), (5000, 4097)])
+def test_tensor_core_probe_equals_the_integer_kernel(gpu, oracle, n1, n2):
+    """include/ocb_probe.h: the top-2 search as an exact s8 contraction on the tensor cores (tcgen05.mma.kind::i8, TMEM
+    accumulators) -- the measured experiment behind north_star's "tensor cores are not used". Its records must be the
+    integer kernel's (and the oracle's) bit for bit, ties included."""
+    a, b = synthetic.config2_pair(n1, n2, seed=n1 + n2)
+    if n2 >= 1000:
+        b[n2 // 2:n2 // 2 + 40] = b[:40]  # exact ties across candidate tiles and candidate ranges
+    got, ms_expand, ms_mma, ranges = gpu.probe_tensor_top2(a, b, reps=2)
+    assert_top2_equal(got, oracle.match_top2(a, b))
+    assert_top2_equal(got, gpu.match_top2(a, b))
+    assert ms_mma > 0 and ranges >= 1
+
+
 def test_concurrent_callers(gpu, oracle):
     # the reference calls this path from many OpenMP workers at once (pipeline.cpp:42-49)
     import threading

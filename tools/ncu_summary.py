@@ -116,7 +116,7 @@ def roofline(rep, out, variant="0", comparisons="100000000"):
     git = subprocess.run(["git", "-C", root, "rev-parse", "HEAD"], capture_output=True, text=True).stdout.strip()
     rec = {
         "kernel": kernel.split("(")[0], "k1_variant": int(variant), "cross_check": args[3] in ("1", "true"),
-        "source_sha256": {f: sha(f) for f in ("hamming_top2.cu", "ocb_internal.cuh")}, "git_rev_of_capture_summary": git,
+        "source_sha256": {f: sha(f) for f in ("hamming_top2.cu",)}, "git_rev_of_capture_summary": git,
         "comparisons_per_launch": int(comparisons), "launches_averaged": len(k1), "report": os.path.basename(rep),
         "ncu": {"time_us": avg("gpu__time_duration.sum"),
                 "dram_bytes": avg("dram__bytes_read.sum", to_bytes) + avg("dram__bytes_write.sum",
