@@ -113,6 +113,8 @@ extern "C"
      *   "k1_items_per_sm"  work items per SM when one pair's candidate axis is split (default 32)
      *   "k1_update"        0 = by run length, 1 = compare + vote + skip, 2 = branch-free two-smallest
      *   "k1_bf_rows"       runs shorter than this use the branch-free update when k1_update == 0
+     *   "k1_engine"        single-pair search: 0 = by size (tensor cores from 512 x 512 rows up), 1 = integer pipes
+     *                      (K1: XOR + POPC), 2 = tensor cores (K1T: exact s8 contraction, tcgen05.mma)
      *   "k2_variant"       0 = by size, 1 = one hypothesis group per CTA, 2 = four groups per CTA in lock-step
      *   "k2_hg"            hypotheses per group (1..8); 0 = balance the SMs */
     int ocb_set_option(const char *key, int64_t value);

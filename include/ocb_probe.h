@@ -3,7 +3,6 @@
  * Not part of the drop-in boundary. */
 #ifndef OCB_PROBE_H
 #define OCB_PROBE_H
-#include <stddef.h>
 #include <stdint.h>
 #ifdef __cplusplus
 extern "C"
@@ -38,16 +37,6 @@ extern "C"
      * compared, square roots that differ, divisions outside the guarded range (not compared)}. 0 or a negative code. */
     int ocb_probe_exact_math(uint64_t seed, uint64_t n, uint32_t exponent_spread, uint64_t *counts5);
 
-    /* The ONE measured experiment behind "tensor cores are not used" (north_star): the same top-2 search as
-     * ocb_match_top2 (without the cross-check) formulated as an exact dense integer contraction -- bits mapped to
-     * +-1 in s8, dot = 512 - 2 * hamming -- on the 5th-generation tensor cores (tcgen05.mma.kind::i8, accumulators in
-     * TMEM, epilogue from tcgen05.ld): csrc/tc_probe.cu. q [n1][8], c [n2][8] host rows; out [n1] records, bit-equal
-     * to ocb_match_top2's when the formulation is right. reps timed repetitions; ms3 (nullable) = {ms per repetition
-     * of the bit -> s8 expansion of both sets, ms per repetition of the MMA + top-2 + merge kernels, candidate ranges
-     * used}. A probe, not a product path: n2 < 2^20, its own device buffers, no streams shared with the C ABI. */
-#include "ocb.h"
-    int ocb_probe_tensor_top2(const uint64_t *q, size_t n1, const uint64_t *c, size_t n2, ocb_top2 *out, int reps,
-                              double *ms3);
 #ifdef __cplusplus
 }
 #endif

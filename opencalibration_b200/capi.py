@@ -78,9 +78,6 @@ def lib():
     if hasattr(L, "ocb_probe_pipes"):
         L.ocb_probe_pipes.restype = i32
         L.ocb_probe_pipes.argtypes = [vp, i32]
-    if hasattr(L, "ocb_probe_tensor_top2"):
-        L.ocb_probe_tensor_top2.restype = i32
-        L.ocb_probe_tensor_top2.argtypes = [vp, sz, vp, sz, vp, i32, vp]
     if hasattr(L, "ocb_probe_exact_math"):
         L.ocb_probe_exact_math.restype = i32
         L.ocb_probe_exact_math.argtypes = [u64, u64, C.c_uint32, vp]
@@ -134,15 +131,6 @@ def probe_exact_math(seed, n, exponent_spread):
     counts = np.zeros(5, dtype=np.uint64)
     check(lib().ocb_probe_exact_math(int(seed), int(n), int(exponent_spread), _ptr(counts)))
     return counts
-
-
-def probe_tensor_top2(q, c, reps=10):
-    """include/ocb_probe.h: the tensor-core formulation of the top-2 search -> (records, ms expand, ms mma, ranges)."""
-    q, c = _rows(q), _rows(c)
-    out = np.zeros(len(q), TOP2_DTYPE)
-    ms = np.zeros(3)
-    check(lib().ocb_probe_tensor_top2(_ptr(q), len(q), _ptr(c), len(c), _ptr(out), int(reps), _ptr(ms)))
-    return out, float(ms[0]), float(ms[1]), int(ms[2])
 
 
 def match_top2(q, c, cross_check=False, out=None, col_out=None):

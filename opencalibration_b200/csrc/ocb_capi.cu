@@ -454,6 +454,8 @@ extern "C"
             o.k1_update = (int)value;
         else if (!strcmp(key, "k1_bf_rows"))
             o.k1_bf_rows = (int)value;
+        else if (!strcmp(key, "k1_engine"))
+            o.k1_engine = (int)value;
         else
             return fail_invalid("unknown option");
         return 0;
@@ -476,6 +478,8 @@ extern "C"
             return o.k1_update;
         if (!strcmp(key, "k1_bf_rows"))
             return o.k1_bf_rows;
+        if (!strcmp(key, "k1_engine"))
+            return o.k1_engine;
         if (!strcmp(key, "k1_queries_per_cta"))
             return k1_queries_per_cta();
         return OCB_E_INVALID;
@@ -492,7 +496,8 @@ extern "C"
         pr.n_q = (uint32_t)n1, pr.n_c = (uint32_t)n2;
         pr.col_out = with_col_best ? reinterpret_cast<uint32_t *>(16) : nullptr;
         k1_plan(&pr, 1, 148, 1 << 20);
-        return align_up(k1_state_bytes(pr), 256) + 256;
+        // whichever engine the call ends up using must fit
+        return std::max(align_up(k1_state_bytes(pr), 256) + 256, k1t_workspace_bytes(n1, n2, with_col_best != 0));
     }
 
     int ocb_match_top2_device(const void *d_q, size_t n1, const void *d_c, size_t n2, void *d_out,
@@ -514,6 +519,14 @@ extern "C"
             OCB_CUDA(cudaMemsetAsync(d_col_best_q, 0xFF, n2 * sizeof(uint32_t), st));
             return 0;
         }
+        // Engine: a pair large enough to fill the tensor pipe goes to K1T (the same records from an exact s8
+        // contraction, hamming_tensor.cu), everything else -- small pairs, pairs beyond K1T's position range -- to K1.
+        const int engine = options().k1_engine;
+        const bool big = n1 >= 512 && n2 >= 512;
+        if (n1 && n2 && k1t_supports(n1, n2) && (engine == 2 || (engine == 0 && big)) &&
+            k1t_workspace_bytes(n1, n2, col) <= workspace_bytes)
+            return k1t_launch(d_q, n1, d_c, n2, static_cast<ocb_top2 *>(d_out),
+                              col ? static_cast<uint32_t *>(d_col_best_q) : nullptr, d_workspace, sm_count(dev), st);
         K1Problem pr;
         memset(&pr, 0, sizeof pr);
         pr.q = static_cast<const uint4 *>(d_q), pr.n_q = (uint32_t)n1;

@@ -40,6 +40,7 @@ struct Options
     int k2_hg = 0;            // hypotheses per CTA of k2_score; 0 = balance the SMs (k2_pick_group)
     int k1_update = 0;      // 0 = choose by candidate-run length, 1 = vote-and-skip, 2 = branch-free
     int k1_bf_rows = 1 << 20; // runs shorter than this use the branch-free update (measured: it wins at every length)
+    int k1_engine = 0;        // single-pair search: 0 = by size, 1 = integer pipes (K1), 2 = tensor cores (K1T)
 };
 Options &options();
 
@@ -85,6 +86,12 @@ void k1_bind_state(K1Problem &P, void *d_state);    // point counters / best64 /
 int k1_launch(const K1Problem *d_problems, const K1Problem *h_problems, size_t n, const K1Plan &plan,
               cudaStream_t stream);
 int k1_queries_per_cta();
+
+// ---- K1T launch interface (hamming_tensor.cu): the same search on the tensor cores, one pair per call ------------
+bool k1t_supports(size_t n1, size_t n2);
+size_t k1t_workspace_bytes(size_t n1, size_t n2, bool col);
+int k1t_launch(const void *d_q, size_t n1, const void *d_c, size_t n2, ocb_top2 *d_out, uint32_t *d_col_best_q,
+               void *d_workspace, int sms, cudaStream_t stream);
 
 // ---- K5 / K6 launch interface (link_tail.cu) ----------------------------------------------------------------
 struct K5Pair

@@ -22,7 +22,6 @@
 
 #include <atomic>
 #include <cfloat>
-#include <type_traits>
 
 namespace ocb
 {
@@ -235,16 +234,10 @@ __device__ __forceinline__ void score_group(K2Shared &sm, const double *__restri
     const bool computes = warp < K2_CW;
     auto load_corr = [&](uint32_t r) {
         const uint32_t p = r * K2_TP + warp * 32 + lane;
-        // lanes past the end get NaN coordinates: their residual is NaN (through the out-of-line IEEE form, the range
-        // test sends every NaN there), which is never an inlier -- the hot loop needs no "is this position valid" test
-        if (p >= n)
-        {
-            const double nan = __longlong_as_double(0x7ff8000000000000ll);
-            return make_double4(nan, nan, nan, nan);
-        }
+        const uint32_t pc = p < n ? p : n - 1; // lanes past the end recompute the last position (never inliers)
         if (corr4)
-            return corr4[p];
-        return normalise_corr(c7 + (size_t)(order ? order[p] : p) * 7);
+            return corr4[pc];
+        return normalise_corr(c7 + (size_t)(order ? order[pc] : pc) * 7);
     };
     double r_thr = 0.0;     // compute warps: reciprocal shared by every MSAC contribution of this thread
     uint32_t thr_rng = 0;
@@ -274,51 +267,6 @@ __device__ __forceinline__ void score_group(K2Shared &sm, const double *__restri
                 c_next = load_corr(r + 1); // in flight while this round computes
             if (r >= 2)
                 mbar_wait(&sm.empty_bar[b], ((r >> 1) - 1) & 1); // the sum warp has consumed round r - 2
-            if constexpr (W == 1)
-            {
-                // one hypothesis at a time; the shared-memory cursors (matrix, contribution slot, mask word) advance by
-                // constants instead of being recomputed from g, and the loop exists twice so that the variant without
-                // inlier masks carries no global-memory cursor
-                auto sweep = [&](auto with_bits) {
-                    const double *Mg = sm.M[0];
-                    double *cp = &sm.contrib[b][0][warp * 32 + lane];
-                    uint32_t *mp = &sm.mask[b][0][warp];
-                    uint32_t *bp = nullptr;
-                    bool writes_bits = false;
-                    if constexpr (decltype(with_bits)::value)
-                    {
-                        writes_bits = lane == 0 && (p >> 5) < words;
-                        bp = bits_pos + (size_t)h0 * words + (p >> 5);
-                    }
-#pragma unroll 1
-                    for (uint32_t g = 0; g < nh; g++, Mg += 18, cp += K2_TP + 2, mp += K2_CW + 1)
-                    {
-                        FastResidual f = residual_fast<KIND>(Mg, c.x, c.y, c.z, c.w, thr, r_thr, thr_rng);
-                        if (f.rng >= RANGE_OK) // rare: tiny, huge or non-finite operands (and lanes past the end)
-                        {
-                            f.e = residual<KIND>(Mg, c.x, c.y, c.z, c.w);
-                            f.ratio = __ddiv_rn(f.e, thr);
-                        }
-                        const bool inl = f.e < thr; // strict, ransac.cpp:189; false for NaN
-                        // an outlier parks +0.0: score + 0.0 == score bit for bit (the score is never -0.0), so the
-                        // sum warp adds whole 32-position words in order without testing single bits
-                        *cp = inl ? __dsub_rn(1.0, __dmul_rn(f.ratio, f.ratio)) : 0.0;
-                        const uint32_t m = __ballot_sync(0xFFFFFFFFu, inl);
-                        *mp = m; // every lane stores the same word
-                        if constexpr (decltype(with_bits)::value)
-                        {
-                            if (writes_bits)
-                                *bp = m;
-                            bp += words;
-                        }
-                    }
-                };
-                if (bits_pos)
-                    sweep(std::true_type());
-                else
-                    sweep(std::false_type());
-            }
-            else
             for (uint32_t g = 0; g < nh; g += W)
             {
                 FastResidual f[W];
@@ -340,6 +288,8 @@ __device__ __forceinline__ void score_group(K2Shared &sm, const double *__restri
                     if (g + w < nh)
                     {
                         const bool inl = valid && (f[w].e < thr); // strict, ransac.cpp:189
+                        // an outlier parks +0.0: score + 0.0 == score bit for bit (the score is never -0.0), so the
+                        // sum warp adds whole 32-position words in order without testing single bits
                         sm.contrib[b][g + w][warp * 32 + lane] =
                             inl ? __dsub_rn(1.0, __dmul_rn(f[w].ratio, f[w].ratio)) : 0.0;
                         const uint32_t m = __ballot_sync(0xFFFFFFFFu, inl);

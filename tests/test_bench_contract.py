@@ -70,7 +70,8 @@ def test_product_arm_line_has_every_contract_key():
     need = (REQUIRED - {"impl"}) | {"roofline", "clocks", "gpu_launches"}
     assert need <= set(d), need - set(d)
     assert d["metric"] == "hamming_comparisons_per_s" and d["n_gpus"] == 1 and d["steps"] == 20 and d["warmup"] == 3
-    assert d["scaling"] == "weak" and d["dtype"] == "u32" and d["gpu_launches"] >= 20
+    assert d["scaling"] == "weak" and d["gpu_launches"] >= 20
+    assert d["engine"].startswith("tensor") and d["dtype"].startswith("s8")  # a 10k x 10k pair goes to the tensor cores
     assert d["value"] > 100 and d["e2e"]["value"] > 50                       # Gcmp/s: far above any CPU path
     assert d["e2e"]["h2d_bytes_per_step"] == 2 * 10000 * 64 and d["e2e"]["d2h_bytes_per_step"] > 0
     rf = d["roofline"]
@@ -80,7 +81,13 @@ def test_product_arm_line_has_every_contract_key():
     assert cb["kind"] == "reference" and cb["cores"] >= 1 and 0 < cb["value"] < d["value"]
     assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
     assert d["config"]["parity_full"] is True  # every query and every column of the timed pair against the oracle
-    assert rf["profile"] and rf["profile"]["k1_variant"] == d["config"]["k1_variant"] and rf["mix_frac"] > 0.5
+    assert rf["bound"] == "tensor" and rf["unit"] == "TFLOP/s" and rf["popc_roofline_equivalent"]["frac"] > 1.0
+    # the engine north_star specifies is measured in the same run, against the integer-pipe roofline
+    ie = d["integer_pipe_engine"]
+    assert ie["parity_full"] is True and 200 < ie["value"] < d["value"]
+    irf = ie["roofline"]
+    assert irf["profile"] and irf["profile"]["k1_variant"] == d["config"]["k1_variant"] and irf["mix_frac"] > 0.5
+    assert abs(irf["frac"] - irf["achieved"] / irf["peak"]) < 1e-9 and irf["frac"] > 0.6  # north_star's target
     assert d["e2e"]["single_caller"]["value"] > 20
     # the sharded survey (configs[3]) is part of the driver-run line at every N, gather inside its timed region
     c4 = d["secondary"]["c4_survey"]

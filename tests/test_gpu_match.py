@@ -17,6 +17,15 @@ def assert_top2_equal(r, oracle_out):
     assert np.array_equal(r["second_d"], sd)
 
 
+@pytest.fixture(autouse=True, params=[1, 2], ids=["int-pipes", "tensor-cores"])
+def engine(request, gpu):
+    """Every test of this file runs on both engines of the single-pair search (the batched entry points are K1 only and
+    simply run twice)."""
+    gpu.set_option("k1_engine", request.param)
+    yield request.param
+    gpu.set_option("k1_engine", 0)
+
+
 @pytest.fixture()
 def default_options(gpu):
     yield
@@ -107,7 +116,7 @@ def test_split_merge_keeps_position_order(gpu, oracle, default_options):
         assert_top2_equal(gpu.match_top2(a, b), oracle.match_top2(a, b))
 
 
-def test_device_resident_entry_point(gpu, oracle):
+def test_device_resident_entry_point(gpu, oracle, engine):
     import torch
     n1, n2 = 3000, 2500
     a, b = synthetic.config2_pair(n1, n2, seed=21)
@@ -122,7 +131,8 @@ def test_device_resident_entry_point(gpu, oracle):
     gpu.match_top2_device(dq.data_ptr(), n1, dc.data_ptr(), n2, dout.data_ptr(), dcol.data_ptr(), wsp, wsb,
                           torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
-    assert gpu.kernel_launches() - before == 1  # one fused kernel: top-2, split merge and cross-check
+    # K1: one fused kernel (top-2, split merge and cross-check); K1T: expansion, search, finish
+    assert gpu.kernel_launches() - before == (1 if engine == 1 else 3)
     r = dout.cpu().numpy().view(gpu.TOP2_DTYPE)
     assert_top2_equal(r, oracle.match_top2(a, b))
     assert np.array_equal(dcol.cpu().numpy().view(np.uint32), oracle.match_col_best(a, b))
@@ -289,18 +299,27 @@ def test_full_size_10k_through_the_mirror_equals_the_reference_object_code(gpu, 
     assert all(np.array_equal(x, y) for x, y in zip(got, want))
 
 
-@pytest.mark.parametrize("n1,n2", [(128, 128), (300, 1000), (1000, 257), (5000, 4097)])
-def test_tensor_core_probe_equals_the_integer_kernel(gpu, oracle, n1, n2):
-    """include/ocb_probe.h: the top-2 search as an exact s8 contraction on the tensor cores (tcgen05.mma.kind::i8, TMEM
-    accumulators) -- the measured experiment behind north_star's "tensor cores are not used". Its records must be the
-    integer kernel's (and the oracle's) bit for bit, ties included."""
-    a, b = synthetic.config2_pair(n1, n2, seed=n1 + n2)
-    if n2 >= 1000:
-        b[n2 // 2:n2 // 2 + 40] = b[:40]  # exact ties across candidate tiles and candidate ranges
-    got, ms_expand, ms_mma, ranges = gpu.probe_tensor_top2(a, b, reps=2)
-    assert_top2_equal(got, oracle.match_top2(a, b))
-    assert_top2_equal(got, gpu.match_top2(a, b))
-    assert ms_mma > 0 and ranges >= 1
+def test_engines_agree_and_auto_picks_by_size(gpu, oracle):
+    """The single-pair search has two engines with one contract: K1 on the integer pipes (XOR + POPC) and K1T on the
+    tensor cores (exact s8 contraction, tcgen05.mma.kind::i8, TMEM accumulators). Same records bit for bit, ties and
+    cross-check included; by default pairs from 512 x 512 rows up go to the tensor cores."""
+    a, b = synthetic.config2_pair(3000, 2777, seed=17)
+    b[1500:1540] = b[:40]   # exact ties across candidate tiles and candidate ranges
+    b[2700] = a[5]
+    want, want_col = oracle.match_top2(a, b), oracle.match_col_best(a, b)
+    launches = {}
+    for engine in (1, 2, 0):
+        gpu.set_option("k1_engine", engine)
+        before = gpu.kernel_launches()
+        r, col = gpu.match_top2(a, b, cross_check=True)
+        launches[engine] = gpu.kernel_launches() - before
+        assert_top2_equal(r, want)
+        assert np.array_equal(col, want_col)
+    gpu.set_option("k1_engine", 0)
+    assert launches[1] == 1 and launches[2] == 3 and launches[0] == 3  # K1: one kernel; K1T: expand, search, finish
+    before = gpu.kernel_launches()
+    gpu.match_top2(a[:100], b[:100])
+    assert gpu.kernel_launches() - before == 1  # small pairs stay on the integer pipes
 
 
 def test_concurrent_callers(gpu, oracle):
