@@ -16,16 +16,17 @@
 //                      shared-memory descriptor: [K chunk of 16 B][row][16 B] (core matrix = 8 rows x 16 B contiguous;
 //                      SBO = 128 B between 8-row groups, LBO = 2048 B between K chunks). A tile is 64 KB and arrives in
 //                      shared memory with ONE bulk copy.
-//   k1t_top2_kernel    CTA = (query tile of 128 rows, contiguous range of candidate tiles), 6 warps:
+//   k1t_top2_kernel    CTA = (query tile of 128 rows, contiguous range of candidate tiles), 10 warps:
 //                        warp 0    producer: bulk copies (cp.async.bulk + mbarrier) of the query tile, then of the
 //                                  candidate tiles through a two-stage ring;
 //                        warp 1    one thread issues, per candidate tile, 16 x tcgen05.mma (M 128 x N 128 x K 32) into
 //                                  one of two 128-column TMEM accumulators and commits them to mbarriers (stage free,
 //                                  accumulator full);
-//                        warps 2-5 epilogue: tcgen05.ld 32 columns at a time (thread = query row), one IMAD turns the
-//                                  dot product into v = distance << 20 | position, then K1's branch-free two-smallest
-//                                  update. Cross-check: per candidate the warp minimum (REDUX) of distance << 8 | row,
-//                                  combined over the four warps through shared memory, one 64-bit atomic max per
+//                        warps 2-9 epilogue (two per TMEM lane quarter, one column half each): tcgen05.ld 32 columns
+//                                  at a time (thread = query row), one IMAD turns the dot product into
+//                                  v = distance << 20 | position, then K1's branch-free two-smallest update.
+//                                  Cross-check: per candidate the warp maximum (REDUX) of (dot + 513) << 8 | (127 - row),
+//                                  combined over the quarters through shared memory, one 64-bit atomic max per
 //                                  candidate and CTA on the complemented (distance, query) key, as in K1.
 //   k1t_finish_kernel  merges the candidate ranges of every query (positions are global, so packed values merge by
 //                      min / max), writes the records and turns the column keys into query indices.
@@ -34,6 +35,7 @@
 #include "ocb_internal.cuh"
 
 #include <algorithm>
+#include <type_traits>
 
 namespace ocb
 {
@@ -45,7 +47,8 @@ constexpr uint32_t T_TILE_BYTES = T_ROWS * T_KBYTES;    // 64 KB
 constexpr uint32_t T_LBO = T_ROWS * 16;                 // bytes between K chunks
 constexpr uint32_t T_SBO = 8 * 16;                      // bytes between 8-row groups
 constexpr int T_STAGES = 2;
-constexpr int T_THREADS = 192;
+constexpr int T_EPI_WARPS = 8;                         // epilogue warps: two per TMEM lane quarter (column halves)
+constexpr int T_THREADS = (2 + T_EPI_WARPS) * 32;
 constexpr uint32_t T_SHIFT = 20;
 constexpr uint32_t T_NONE = 0xFFFFFFFFu;
 constexpr uint32_t T_TMEM_COLS = 256;
@@ -105,7 +108,7 @@ struct K1TParams
 {
     const uint4 *q_tiles;       // expanded query tiles
     const uint4 *c_tiles;       // expanded candidate tiles
-    uint32_t *part;             // [ranges][n1_padded][2] packed (s1, s2)
+    uint32_t *part;             // [ranges][2 column halves][n1_padded][2] packed (s1, s2)
     unsigned long long *col64;  // [n2] complemented (distance, query) keys, zero before the launch; cross-check only
     uint32_t n1, n1_padded, n2, c_tiles_total, tiles_per_range;
 };
@@ -134,7 +137,7 @@ template <bool COL> __global__ void __launch_bounds__(T_THREADS, 1) k1t_top2_ker
             mbar_init(&b_full[s], 1);
             mbar_init(&b_empty[s], 1);
             mbar_init(&d_full[s], 1);
-            mbar_init(&d_empty[s], 4);
+            mbar_init(&d_empty[s], T_EPI_WARPS);
         }
         mbar_fence_init();
     }
@@ -210,19 +213,22 @@ template <bool COL> __global__ void __launch_bounds__(T_THREADS, 1) k1t_top2_ker
     }
     else
     {
-        const uint32_t quarter = warp & 3u;       // the TMEM lanes a warp may read: 32 * (warp id % 4) ..
+        // Eight epilogue warps: warp w reads the TMEM lanes of quarter w % 4 (a hardware rule) and the column half
+        // (w - 2) / 4 of every accumulator, so that every scheduler of the SM has two warps to issue from.
+        const uint32_t quarter = warp & 3u;
+        const uint32_t half = (warp - 2u) >> 2;
         const uint32_t row = quarter * 32u + lane; // query row of this thread within the tile
         const uint32_t qpos = qtile * T_ROWS + row;
-        const uint32_t row_key = qpos < P.n1 ? row : 0xFFFFFFFFu; // padding rows never win a column
+        // cross-check key of (this query, a candidate) = (dot + 513) << 8 | (127 - row): its MAXIMUM over the queries is
+        // the smallest distance and, among equals, the smallest row; 0 = nothing (padding rows contribute 0)
+        const uint32_t key_mul = qpos < P.n1 ? 256u : 0u;
+        const uint32_t key_add = qpos < P.n1 ? ((513u << 8) | (127u - row)) : 0u;
         uint32_t s1 = T_NONE, s2 = T_NONE;
-        for (uint32_t t = 0; t < ntiles; t++)
-        {
+        auto sweep = [&](uint32_t t, auto partial) {
             const uint32_t buf = t & 1;
-            wait_or_trap(&d_full[buf], (t >> 1) & 1);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t pos0 = (t_begin + t) * T_ROWS;
 #pragma unroll 1
-            for (uint32_t c0 = 0; c0 < T_ROWS; c0 += 32)
+            for (uint32_t c0 = half * 64u; c0 < half * 64u + 64u; c0 += 32)
             {
                 uint32_t d[32];
                 const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + buf * T_ROWS + c0;
@@ -236,26 +242,24 @@ template <bool COL> __global__ void __launch_bounds__(T_THREADS, 1) k1t_top2_ker
                                "=r"(d[29]), "=r"(d[30]), "=r"(d[31])
                              : "r"(taddr));
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                // v = (512 - dot) / 2 << 20 | position; dot is even, so (512 - dot) << 19 is exact
+                // v = (512 - dot) / 2 << 20 | position; dot is even, so (512 - dot) << 19 is exact: one IMAD
                 const uint32_t base = (512u << (T_SHIFT - 1)) + pos0 + c0;
-                uint32_t mine = T_NONE; // cross-check: this lane keeps the warp minimum of column c0 + lane
+                uint32_t *cm = colmin + (t & 1u) * 512u + quarter * 128u + c0;
 #pragma unroll
                 for (int i = 0; i < 32; i++)
                 {
-                    uint32_t v = base + (uint32_t)i - (d[i] << (T_SHIFT - 1));
-                    v = pos0 + c0 + (uint32_t)i < P.n2 ? v : T_NONE;
+                    uint32_t v = d[i] * (0u - (1u << (T_SHIFT - 1))) + (base + (uint32_t)i);
+                    if constexpr (decltype(partial)::value) // only the last candidate tile can hold padding columns
+                        v = pos0 + c0 + (uint32_t)i < P.n2 ? v : T_NONE;
                     s2 = min(s2, max(s1, v));
                     s1 = min(s1, v);
                     if constexpr (COL)
                     {
-                        // (distance << 8 | row) orders by distance, then by query position within the tile
-                        const uint32_t w = row_key == 0xFFFFFFFFu ? 0xFFFFFFFFu : (((v >> T_SHIFT) << 8) | row_key);
-                        const uint32_t m = __reduce_min_sync(0xFFFFFFFFu, w);
-                        mine = lane == (uint32_t)i ? m : mine;
+                        const uint32_t m = __reduce_max_sync(0xFFFFFFFFu, d[i] * key_mul + key_add);
+                        if (lane == 0)
+                            cm[i] = m; // the warp's best (distance, row) for candidate pos0 + c0 + i
                     }
                 }
-                if constexpr (COL)
-                    colmin[(t & 1u) * 512u + quarter * 128u + c0 + lane] = mine;
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
@@ -263,22 +267,34 @@ template <bool COL> __global__ void __launch_bounds__(T_THREADS, 1) k1t_top2_ker
                 mbar_arrive(&d_empty[buf]);
             if constexpr (COL)
             {
-                // the four epilogue warps meet (named barrier 1, 128 threads); thread k then owns candidate pos0 + k.
-                // Buffer t & 1 is written again in tile t + 2, i.e. after the barrier of tile t + 1, which this thread
-                // reaches only after this flush.
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                const uint32_t k = row;
-                const uint32_t *cm = colmin + (t & 1u) * 512u;
-                const uint32_t m = min(min(cm[k], cm[128 + k]), min(cm[256 + k], cm[384 + k]));
-                if (pos0 + k < P.n2 && m != 0xFFFFFFFFu)
+                // the eight epilogue warps meet (named barrier 1); thread k < 128 then owns candidate pos0 + k. Buffer
+                // t & 1 is written again in tile t + 2, i.e. after the barrier of tile t + 1, which that thread reaches
+                // only after this flush.
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                const uint32_t k = (warp - 2u) * 32u + lane;
+                if (k < T_ROWS)
                 {
-                    const unsigned long long key =
-                        ((unsigned long long)(m >> 8) << 32) | (unsigned long long)(qtile * T_ROWS + (m & 0xFFu));
-                    red_max_u64_global(&P.col64[pos0 + k], ~key);
+                    const uint32_t *all = colmin + (t & 1u) * 512u;
+                    const uint32_t m = max(max(all[k], all[128 + k]), max(all[256 + k], all[384 + k]));
+                    if (pos0 + k < P.n2 && m != 0u)
+                    {
+                        const unsigned long long key = ((unsigned long long)((1025u - (m >> 8)) >> 1) << 32) |
+                                                       (unsigned long long)(qtile * T_ROWS + 127u - (m & 0xFFu));
+                        red_max_u64_global(&P.col64[pos0 + k], ~key);
+                    }
                 }
             }
+        };
+        for (uint32_t t = 0; t < ntiles; t++)
+        {
+            wait_or_trap(&d_full[t & 1], (t >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if ((t_begin + t + 1) * T_ROWS <= P.n2)
+                sweep(t, std::false_type());
+            else
+                sweep(t, std::true_type());
         }
-        uint32_t *out = P.part + ((size_t)range * P.n1_padded + qpos) * 2;
+        uint32_t *out = P.part + ((size_t)(range * 2u + half) * P.n1_padded + qpos) * 2;
         out[0] = s1, out[1] = s2;
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -347,7 +363,7 @@ K1TLayout k1t_layout(size_t n1, size_t n2, bool col, int sms)
     };
     L.o_qt = take((size_t)L.q_tiles * T_TILE_BYTES);
     L.o_ct = take((size_t)L.c_tiles * T_TILE_BYTES);
-    L.o_part = take((size_t)L.ranges * L.n1p * 2 * sizeof(uint32_t));
+    L.o_part = take((size_t)L.ranges * 2 * L.n1p * 2 * sizeof(uint32_t));
     L.o_col = take(col ? n2 * sizeof(unsigned long long) : 0);
     L.total = off;
     return L;
@@ -400,7 +416,7 @@ int k1t_launch(const void *d_q, size_t n1, const void *d_c, size_t n2, ocb_top2 
         k1t_top2_kernel<false><<<dim3(L.q_tiles, L.ranges), T_THREADS, smem, stream>>>(P);
     }
     const uint32_t finish = (uint32_t)std::max(n1, col ? n2 : (size_t)0);
-    k1t_finish_kernel<<<(finish + 255) / 256, 256, 0, stream>>>(P.part, L.ranges, L.n1p, (uint32_t)n1, d_out, P.col64,
+    k1t_finish_kernel<<<(finish + 255) / 256, 256, 0, stream>>>(P.part, L.ranges * 2, L.n1p, (uint32_t)n1, d_out, P.col64,
                                                               (uint32_t)n2, d_col_best_q);
     count_launch(3);
     OCB_CUDA(cudaGetLastError());
