@@ -151,10 +151,14 @@ def tensor_roofline(achieved_gcmp, ms_per_step, peaks, peak_src, sm_max, int_roo
     achieved = ops / (ms_per_step * 1e-3) / 1e12
     bf16 = float(peaks.get("bf16_tflops", 1590.0))
     peak = 2.0 * bf16
-    prof = None
+    import hashlib
+    prof, why_not = None, "profiles/k1t_roofline.json is missing"
     path = os.path.join(ROOT, "profiles", "k1t_roofline.json")
     if os.path.exists(path):
-        prof = json.load(open(path))
+        prof, why_not = json.load(open(path)), None
+        src = os.path.join(ROOT, "opencalibration_b200", "csrc", "hamming_tensor.cu")
+        if hashlib.sha256(open(src, "rb").read()).hexdigest() != prof.get("source_sha256", {}).get("hamming_tensor.cu"):
+            prof, why_not = None, "profiles/k1t_roofline.json was taken with another hamming_tensor.cu"
     algo_bytes = (N1 + N2) * 64 + N1 * 8 + N2 * 4
     return {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
             "traffic": prof["ncu"]["dram_bytes_per_step"] if prof else None,
@@ -172,7 +176,7 @@ def tensor_roofline(achieved_gcmp, ms_per_step, peaks, peak_src, sm_max, int_roo
             "hbm": {"achieved_gbs": algo_bytes / (ms_per_step * 1e-3) / 1e9, "peak_gbs": peaks.get("hbm_gbs"),
                     "algorithmic_bytes_per_step": algo_bytes,
                     "measured_dram_bytes_per_step": prof["ncu"]["dram_bytes_per_step"] if prof else None},
-            "profile": prof}
+            "profile": prof, "profile_unusable": why_not}
 
 
 def _timed(torch, fn, reps):

@@ -139,5 +139,56 @@ def roofline(rep, out, variant="0", comparisons="100000000"):
     print(json.dumps(rec, indent=1))
 
 
+def roofline_k1t(rep, out, comparisons="100000000"):
+    """profiles/k1t_roofline.json: the tensor-core engine's three kernels (expansion, search, finish) of one step."""
+    import hashlib
+    import json
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], check=True, capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    header, units, launches_ = rows[0], rows[1], rows[2:]
+    col = {h: c for c, h in enumerate(header)}
+    to_bytes = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    to_us = {"ns": 1e-3, "us": 1.0, "ms": 1e3}
+
+    def val(r, metric):
+        return float(r[col[metric]].replace(",", ""))
+
+    kernels = {}
+    for r in launches_:
+        name = re.sub(r"\(.*", "", r[col["Kernel Name"]])
+        name = re.sub(r"^void |.*unnamed>::", "", name)
+        k = kernels.setdefault(name, {"launches": 0, "time_us": 0.0, "dram_bytes": 0.0, "rows": []})
+        k["launches"] += 1
+        k["time_us"] += val(r, "gpu__time_duration.sum") * to_us[units[col["gpu__time_duration.sum"]]]
+        k["dram_bytes"] += (val(r, "dram__bytes_read.sum") * to_bytes[units[col["dram__bytes_read.sum"]]] +
+                            val(r, "dram__bytes_write.sum") * to_bytes[units[col["dram__bytes_write.sum"]]])
+        k["rows"].append(r)
+    search = next(k for n, k in kernels.items() if "k1t_top2_kernel" in n)
+    steps = search["launches"]
+
+    def avg(k, metric):
+        return sum(val(r, metric) for r in k["rows"]) / len(k["rows"])
+    sha = hashlib.sha256(open(os.path.join(root, "opencalibration_b200", "csrc", "hamming_tensor.cu"), "rb").read()).hexdigest()
+    git = subprocess.run(["git", "-C", root, "rev-parse", "HEAD"], capture_output=True, text=True).stdout.strip()
+    rec = {"kernels": {n: {"time_us": k["time_us"] / k["launches"], "dram_bytes": k["dram_bytes"] / k["launches"]}
+                       for n, k in kernels.items()},
+           "source_sha256": {"hamming_tensor.cu": sha}, "git_rev_of_capture_summary": git, "report": os.path.basename(rep),
+           "comparisons_per_step": int(comparisons), "steps_averaged": steps,
+           "ncu": {"dram_bytes_per_step": sum(k["dram_bytes"] for k in kernels.values()) / steps,
+                   "search_time_us": search["time_us"] / steps,
+                   "tensor_pipe_pct_active": avg(search, "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"),
+                   "alu_pct_of_peak": avg(search, "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"),
+                   "issue_slots_pct": avg(search, "smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                   "l2_hit_pct": avg(search, "lts__t_sector_hit_rate.pct"),
+                   "warp_instructions": avg(search, "smsp__inst_executed.sum"),
+                   "registers_per_thread": avg(search, "launch__registers_per_thread"),
+                   "sm_ghz": avg(search, "sm__cycles_elapsed.avg.per_second")}}
+    rec["ncu"]["warp_instructions_per_32_comparisons"] = rec["ncu"]["warp_instructions"] / (int(comparisons) / 32)
+    json.dump(rec, open(out, "w"), indent=1)
+    print(json.dumps(rec, indent=1))
+
+
 if __name__ == "__main__":
-    {"full": full, "launches": launches, "roofline": roofline}[sys.argv[1]](*sys.argv[2:])
+    {"full": full, "launches": launches, "roofline": roofline, "roofline_k1t": roofline_k1t}[sys.argv[1]](*sys.argv[2:])
