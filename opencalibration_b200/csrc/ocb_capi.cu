@@ -456,6 +456,8 @@ extern "C"
             o.k1_bf_rows = (int)value;
         else if (!strcmp(key, "k1_engine"))
             o.k1_engine = (int)value;
+        else if (!strcmp(key, "k1t_variant"))
+            o.k1t_variant = (int)value;
         else
             return fail_invalid("unknown option");
         return 0;
@@ -480,6 +482,8 @@ extern "C"
             return o.k1_bf_rows;
         if (!strcmp(key, "k1_engine"))
             return o.k1_engine;
+        if (!strcmp(key, "k1t_variant"))
+            return o.k1t_variant;
         if (!strcmp(key, "k1_queries_per_cta"))
             return k1_queries_per_cta();
         return OCB_E_INVALID;

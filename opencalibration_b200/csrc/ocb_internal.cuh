@@ -41,6 +41,7 @@ struct Options
     int k1_update = 0;      // 0 = choose by candidate-run length, 1 = vote-and-skip, 2 = branch-free
     int k1_bf_rows = 1 << 20; // runs shorter than this use the branch-free update (measured: it wins at every length)
     int k1_engine = 0;        // single-pair search: 0 = by size, 1 = integer pipes (K1), 2 = tensor cores (K1T)
+    int k1t_variant = 0;      // K1T search kernel: 0 = default, 1 = first form, 2 / 3 = second form, one / two query tiles per CTA
 };
 Options &options();
 

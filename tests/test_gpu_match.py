@@ -17,13 +17,17 @@ def assert_top2_equal(r, oracle_out):
     assert np.array_equal(r["second_d"], sd)
 
 
-@pytest.fixture(autouse=True, params=[1, 2], ids=["int-pipes", "tensor-cores"])
+@pytest.fixture(autouse=True, params=[(1, 0), (2, 1), (2, 2), (2, 3), (2, 4)],
+                ids=["int-pipes", "tensor-cores-form1", "tensor-cores-form2-m128", "tensor-cores-form2-m256",
+                     "tensor-cores-form3-tmem"])
 def engine(request, gpu):
-    """Every test of this file runs on both engines of the single-pair search (the batched entry points are K1 only and
-    simply run twice)."""
-    gpu.set_option("k1_engine", request.param)
-    yield request.param
+    """Every test of this file runs on both engines of the single-pair search and on every form of the tensor-core
+    search kernel (the batched entry points are K1 only and simply run again)."""
+    gpu.set_option("k1_engine", request.param[0])
+    gpu.set_option("k1t_variant", request.param[1])
+    yield request.param[0]
     gpu.set_option("k1_engine", 0)
+    gpu.set_option("k1t_variant", 0)
 
 
 @pytest.fixture()
@@ -49,6 +53,23 @@ def test_top2_matches_oracle(gpu, oracle, n1, n2):
     r, col = gpu.match_top2(a, b, cross_check=True)
     assert_top2_equal(r, oracle.match_top2(a, b))
     assert np.array_equal(col, oracle.match_col_best(a, b))
+
+
+@pytest.mark.parametrize("n1,n2", [(40000, 100), (5000, 700), (130, 20000), (300, 33), (2049, 4097)])
+def test_tensor_forms_on_span_shapes(gpu, oracle, engine, n1, n2):
+    """Shapes that exercise the persistent spans of the second form of the tensor-core search: spans that cross from one
+    query tile group into the next after one, two or many candidate steps, a single group shared by a hundred CTAs,
+    fewer steps than SMs."""
+    if engine != 2:
+        pytest.skip("tensor-core engine only")
+    a, b = synthetic.config2_pair(n1, n2, seed=n1 + 7 * n2)
+    b[n2 - 1] = b[0]
+    b[n2 // 3] = a[n1 - 1]
+    a[n1 // 2] = a[0]  # equal queries: the cross-check must name the first one
+    r, col = gpu.match_top2(a, b, cross_check=True)
+    assert_top2_equal(r, oracle.match_top2(a, b))
+    assert np.array_equal(col, oracle.match_col_best(a, b))
+    assert_top2_equal(gpu.match_top2(a, b), oracle.match_top2(a, b))
 
 
 def test_empty_and_degenerate_inputs(gpu, oracle):
