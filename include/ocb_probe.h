@@ -37,6 +37,12 @@ extern "C"
      * compared, square roots that differ, divisions outside the guarded range (not compared)}. 0 or a negative code. */
     int ocb_probe_exact_math(uint64_t seed, uint64_t n, uint32_t exponent_spread, uint64_t *counts5);
 
+    /* Tensor pipe: average cycles per tcgen05.mma.kind::i8 (M 128 x N n x K 32, one CTA per SM on `ctas` SMs) when one
+     * thread issues rounds x chains of them back to back, rotating over `chains` independent accumulators of n columns,
+     * with A read from shared memory (a_in_tmem = 0) or from tensor memory (1). The arithmetic alone takes n / 2 cycles.
+     * chains * n <= 512 (384 with A in tensor memory). 0 or a negative code. */
+    int ocb_probe_umma(int a_in_tmem, int n, int chains, int rounds, int ctas, double *cycles_per_mma);
+
 #ifdef __cplusplus
 }
 #endif

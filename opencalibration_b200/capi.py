@@ -81,6 +81,9 @@ def lib():
     if hasattr(L, "ocb_probe_exact_math"):
         L.ocb_probe_exact_math.restype = i32
         L.ocb_probe_exact_math.argtypes = [u64, u64, C.c_uint32, vp]
+    if hasattr(L, "ocb_probe_umma"):
+        L.ocb_probe_umma.restype = i32
+        L.ocb_probe_umma.argtypes = [i32, i32, i32, i32, i32, vp]
     _lib = L
     return L
 
@@ -131,6 +134,13 @@ def probe_exact_math(seed, n, exponent_spread):
     counts = np.zeros(5, dtype=np.uint64)
     check(lib().ocb_probe_exact_math(int(seed), int(n), int(exponent_spread), _ptr(counts)))
     return counts
+
+
+def probe_umma(a_in_tmem, n, chains, rounds=512, ctas=148):
+    """include/ocb_probe.h: cycles per tcgen05.mma.kind::i8 (M 128 x N n x K 32) over `chains` independent accumulators."""
+    out = np.zeros(1, dtype=np.float64)
+    check(lib().ocb_probe_umma(int(bool(a_in_tmem)), int(n), int(chains), int(rounds), int(ctas), _ptr(out)))
+    return float(out[0])
 
 
 def match_top2(q, c, cross_check=False, out=None, col_out=None):

@@ -36,6 +36,7 @@
 
 #include <algorithm>
 #include <type_traits>
+#include <vector>
 
 namespace ocb
 {
@@ -52,7 +53,7 @@ constexpr int T_THREADS = (2 + T_EPI_WARPS) * 32;
 constexpr uint32_t T_SHIFT = 20;
 constexpr uint32_t T_NONE = 0xFFFFFFFFu;
 constexpr uint32_t T_TMEM_COLS = 256;
-constexpr int K1T_DEFAULT_VARIANT = 1; // form of the search kernel when the option k1t_variant is 0 (see k1t_launch)
+constexpr int K1T_DEFAULT_VARIANT = 4; // form of the search kernel when the option k1t_variant is 0 (see k1t_launch)
 
 // rows [n][8] u64 -> tiles [ceil(n/128)][32 K chunks][128 rows][16 B] of s8 (+1 / -1); rows past n: all -1
 __global__ void __launch_bounds__(256)
@@ -1276,6 +1277,87 @@ int k1t2_launch(bool a_in_tmem, int mt, int nt, const void *d_q, size_t n1, cons
     return 0;
 }
 
+// ---- diagnostic (include/ocb_probe.h): how fast the tensor pipe retires tcgen05.mma.kind::i8 (M 128 x N x K 32) as a
+// function of N, of the number of independent accumulators the MMAs rotate over, and of where A lives
+__global__ void __launch_bounds__(128, 1) umma_probe_kernel(int a_in_tmem, int n, int chains, int rounds,
+                                                            unsigned long long *cycles_out)
+{
+    extern __shared__ __align__(128) unsigned char probe_smem[];
+    unsigned char *sA = probe_smem;                 // 64 KB: one query tile (shared-memory A only)
+    unsigned char *sB = probe_smem + 65536;         // up to 256 rows x 512 B
+    __shared__ uint64_t bar;
+    __shared__ uint32_t slot;
+    for (uint32_t i = threadIdx.x; i < (65536u + 131072u) / 16; i += blockDim.x)
+        reinterpret_cast<uint4 *>(probe_smem)[i] = make_uint4(0x01FF01FFu, 0xFF01FF01u, 0x0101FFFFu, 0xFFFF0101u);
+    if (threadIdx.x == 0)
+    {
+        mbar_init(&bar, 1);
+        mbar_fence_init();
+    }
+    fence_proxy_async_smem();
+    if (threadIdx.x < 32)
+    {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&slot)), "r"(512u));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = slot;
+    if (threadIdx.x < 32)
+    {
+        const uint32_t idesc =
+            (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t a_addr = smem_u32(sA), b_addr = smem_u32(sB);
+        const uint32_t lbo_b = (uint32_t)n * 16u;
+        long long t0 = 0, t1 = 0;
+        if (elect_one())
+        {
+            t0 = clock64();
+            for (int r = 0; r < rounds; r++)
+            {
+                const uint32_t j = (uint32_t)r & 15u;
+                uint64_t bdesc = (uint64_t)(((b_addr + j * 2 * lbo_b) >> 4) & 0x3FFFu);
+                bdesc |= (uint64_t)((lbo_b >> 4) & 0x3FFFu) << 16;
+                bdesc |= (uint64_t)((T_SBO >> 4) & 0x3FFFu) << 32;
+                bdesc |= 1ull << 46;
+                const uint64_t adesc = umma_desc_lbo<128>(a_addr + j * 2 * (128u * 16u));
+                const uint32_t a_tmem = tmem_base + 384u + j * 8u;
+                for (int c = 0; c < chains; c++)
+                {
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(c * n);
+                    if (a_in_tmem)
+                        asm volatile("{\n\t"
+                                     ".reg .pred p;\n\t"
+                                     "setp.ne.b32 p, %4, 0;\n\t"
+                                     "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t"
+                                     "}\n" ::"r"(d_tmem),
+                                     "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(1u), "r"(0u)
+                                     : "memory");
+                    else
+                        asm volatile("{\n\t"
+                                     ".reg .pred p;\n\t"
+                                     "setp.ne.b32 p, %4, 0;\n\t"
+                                     "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t"
+                                     "}\n" ::"r"(d_tmem),
+                                     "l"(adesc), "l"(bdesc), "r"(idesc), "r"(1u), "r"(0u)
+                                     : "memory");
+                }
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar))
+                         : "memory");
+            wait_or_trap(&bar, 0);
+            t1 = clock64();
+            cycles_out[blockIdx.x] = (unsigned long long)(t1 - t0);
+        }
+        __syncwarp();
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x < 32)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+}
+
 } // namespace
 
 bool k1t_supports(size_t n1, size_t n2)
@@ -1303,7 +1385,8 @@ int k1t_launch(const void *d_q, size_t n1, const void *d_c, size_t n2, ocb_top2 
                void *d_workspace, int sms, cudaStream_t stream)
 {
     // form of the search kernel: 1 = first form (eight epilogue warps, one CTA per (query tile, candidate range)),
-    // 2 / 3 = second form with one / two query tiles per CTA; 0 = the default
+    // 2 / 3 = second form with one / two query tiles per CTA, 4 = third form (query operand in tensor memory);
+    // 0 = the default (the third form)
     int variant = options().k1t_variant;
     if (variant <= 0 || variant > 4)
         variant = K1T_DEFAULT_VARIANT;
@@ -1347,4 +1430,37 @@ int k1t_launch(const void *d_q, size_t n1, const void *d_c, size_t n2, ocb_top2 
     return 0;
 }
 
+int umma_probe(int a_in_tmem, int n, int chains, int rounds, int ctas, double *cycles_per_mma)
+{
+    if (n < 16 || n > 256 || n % 16 || chains < 1 || chains * n > (a_in_tmem ? 384 : 512) || rounds < 1 || ctas < 1 ||
+        !cycles_per_mma)
+        return fail_invalid("umma probe arguments");
+    unsigned long long *d = nullptr;
+    OCB_CUDA(cudaMalloc(&d, sizeof(unsigned long long) * ctas));
+    const size_t smem = 65536 + 131072;
+    cudaError_t e = cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess)
+    {
+        umma_probe_kernel<<<ctas, 128, smem>>>(a_in_tmem, n, chains, rounds, d);
+        e = cudaDeviceSynchronize();
+    }
+    unsigned long long worst = 0;
+    if (e == cudaSuccess)
+    {
+        std::vector<unsigned long long> h(ctas);
+        e = cudaMemcpy(h.data(), d, sizeof(unsigned long long) * ctas, cudaMemcpyDeviceToHost);
+        for (unsigned long long v : h)
+            worst = std::max(worst, v);
+    }
+    cudaFree(d);
+    OCB_CUDA(e);
+    *cycles_per_mma = (double)worst / ((double)rounds * chains);
+    return 0;
+}
+
 } // namespace ocb
+
+extern "C" int ocb_probe_umma(int a_in_tmem, int n, int chains, int rounds, int ctas, double *cycles_per_mma)
+{
+    return ocb::umma_probe(a_in_tmem, n, chains, rounds, ctas, cycles_per_mma);
+}

@@ -165,7 +165,7 @@ def roofline_k1t(rep, out, comparisons="100000000"):
         k["dram_bytes"] += (val(r, "dram__bytes_read.sum") * to_bytes[units[col["dram__bytes_read.sum"]]] +
                             val(r, "dram__bytes_write.sum") * to_bytes[units[col["dram__bytes_write.sum"]]])
         k["rows"].append(r)
-    search = next(k for n, k in kernels.items() if "k1t_top2_kernel" in n)
+    search = next(k for n, k in kernels.items() if re.search(r"k1t\d*_top2_kernel", n))
     steps = search["launches"]
 
     def avg(k, metric):
@@ -182,6 +182,10 @@ def roofline_k1t(rep, out, comparisons="100000000"):
                    "alu_pct_of_peak": avg(search, "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"),
                    "issue_slots_pct": avg(search, "smsp__issue_active.avg.pct_of_peak_sustained_active"),
                    "l2_hit_pct": avg(search, "lts__t_sector_hit_rate.pct"),
+                   "l2_to_sm_bytes": avg(search, "l1tex__m_xbar2l1tex_read_bytes.sum") *
+                   to_bytes[units[col["l1tex__m_xbar2l1tex_read_bytes.sum"]]],
+                   "tensor_core_shared_memory_wavefronts": avg(search, "l1tex__data_pipe_tc_wavefronts_mem_shared.sum"),
+                   "sm_cycles_active": avg(search, "sm__cycles_active.avg"),
                    "warp_instructions": avg(search, "smsp__inst_executed.sum"),
                    "registers_per_thread": avg(search, "launch__registers_per_thread"),
                    "sm_ghz": avg(search, "sm__cycles_elapsed.avg.per_second")}}
