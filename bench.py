@@ -141,7 +141,7 @@ def roofline(achieved, sm_max, held, peak_src, ms_per_step, peaks, running_varia
     return out
 
 
-def tensor_roofline(achieved_gcmp, ms_per_step, peaks, peak_src, sm_max, int_roofline):
+def tensor_roofline(achieved_gcmp, ms_per_step, peaks, peak_src, sm_max, int_roofline, mma_cycles=None):
     """K1T: the search as an exact s8 contraction on the tensor cores. Algorithmic work per comparison = 512 multiply-
     accumulates = 1024 integer operations (SURVEY 8d counts the same comparison as 16 XOR + 16 POPC on the integer
     pipes). Peak = dense s8 rate = 2 x the measured bf16 GEMM rate of MEASURED_PEAKS.json (the tensor pipe runs 8-bit
@@ -165,10 +165,14 @@ def tensor_roofline(achieved_gcmp, ms_per_step, peaks, peak_src, sm_max, int_roo
             "op": "s8 multiply-accumulate = 2 integer operations, accumulated exactly in s32 (tcgen05.mma.kind::i8)",
             "peak_source": f"2 x bf16_tflops ({bf16:.1f}, {peak_src} MEASURED_PEAKS.json, burst): dense 8-bit rate of the "
                            f"tensor pipe",
-            "limiter": "L2 bandwidth at this tile shape: every CTA streams all candidate tiles "
-                       f"({(N1 + 127) // 128} x {N2} x 512 B = {(N1 + 127) // 128 * N2 * 512 / 1e6:.0f} MB per step), then the "
-                       "epilogue's issue slots (DESIGN.md section 3)",
-            "l2_stream_TBps": (N1 + 127) // 128 * N2 * 512 / (ms_per_step * 1e-3) / 1e12,
+            "limiter": "the latency of dependent tcgen05.mma on one accumulator (~150 cycles whatever N is: "
+                       "ocb_probe_umma, `mma_cycles` below) with 256 of the 512 tensor-memory columns holding the query "
+                       "operand: two accumulators of 64 columns per buffer retire an M128 x N64 x K32 MMA every ~64 cycles "
+                       "against 32 of arithmetic; next the L2 -> SM stream (every group of 256 query rows streams all "
+                       f"candidate tiles: {(N1 + 255) // 256} x {N2} x 512 B = {(N1 + 255) // 256 * N2 * 512 / 1e6:.0f} MB per "
+                       "step) and the epilogue's issue slots (DESIGN.md section 3)",
+            "l2_stream_TBps": (N1 + 255) // 256 * N2 * 512 / (ms_per_step * 1e-3) / 1e12,
+            "mma_cycles": mma_cycles,
             "popc_roofline_equivalent": {"achieved": achieved_gcmp, "peak": int_roofline["peak"], "unit": UNIT,
                                          "frac": achieved_gcmp / int_roofline["peak"],
                                          "note": "the same step against the plain XOR+POPC roofline of SURVEY 8d (the "
@@ -548,7 +552,11 @@ def run_ours(args):
     int_roofline = roofline(int_achieved, sm_max, int_clocks.get("sm_mhz") or sm_max, peak_src, int_ms, peaks,
                             capi.get_option("k1_variant"))
     if headline_engine.startswith("tensor"):
-        line["roofline"] = tensor_roofline(achieved, ms_per_step, peaks, peak_src, sm_max, int_roofline)
+        # the tensor pipe measured by itself on this GPU: cycles per M128 x N x K32 s8 MMA (arithmetic: N / 2 cycles)
+        probes = {"a_in_tmem_n64_2acc": (1, 64, 2), "a_in_tmem_n64_4acc": (1, 64, 4), "a_in_tmem_n128_2acc": (1, 128, 2),
+                  "a_in_tmem_n256_1acc": (1, 256, 1), "a_in_smem_n128_2acc": (0, 128, 2), "a_in_smem_n256_1acc": (0, 256, 1)}
+        mma_cycles = {k: round(capi.probe_umma(*v), 1) for k, v in probes.items()}
+        line["roofline"] = tensor_roofline(achieved, ms_per_step, peaks, peak_src, sm_max, int_roofline, mma_cycles)
         line["dtype"] = "s8 x s8 -> s32 (exact)"
     else:
         line["roofline"] = int_roofline
@@ -834,7 +842,8 @@ def main():
     ap.add_argument("--no-secondary", action="store_true")
     ap.add_argument("--no-survey", action="store_true", help="c2: skip the sharded configs[3] survey block")
     ap.add_argument("--no-verify", action="store_true", help="skip the after-the-clock checks of the survey block")
-    ap.add_argument("--callers", type=int, default=4, help="concurrent host callers of the e2e measurement")
+    ap.add_argument("--callers", type=int, default=12,
+                    help="concurrent host callers of the e2e measurement (capped by the host cores of this rank)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -14,7 +14,7 @@ HOST = os.path.join(PKG, "host")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-Wall", "-shared"]
 CUDA_SOURCES = ["hamming_top2.cu", "hamming_lists.cu", "score_models.cu", "fit_models.cu", "link_tail.cu", "hamming_tensor.cu", "pipe_probe.cu", "ocb_capi.cu"]
-HOST_SOURCES = ["linalg.cpp", "models.cpp", "homography_decompose.cpp", "distort_keypoints.cpp", "link_batch.cpp", "partition.cpp", "match_features.cpp", "guided_match.cpp", "ransac.cpp", "graph_wire.cpp", "graph_wire_capi.cpp", "flat_shim.cpp"]
+HOST_SOURCES = ["linalg.cpp", "models.cpp", "homography_decompose.cpp", "distort_keypoints.cpp", "link_batch.cpp", "partition.cpp", "match_features.cpp", "guided_match.cpp", "ransac.cpp", "relax_refit.cpp", "graph_wire.cpp", "graph_wire_capi.cpp", "flat_shim.cpp"]
 
 
 def _newer(target, deps):

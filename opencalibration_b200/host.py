@@ -94,6 +94,8 @@ def lib():
     L.ocbh_link_get.argtypes = [C.c_void_p, sz, _szp, _szp, _f64p, _f64p, C.c_void_p, _f64p, _f64p, _szp]
     L.ocbh_link_get.restype = None
     L.ocbh_ransac_batch.argtypes = [i32, _f64p, _szp, sz, i32, _f64p, _f64p, _u8p, _szp]
+    L.ocbh_refit_evaluate_batch.restype = i32
+    L.ocbh_refit_evaluate_batch.argtypes = [_f64p, _szp, sz, i32, C.c_double, _f64p, _f64p, _u8p]
     L.ocbh_run_parallel_handles.argtypes = [C.c_void_p, C.c_void_p, sz, i32, i32, i32, _szp, _f64p]
     _lib = L
     return L
@@ -437,6 +439,23 @@ def link_pairs(feature_sets, cameras8, pairs, num_sparse=None, threads=0, pairs_
     if not res:
         raise OcbError("host mirror: " + lib().ocbh_last_error().decode())
     return LinkResults(res, len(pr))
+
+
+def refit_evaluate_batch(corr_list, inlier_list, rounds=3, thr=0.0):
+    """The loop of RelaxGroup::finalize (src/relax/relax_group.cpp:156-165) for many edges in lock step:
+    rounds x (homography fitInliers, evaluate) -> list of (score, M18, inliers)."""
+    corr_list = [_corr(c) for c in corr_list]
+    n = len(corr_list)
+    offsets = np.zeros(n + 1, np.uintp)
+    offsets[1:] = np.cumsum([len(c) for c in corr_list])
+    total = int(offsets[-1])
+    allc = np.concatenate(corr_list) if total else np.zeros((0, 7))
+    inl = np.zeros(max(total, 1), np.uint8)
+    for j, f in enumerate(inlier_list):
+        inl[int(offsets[j]):int(offsets[j + 1])] = np.asarray(f, np.uint8)
+    scores, M18 = np.zeros(max(n, 1)), np.full((max(n, 1), 18), np.nan)
+    _check(lib().ocbh_refit_evaluate_batch(np.ascontiguousarray(allc), offsets, n, int(rounds), float(thr), scores, M18, inl))
+    return [(float(scores[j]), M18[j].copy(), inl[int(offsets[j]):int(offsets[j + 1])].astype(bool)) for j in range(n)]
 
 
 def ransac_batch(kind, corr_list, threads=0):

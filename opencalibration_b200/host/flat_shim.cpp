@@ -696,6 +696,38 @@ extern "C"
             order[i] = (uint32_t)ranked[i].idx;
     }
 
+    // refit_evaluate_batch over n_jobs correspondence sets (rows offsets[j] .. offsets[j + 1] of corr); inl: in = the
+    // previous inliers, out = the last evaluate's; M18 [n_jobs][18] out; thr: inlier threshold (<= 0: the model's default)
+    int ocbh_refit_evaluate_batch(const double *corr, const size_t *offsets, size_t n_jobs, int rounds, double thr,
+                                  double *scores, double *M18, uint8_t *inl)
+    {
+        return guarded([&] {
+            std::vector<std::vector<correspondence>> corrs(n_jobs);
+            std::vector<homography_model> models(n_jobs);
+            std::vector<std::vector<bool>> inliers(n_jobs);
+            std::vector<ocb_host::RefitJob> jobs(n_jobs);
+            for (size_t j = 0; j < n_jobs; j++)
+            {
+                const size_t n = offsets[j + 1] - offsets[j];
+                corrs[j] = make_corr(corr + offsets[j] * 7, n);
+                inliers[j].resize(n);
+                for (size_t k = 0; k < n; k++)
+                    inliers[j][k] = inl[offsets[j] + k] != 0;
+                if (thr > 0)
+                    models[j].inlier_threshold = thr;
+                jobs[j].matches = &corrs[j], jobs[j].model = &models[j], jobs[j].inliers = &inliers[j];
+            }
+            ocb_host::refit_evaluate_batch(jobs, rounds);
+            for (size_t j = 0; j < n_jobs; j++)
+            {
+                scores[j] = jobs[j].score;
+                ocb_host::detail::pack_model(models[j], M18 + j * 18);
+                for (size_t k = 0; k < inliers[j].size(); k++)
+                    inl[offsets[j] + k] = inliers[j][k] ? 1 : 0;
+            }
+        });
+    }
+
     int ocbh_ransac_batch(int kind, const double *corr, const size_t *offsets, size_t n_jobs, int threads, double *scores,
                           double *M18, uint8_t *inl, size_t *stats2)
     {

@@ -86,4 +86,19 @@ template <typename Model> struct RansacJob
 using CorrBinder = std::function<void(const std::vector<ocb_corr_set> &)>;
 template <typename Model>
 void ransac_batch(std::vector<RansacJob<Model>> &jobs, int threads = 0, const CorrBinder *binder = nullptr);
+
+// The second caller of homography_model::fitInliers / evaluate, RelaxGroup::finalize (src/relax/relax_group.cpp:
+// 137-177): when the camera models changed, every edge refits its homography from its previous inliers with
+//     for (int i = 0; i < 3; i++) { h.fitInliers(correspondences, inliers); h.evaluate(correspondences, inliers); }
+// refit_evaluate_batch does that for all edges of a batch in lock step -- `rounds` request tables of all-inlier
+// device refits + evaluations (one launch and one copy each way per round) -- and leaves in every job the model, the
+// inlier vector and the last evaluate's score exactly as that loop would.
+struct RefitJob
+{
+    const std::vector<opencalibration::correspondence> *matches = nullptr;
+    opencalibration::homography_model *model = nullptr; // inlier_threshold is read, the matrices are written
+    std::vector<bool> *inliers = nullptr;               // in: the previous inliers; out: the last evaluate's
+    double score = 0;                                   // out: the last evaluate's return value
+};
+void refit_evaluate_batch(std::vector<RefitJob> &jobs, int rounds = 3);
 } // namespace ocb_host

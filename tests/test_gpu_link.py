@@ -96,6 +96,49 @@ def test_link_pairs_rejects_bad_input(gpu, hostlib):
         hostlib.link_pairs(sets, [survey.camera8()] * 2, [(0, 1)], num_sparse=[101, 0])
 
 
+def test_link_pairs_edge_cases(gpu, hostlib, oracle):
+    """Submission sizes around the list length, an empty list, repeated and self pairs, images without features on
+    either side, a failing call between two good ones, and a submission size of one with two submissions in flight:
+    every result equals the per-pair flow and the runner stays usable."""
+    survey = synthetic.PlanarSurvey(2, 3, 600, seed=21)
+    imgs = [survey.image(i) for i in range(survey.n_images)]
+    imgs[5] = tuple(x[:0] for x in imgs[5])  # no features at all
+    cam = survey.camera8()
+    cams = [cam] * survey.n_images
+    sets = [hostlib.FeatureSet(d, xy, s) for d, xy, s in imgs]
+    pairs = survey.pairs + [(1, 1), (0, 1), (0, 1), (5, 0), (0, 5), (5, 5)]
+    want = [expected_pair(oracle, imgs[a], imgs[b], cam) for a, b in pairs]
+
+    def check(res, which):
+        assert res.n_pairs == len(which)
+        for p, k in enumerate(which):
+            check_pair(res.get(p), want[k])
+
+    everything = list(range(len(pairs)))
+    # one submission far larger than the list, exactly the list, one pair per submission (two in flight), and a size
+    # that leaves a ragged last submission
+    for pps in (10_000, len(pairs), 1, len(pairs) - 1):
+        check(hostlib.link_pairs(sets, cams, pairs, threads=3, pairs_per_submission=pps), everything)
+    # an empty pair list is a valid call
+    empty = hostlib.link_pairs(sets, cams, [], threads=2)
+    assert empty.n_pairs == 0 and empty.stats["comparisons"] == 0
+    # a single pair, a single worker thread
+    check(hostlib.link_pairs(sets, cams, pairs[:1], threads=1, pairs_per_submission=1), [0])
+    # a rejected call (index out of range in the middle of the list) leaves nothing behind: the next call is complete
+    bad = list(pairs)
+    bad[len(bad) // 2] = (0, 99)
+    with pytest.raises(hostlib.OcbError):
+        hostlib.link_pairs(sets, cams, bad, threads=3, pairs_per_submission=2)
+    check(hostlib.link_pairs(sets, cams, pairs, threads=3, pairs_per_submission=2), everything)
+    # matches only (no RANSAC): images without features give empty lists, repeated pairs equal lists
+    res = hostlib.link_pairs(sets, cams, pairs, run_ransac=False, pairs_per_submission=3)
+    for p in range(len(pairs)):
+        got, exp = res.get(p), want[p]
+        assert np.array_equal(got["matches"][0], exp["matches"][0]) and np.array_equal(got["matches"][1], exp["matches"][1])
+        assert np.array_equal(got["matches"][2], exp["matches"][2])
+    assert len(res.get(len(pairs) - 1)["matches"][0]) == 0 and len(res.get(len(pairs) - 3)["matches"][0]) == 0
+
+
 def test_c4_survey_slice_equals_the_reference_object_code(gpu, hostlib):
     """BASELINE configs[3] at full image size: >= 200 directed pairs of the 25 x 40 survey, 8192 features per image,
     through the batched runner; EVERY pair's match list (indices, distances, order) against the reference's own
