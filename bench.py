@@ -476,7 +476,8 @@ def run_ours(args):
     e2e_single_ms = float(e2e_s.item()) * 1e3 / e2e_steps
     callers = max(1, min(args.callers, (os.cpu_count() or 1) // max(world, 1)))
     host.run_parallel_handles([fa] * callers, [fb] * callers, threads=callers, cross_check=True, reps=2)
-    conc_steps = max(callers * 2, min(args.steps, 200) // callers * callers)
+    # every caller makes at least eight calls (with two the start-up of the workers is a third of the region)
+    conc_steps = callers * max(8, min(args.steps, 200) // callers)
     barrier()
     conc_secs, _ = host.run_parallel_handles([fa] * callers, [fb] * callers, threads=callers, cross_check=True,
                                              reps=conc_steps // callers)

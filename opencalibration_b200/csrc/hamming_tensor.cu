@@ -11,27 +11,31 @@
 // floating-point contraction"; measured on B200 the integer form peaks at 410 - 460 Gcmp/s, this
 // one runs the 10k x 10k pair at > 1000 Gcmp/s with identical results, so it is the engine for large single pairs.
 //
-// Data flow
-//   k1t_expand_kernel  64-byte rows -> s8 tiles of 128 rows in the K-major, no-swizzle canonical layout of a UMMA
-//                      shared-memory descriptor: [K chunk of 16 B][row][16 B] (core matrix = 8 rows x 16 B contiguous;
-//                      SBO = 128 B between 8-row groups, LBO = 2048 B between K chunks). A tile is 64 KB and arrives in
-//                      shared memory with ONE bulk copy.
-//   k1t_top2_kernel    CTA = (query tile of 128 rows, contiguous range of candidate tiles), 10 warps:
-//                        warp 0    producer: bulk copies (cp.async.bulk + mbarrier) of the query tile, then of the
-//                                  candidate tiles through a two-stage ring;
-//                        warp 1    one thread issues, per candidate tile, 16 x tcgen05.mma (M 128 x N 128 x K 32) into
-//                                  one of two 128-column TMEM accumulators and commits them to mbarriers (stage free,
-//                                  accumulator full);
-//                        warps 2-9 epilogue (two per TMEM lane quarter, one column half each): tcgen05.ld 32 columns
-//                                  at a time (thread = query row), one IMAD turns the dot product into
-//                                  v = distance << 20 | position, then K1's branch-free two-smallest update.
-//                                  Cross-check: per candidate the warp maximum (REDUX) of (dot + 513) << 8 | (127 - row),
-//                                  combined over the quarters through shared memory, one 64-bit atomic max per
-//                                  candidate and CTA on the complemented (distance, query) key, as in K1.
-//   k1t_finish_kernel  merges the candidate ranges of every query (positions are global, so packed values merge by
-//                      min / max), writes the records and turns the column keys into query indices.
-// Bound: L2 bandwidth at this tile shape (every CTA streams the candidate tiles: n1 / 128 x n2 x 512 B), then the
-// epilogue's issue slots; the tensor pipe itself is about one third busy.
+// Data flow (three launches per call: expansion, search, finish)
+//   expansion   64-byte candidate rows -> s8 tiles in the K-major, no-swizzle canonical layout of a UMMA shared-memory
+//               descriptor: [K chunk of 16 B][row][16 B] (core matrix = 8 rows x 16 B contiguous; SBO = 128 B between
+//               8-row groups, LBO = rows x 16 B between K chunks); a tile arrives in shared memory with ONE bulk copy.
+//   search      persistent CTAs, warp-specialised: a bulk-copy producer (cp.async.bulk + mbarrier), one MMA-issuing warp
+//               (tcgen05.mma.kind::i8 into TMEM accumulators, tcgen05.commit to mbarriers), 8 or 16 epilogue warps
+//               (tcgen05.ld, thread = query row: packed keys, branch-free two-smallest), a cross-check flush warp.
+//   finish      merges the partial pairs of the CTAs that worked on a query row, writes the records and turns the
+//               column keys into query indices.
+// Four forms of the search kernel are kept (option k1t_variant; every test of tests/test_gpu_match.py runs on each):
+//   1  first form    CTA = (128-query tile, candidate range), A and B from shared memory, 8 epilogue warps.
+//   2  second form   16 epilogue warps, persistent spans over the linearised (query tile, candidate step) space, MMAs
+//                    issued by an ELECTED lane of a warp-uniform loop (under `lane == 0` ptxas wraps every tcgen05.mma in
+//                    an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall: ~110 cycles of issue per MMA), 16-bit cross-check
+//                    keys handed to a flush warp through mbarriers instead of a CTA-wide barrier per step.
+//   3                the same with two query tiles per CTA against steps of 64 candidates (half the L2 stream; slower:
+//                    an A read from shared memory costs 32 wavefronts per MMA whatever N is).
+//   4  third form    DEFAULT: the query operand lives in TENSOR MEMORY (tcgen05.mma with A from TMEM): the epilogue
+//                    warps expand their own query rows in registers and tcgen05.st them, two query tiles per CTA, the
+//                    227 KB of shared memory are a six-stage ring of candidate steps, top-2 on packed 16-bit keys
+//                    (VIMNMX.U16x2 / VIMNMX3.U16x2).
+// What bounds it (ocb_probe_umma, include/ocb_probe.h): an accumulator accepts a dependent MMA
+// only every ~150 cycles whatever N is, and 256 of the 512 TMEM columns hold A, so two accumulators of 64 columns are in
+// flight per buffer: an M 128 x N 64 x K 32 MMA retires every ~64 cycles against 32 of arithmetic -- half the tensor pipe.
+// The full rate needs N = 256 per MMA, i.e. a CTA pair (cta_group::2); not built.
 #include "ocb_internal.cuh"
 
 #include <algorithm>
@@ -799,20 +803,25 @@ __global__ void __launch_bounds__(256)
         const uint32_t first = (qb * c_steps) / per, last = ((qb + 1) * c_steps - 1) / per;
         const uint32_t slots = (last - first + 1) * bpm;
         uint32_t s1 = T_NONE, s2 = T_NONE;
-        for (uint32_t s0 = 0; s0 < slots; s0 += 8) // eight independent loads in flight (the kernel is pure latency)
+        // The kernel is pure latency: eight loads in flight per thread. (Written as volatile loads from clamped, always
+        // valid addresses: left to itself ptxas issues one load, consumes it, issues the next -- ten L2 round trips.)
+        for (uint32_t s0 = 0; s0 < slots; s0 += 8)
         {
             uint2 p[8];
 #pragma unroll
             for (uint32_t k = 0; k < 8; k++)
-                p[k] = s0 + k < slots ? *reinterpret_cast<const uint2 *>(part + ((size_t)(s0 + k) * n1_padded + g) * 2)
-                                      : make_uint2(T_NONE, T_NONE);
+            {
+                const uint32_t *src = part + ((size_t)min(s0 + k, slots - 1u) * n1_padded + g) * 2;
+                asm volatile("ld.global.v2.u32 {%0, %1}, [%2];" : "=r"(p[k].x), "=r"(p[k].y) : "l"(src));
+            }
 #pragma unroll
             for (uint32_t k = 0; k < 8; k++)
             {
-                s2 = min(s2, max(s1, p[k].x));
-                s1 = min(s1, p[k].x);
-                s2 = min(s2, max(s1, p[k].y));
-                s1 = min(s1, p[k].y);
+                const uint32_t a = s0 + k < slots ? p[k].x : T_NONE, b = s0 + k < slots ? p[k].y : T_NONE;
+                s2 = min(s2, max(s1, a));
+                s1 = min(s1, a);
+                s2 = min(s2, max(s1, b));
+                s1 = min(s1, b);
             }
         }
         ocb_top2 r;

@@ -21,8 +21,11 @@ def edges(oracle, n_edges):
         corr, _ = oracle.scene_homography(n_in, n_out, 100 + e)
         _, _, inl, _ = oracle.ransac(H, corr)
         inl = inl.copy()
-        if e % 3 == 1:  # the camera model changed: some old inliers are wrong now, some outliers are flagged
-            flip = rng.choice(len(inl), len(inl) // 10, replace=False)
+        if e % 3 == 1:  # the camera model changed: a tenth of the old inliers is lost (evaluate brings them back)
+            drop = rng.choice(np.flatnonzero(inl), int(inl.sum()) // 10, replace=False)
+            inl[drop] = False
+        if e == 7:  # ... and here outliers are flagged as inliers: the least-squares refit is ruined, evaluate finds
+            flip = rng.choice(len(inl), len(inl) // 10, replace=False)  # nothing and the next refit sees no inlier
             inl[flip] = ~inl[flip]
         if e % 5 == 4:  # only a handful of old inliers
             keep = np.flatnonzero(inl)[:6]
@@ -47,12 +50,14 @@ def test_batched_refit_equals_the_per_edge_loop(gpu, hostlib, oracle):
     E = edges(oracle, 9)
     got = hostlib.refit_evaluate_batch([c for c, _ in E], [i for _, i in E], rounds=3)
     assert len(got) == len(E)
+    good = 0
     for (corr, inl), (score, M, new_inl) in zip(E[:-1], got[:-1]):
         s_m, M_m, i_m = per_edge_loop(hostlib.fit_inliers, hostlib.evaluate, corr, inl)
-        assert score == s_m and np.array_equal(M, M_m) and np.array_equal(new_inl, i_m)
+        assert score == s_m and np.array_equal(M, M_m, equal_nan=True) and np.array_equal(new_inl, i_m)
         s_o, M_o, i_o = per_edge_loop(oracle.fit_inliers, oracle.evaluate, corr, inl)
-        assert score == s_o and np.array_equal(M, M_o) and np.array_equal(new_inl, i_o)
-        assert new_inl.sum() >= 4 and score > 0
+        assert score == s_o and np.array_equal(M, M_o, equal_nan=True) and np.array_equal(new_inl, i_o)
+        good += bool(new_inl.sum() >= 4 and score > 0)
+    assert good == len(E) - 2  # every edge but the ruined one (and the empty one) ends with a supported homography
     score, M, new_inl = got[-1]
     assert score == 0 and len(new_inl) == 0
 
@@ -62,13 +67,13 @@ def test_batched_refit_rounds_and_threshold(gpu, hostlib, oracle):
     _, _, inl, _ = oracle.ransac(H, corr)
     one = hostlib.refit_evaluate_batch([corr], [inl], rounds=1)[0]
     s, M, i = per_edge_loop(hostlib.fit_inliers, hostlib.evaluate, corr, inl, rounds=1)
-    assert one[0] == s and np.array_equal(one[1], M) and np.array_equal(one[2], i)
+    assert one[0] == s and np.array_equal(one[1], M, equal_nan=True) and np.array_equal(one[2], i)
     tight = hostlib.refit_evaluate_batch([corr], [inl], rounds=2, thr=0.001)[0]
     M2 = hostlib.fit_inliers(H, np.full(18, np.nan), corr, inl)
     s2, i2 = hostlib.evaluate(H, M2, corr, thr=0.001)
     M2 = hostlib.fit_inliers(H, M2, corr, i2)
     s2, i2 = hostlib.evaluate(H, M2, corr, thr=0.001)
-    assert tight[0] == s2 and np.array_equal(tight[1], M2) and np.array_equal(tight[2], i2)
+    assert tight[0] == s2 and np.array_equal(tight[1], M2, equal_nan=True) and np.array_equal(tight[2], i2)
     assert tight[2].sum() <= one[2].sum()
     with pytest.raises(Exception):
         hostlib.refit_evaluate_batch([corr], [inl[:-1]])
