@@ -796,6 +796,9 @@ __global__ void __launch_bounds__(256)
                        const unsigned long long *__restrict__ col64, uint32_t n2, uint32_t *__restrict__ col_out)
 {
     const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long column_key = 0ull; // asked for first: its round trip overlaps the ones of the partial pairs
+    if (col_out && g < n2)
+        asm volatile("ld.global.u64 %0, [%1];" : "=l"(column_key) : "l"(col64 + g));
     if (g < n1)
     {
         // the CTAs whose spans touch this row's query tile group each left bpm partial pairs
@@ -831,7 +834,7 @@ __global__ void __launch_bounds__(256)
         out[g] = r;
     }
     if (col_out && g < n2)
-        col_out[g] = (uint32_t)(~col64[g]); // zero (nothing seen) -> OCB_NO_INDEX
+        col_out[g] = (uint32_t)(~column_key); // zero (nothing seen) -> OCB_NO_INDEX
 }
 
 
@@ -869,7 +872,8 @@ template <bool COL> __global__ void __launch_bounds__(V_THREADS, 1) k1t4_top2_ke
              *b_full = bars + 10, *b_empty = bars + 10 + W_STAGES;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 10 + 2 * W_STAGES);
     static_assert((10 + 2 * W_STAGES + 1) * 8 <= V_BAR_BYTES, "barrier block");
-    uint16_t *colmin = reinterpret_cast<uint16_t *>(k1t4_smem + W_STAGES * W_B_BYTES + V_BAR_BYTES);
+    // cross-check keys of a step, [2 buffers][8 row groups][64 candidates] (32-bit words: four keys per 16-byte store)
+    uint32_t *colmin = reinterpret_cast<uint32_t *>(k1t4_smem + W_STAGES * W_B_BYTES + V_BAR_BYTES);
 
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t l_begin = blockIdx.x * P.per;
@@ -993,7 +997,7 @@ template <bool COL> __global__ void __launch_bounds__(V_THREADS, 1) k1t4_top2_ke
                 {
                     const uint32_t b = t & 1;
                     wait_or_trap(&c_full[b], (t >> 1) & 1);
-                    const uint16_t *cm = colmin + b * (G * W_NT);
+                    const uint32_t *cm = colmin + b * (G * W_NT);
                     uint32_t best[W_NT / 32];
 #pragma unroll
                     for (uint32_t k = 0; k < W_NT / 32; k++)
@@ -1112,7 +1116,7 @@ template <bool COL> __global__ void __launch_bounds__(V_THREADS, 1) k1t4_top2_ke
                 __syncwarp();
                 if (lane == 0)
                     mbar_arrive(&d_empty[buf]);
-                uint16_t *cm = colmin + (t & 1u) * (G * W_NT) + g * W_NT + cblk * 32u;
+                uint32_t *cm = colmin + (t & 1u) * (G * W_NT) + g * W_NT + cblk * 32u;
                 if constexpr (COL)
                     if (t >= 2)
                         wait_or_trap(&c_empty[t & 1], ((t >> 1) - 1) & 1);
@@ -1141,13 +1145,13 @@ template <bool COL> __global__ void __launch_bounds__(V_THREADS, 1) k1t4_top2_ke
                     b1 = __vminu2(b1, lo);
                     if constexpr (COL)
                     {
-                        // the warp's best (distance, row) for the candidates pos0 + i .. i + 3: four 16-bit keys, one
-                        // store (every lane stores the same words: the values stay in uniform registers)
+                        // the warp's best (distance, row) for the candidates pos0 + i .. i + 3: four keys, one 16-byte
+                        // store (every lane stores the same words)
                         uint32_t m[4];
 #pragma unroll
                         for (int k = 0; k < 4; k++)
                             m[k] = __reduce_max_sync(0xFFFFFFFFu, d[i + k] * key_mul + key_add);
-                        *reinterpret_cast<uint2 *>(cm + i) = make_uint2(m[0] | (m[1] << 16), m[2] | (m[3] << 16));
+                        *reinterpret_cast<uint4 *>(cm + i) = make_uint4(m[0], m[1], m[2], m[3]);
                     }
                 }
                 if constexpr (COL)
@@ -1237,7 +1241,7 @@ int k1t2_run(const K1T2Params &P, const K1T2Layout &L, cudaStream_t stream)
 
 template <bool COL> int k1t4_run(const K1T4Params &P, uint32_t ctas, cudaStream_t stream)
 {
-    constexpr size_t smem = (size_t)W_STAGES * W_B_BYTES + V_BAR_BYTES + V_COLMIN_BYTES;
+    constexpr size_t smem = (size_t)W_STAGES * W_B_BYTES + V_BAR_BYTES + 2 * V_COLMIN_BYTES;
     static_assert(smem <= 232448, "227 KB of dynamic shared memory per CTA");
     OCB_CUDA(cudaFuncSetAttribute(k1t4_top2_kernel<COL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k1t4_top2_kernel<COL><<<ctas, V_THREADS, smem, stream>>>(P);
