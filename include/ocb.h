@@ -115,6 +115,9 @@ extern "C"
      *   "k1_bf_rows"       runs shorter than this use the branch-free update when k1_update == 0
      *   "k1_engine"        single-pair search: 0 = by size (tensor cores from 512 x 512 rows up), 1 = integer pipes
      *                      (K1: XOR + POPC), 2 = tensor cores (K1T: exact s8 contraction, tcgen05.mma)
+     *   "k1t_variant"      form of K1T's search kernel: 0 = default (4), 1 = first form, 2 / 3 = second form with one /
+     *                      two query tiles per CTA (operands from shared memory), 4 = third form (query operand in
+     *                      tensor memory)
      *   "k2_variant"       0 = by size, 1 = one hypothesis group per CTA, 2 = four groups per CTA in lock-step
      *   "k2_hg"            hypotheses per group (1..8); 0 = balance the SMs */
     int ocb_set_option(const char *key, int64_t value);
