@@ -4,15 +4,22 @@
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2]
 
 Workload at every N = BASELINE.json configs[1]: one synthetic pair of 10 000 x 10 000 512-bit descriptors per GPU,
-top-2 search + ratio test + cross-check. One "step" = one pass of the hot path over that pair: ONE K1 launch computes
-the n1 x n2 row comparisons once and derives from them both the per-query top-2 (ratio test) and the per-candidate
-best query (cross-check). Ranks are independent (pairs shard embarrassingly; no data-path collective): weak scaling,
-value = comparisons of all ranks / max-over-ranks device time.
+top-2 search + ratio test + cross-check. One "step" = one pass of the hot path over that pair through
+ocb_match_top2_device: the n1 x n2 row comparisons are computed once and give both the per-query top-2 (ratio test)
+and the per-candidate best query (cross-check). The library picks the engine by size: for this pair the tensor-core
+engine (K1T: expansion, search and finish kernels - `value`, `roofline`); the same step on the integer-pipe engine that
+north_star specifies (K1: one fused kernel) is timed in the same run (`integer_pipe_engine`, with its own roofline).
+Ranks are independent (pairs shard embarrassingly; no data-path collective): weak scaling, value = comparisons of all
+ranks / max-over-ranks device time. `secondary` carries configs[2] (MSAC scoring), the dense-stage guided matcher and,
+at every N, the sharded configs[3] survey (`c4_survey`: Hilbert partition of the overlap graph, host gather of the match
+lists inside its timed region, strong scaling against the single-GPU rate measured in the same job).
 
   value  device-resident: descriptors already in HBM, CUDA events on the launching stream around each step, the L2
          flushed (256 MiB write) between timed steps;
   e2e    the same step through the reference-facing C++ entry point (match_features_subset on std::vector<feature_2d>
-         held on the host + cross-check flags): row packing, H2D, kernels, D2H, double ratio test, std::sort - wall clock;
+         held on the host + cross-check flags): row packing, H2D, kernels, D2H, double ratio test, std::sort - wall clock,
+         `--callers` concurrent OpenMP callers (the reference's run_parallel executes one closure per pair on all its
+         workers), at least eight calls each; the single caller is reported next to it;
   cpu_baseline / --impl reference: the reference's own match_features.cpp object code (oracle/_ref, -mpopcnt build;
          the as-shipped build is reported next to it) under the reference's OpenMP-over-pairs driver on the box's host cores.
 """
